@@ -1,0 +1,148 @@
+/*
+ * snk_b200.h -- C ABI of the B200-native unit-selection search engine.
+ *
+ * The reference (CSTR-Edinburgh/snickery) has no FFI: its seam for this path is a
+ * set of Python calls on scipy/sklearn KD-trees, numpy and OpenFst objects
+ * (SURVEY.md section 8b).  Each entry point below names the reference call site it
+ * replaces (paths under /root/reference/script/).  INTEGRATION.md shows the ctypes
+ * stub a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; snk_last_error()
+ *    returns a thread-local, NUL-terminated description of the last failure.
+ *  - no exceptions cross the ABI; no torch types appear in signatures.
+ *  - "host" entry points take plain host pointers (pageable or pinned), perform
+ *    H2D / D2H copies themselves and return when results are in host memory.
+ *  - "_dev" entry points take device pointers on the handle's device and enqueue
+ *    on the given cudaStream_t (passed as void*); they do not synchronise.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point
+ *    fails with an error.
+ *  - a handle is not thread-safe; different handles may be used from different
+ *    threads.  A handle must not be shared across fork().
+ */
+#ifndef SNK_B200_H
+#define SNK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct snk_db snk_db;
+
+/* join-context layouts (what prev_join_rep / current_join_rep mean for greedy search) */
+#define SNK_LAYOUT_SIMPLE 0u      /* synth_simple.py:194-195,213-214: prev=start[u]=Jw[u], cur=end[u+m-1]=Jw[u+m]          */
+#define SNK_LAYOUT_HALFPHONE_EPOCH 1u /* synth_halfphone.py:552-553,580-581: prev=Jw[u][:Dj/2], cur=Jw[u+m-1][Dj/2:]        */
+
+/* search spaces for snk_knn */
+#define SNK_SPACE_TARGET 0 /* rows = weighted train_unit_features [N, Dt]      (synth_halfphone.py:379,1364) */
+#define SNK_SPACE_JOINT 1  /* rows = [prev_join_rep || multiepoch window] [N', Djq+m*Dt] (synth_simple.py:224-229) */
+
+/* shortlist engines (SNK_ENGINE_AUTO picks the tensor-core kernel when shapes allow) */
+#define SNK_ENGINE_AUTO 0
+#define SNK_ENGINE_SIMT 1 /* fp32 direct-difference distances on CUDA cores + top-k scan              */
+#define SNK_ENGINE_TC 2   /* fp16 tcgen05 distance GEMM with fused per-query top-k in the epilogue    */
+
+const char *snk_last_error(void);
+int snk_version(void);
+/* number of visible CUDA devices (0 if none; never an error) */
+int snk_device_count(void);
+
+/* ---- database lifetime ---------------------------------------------------------------
+ * Replaces: Synthesiser.__init__ array loads (synth_simple.py:76-106) + the cKDTree
+ * constructors (synth_simple.py:229; synth_halfphone.py:379,605).  F and Jc are the
+ * standardised, UNWEIGHTED float32 arrays exactly as stored in the voice HDF5
+ * (train_simple.py:137,142,278-289): F [N, Dt], Jc [N+1, Dj].  They are copied.      */
+int snk_db_create(snk_db **out, int device_id, int64_t N, int Dt, int Dj, int multiepoch,
+                  const float *F, const float *Jc, unsigned layout_flags);
+int snk_db_destroy(snk_db *db);
+int snk_db_info(const snk_db *db, int64_t *N, int64_t *Nprime, int *Dt, int *Dj, int *multiepoch,
+                int *joint_dim);
+/* Replaces set_target_weights + set_join_weights + get_tree_for_greedy_search
+ * (synth_simple.py:234-274,190-230): per-coefficient float64 weight vectors wt [Dt],
+ * wj [Dj].  No tree is built: the "index" is the weighted matrices themselves.       */
+int snk_db_set_weights(snk_db *db, const double *wt, const double *wj);
+/* choose the shortlist engine for subsequent searches (default AUTO) */
+int snk_db_set_engine(snk_db *db, int engine);
+/* counters since creation: [0] queries searched, [1] queries whose tensor-core shortlist
+ * failed the exactness certificate and were re-searched with the SIMT engine,
+ * [2] kernels launched, [3] reserved */
+int snk_db_counters(const snk_db *db, int64_t counters[4], int reset);
+
+/* ---- k-NN: tree.query(X, k) ------------------------------------------------------------
+ * Replaces cKDTree.query / sklearn KDTree.query (synth_halfphone.py:1364,1384;
+ * synth_simple.py:490; StashableKDTree.py).  Q is float64 [nq, D] already weighted like
+ * the reference's queries.  Outputs: Euclidean (sqrt) float64 distances ascending and
+ * int64 row ids, [nq, k].  If k exceeds the number of rows the tail is (inf, nrows) as
+ * scipy does.  Ties: lowest row id first.                                              */
+int snk_knn(snk_db *db, int space, const double *Q, int64_t nq, int k, double *dist, int64_t *idx);
+int snk_knn_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist,
+                int64_t *d_idx, int64_t id_offset, void *stream);
+/* k-way merge of R per-shard results [R, nq, k] (ascending) into [nq, k]; used after the
+ * NCCL all-gather of the sharded-database search.               */
+int snk_topk_merge_dev(int device_id, const double *d_dist_all, const int64_t *d_idx_all, int R,
+                       int64_t nq, int k, double *d_dist, int64_t *d_idx, void *stream);
+
+/* ---- greedy joint search ------------------------------------------------------------------
+ * Replaces Synthesiser.greedy_joint_search (synth_simple.py:458-503;
+ * synth_halfphone.py:1900-1945) for a batch of B utterances.  targets: float64, the
+ * utterances' weighted unit_features [T_b, Dt] concatenated; lens[b] = T_b;
+ * start_state[b] = -1 or a unit id (may be NULL = all -1).  Outputs: paths, the
+ * T_b // multiepoch selected row ids per utterance concatenated; step_dist (optional,
+ * may be NULL) the joint Euclidean distance of each step.                              */
+int snk_greedy_batch(snk_db *db, const double *targets, const int64_t *lens, int B,
+                     const int64_t *start_state, int64_t *paths, double *step_dist);
+/* device variant: d_targets as above in device memory; lens / start_state are HOST arrays
+ * (they only size the launch); outputs in device memory.                               */
+int snk_greedy_batch_dev(snk_db *db, const double *d_targets, const int64_t *lens, int B,
+                         const int64_t *start_state, int64_t *d_paths, double *d_step_dist,
+                         void *stream);
+
+/* ---- candidate target distances --------------------------------------------------------
+ * Replaces the distance half of preselect_units_quinphone (synth_halfphone.py:1346-1351):
+ * dist[t,j] = || Fw[cand[t,j]] - targets[t] ||_2 ; cand == -1 indexes the last unit as
+ * numpy does.  cand int64 [T,K], targets float64 [T,Dt], dist float64 [T,K].           */
+int snk_candidate_distances(snk_db *db, const int64_t *cand, const double *targets, int64_t T, int K,
+                            double *dist);
+
+/* ---- join-cost tiles ------------------------------------------------------------------------
+ * Replaces get_natural_distance_vectorised over the pair lists of
+ * make_on_the_fly_join_lattice_BLOCK_DIRECT (synth_halfphone.py:2942-2951,3206-3301):
+ * for each utterance b and step t < T_b-1 the K x K tile
+ *   tile[a][c] = || end[cand[t,a]] - start[cand[t+1,c]] ||_2   (float32)
+ * with +inf where either unit is inadmissible (-1, < 1, >= N-1: :3238-3268).
+ * tiles: float32 [sum_b (T_b - 1), K, K].                                               */
+int snk_join_tiles(snk_db *db, const int64_t *cand, const int64_t *lens, int B, int K, float *tiles);
+
+/* ---- join + Viterbi --------------------------------------------------------------------------
+ * Replaces Synthesiser.viterbi_search (synth_halfphone.py:1399-1436) =
+ * make_target_sausage_lattice + join lattice + compose + shortestpath
+ * (fst_functions_wrapped.py:28-58,172-217,368,387-408) for B utterances.
+ * cand int64 [sum T_b, K] (-1 padded), tdist float64 [sum T_b, K].
+ * paths int64 [sum T_b]: unit ids; when an utterance has no admissible path
+ * (T_b < 2, or every path blocked) path_len[b] = 0 as the reference returns [].
+ * path_cost[b]: float32-accumulated cost in OpenFst's arc order, widened to double;
+ * tcost / jcost (optional, may be NULL): float64 sums of the target and join parts.
+ * flags: bit 0 = greedy over candidates (beam 1: keep only the best state per step).    */
+int snk_join_viterbi_batch(snk_db *db, const int64_t *cand, const double *tdist, const int64_t *lens,
+                           int B, int K, unsigned flags, int64_t *paths, int64_t *path_len,
+                           double *path_cost, double *tcost, double *jcost);
+int snk_join_viterbi_batch_dev(snk_db *db, const int64_t *d_cand, const double *d_tdist,
+                               const int64_t *lens, int B, int K, unsigned flags, int64_t *d_paths,
+                               int64_t *d_path_len, double *d_path_cost, double *d_tcost,
+                               double *d_jcost, void *stream);
+
+/* ---- per-stream cost report ------------------------------------------------------------------
+ * Replaces get_target_scores_per_stream / get_join_scores_per_stream
+ * (synth_halfphone.py:1964-1981,2977-3008) for one greedy path: squared-error sums per
+ * stream.  stream widths are given as arrays; tscores [P, n_tstreams], jscores
+ * [P-1, n_jstreams] (float64).  targets: the utterance's weighted unit_features [T, Dt]. */
+int snk_greedy_path_scores(snk_db *db, const double *targets, int64_t T, const int64_t *path,
+                           int64_t P, const int *twidths, int n_tstreams, const int *jwidths,
+                           int n_jstreams, double *tscores, double *jscores);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNK_B200_H */

@@ -1,0 +1,361 @@
+// C ABI of the engine (include/snk_b200.h): handle lifetime and the host-pointer entry points.
+#include "common.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+
+int snk_join_tiles_dev(snk_db *db, const int64_t *d_cand, const int64_t *lens, int B, int K, float *d_tiles,
+                       cudaStream_t st);
+int snk_candidate_distances_dev(snk_db *db, const int64_t *d_cand, const double *d_targets, int64_t T, int K,
+                                double *d_dist, cudaStream_t st);
+int snk_path_scores_dev(snk_db *db, const double *d_targets, int64_t T, const int64_t *d_path, int64_t P,
+                        const int *d_tw, int nts, const int *d_jw, int njs, double *d_ts, double *d_js,
+                        cudaStream_t st);
+
+static thread_local char g_err[1024] = "";
+
+void snk_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int snk_buf_reserve(snk_buf *b, size_t bytes) {
+    if (bytes <= b->cap) return 0;
+    if (b->p) {
+        SNK_CUDA(cudaFree(b->p));
+        b->p = nullptr;
+        b->cap = 0;
+    }
+    const size_t want = bytes + bytes / 4 + 256;
+    SNK_CUDA(cudaMalloc(&b->p, want));
+    b->cap = want;
+    return 0;
+}
+void snk_buf_free(snk_buf *b) {
+    if (b->p) cudaFree(b->p);
+    b->p = nullptr;
+    b->cap = 0;
+}
+
+extern "C" {
+
+const char *snk_last_error(void) { return g_err; }
+int snk_version(void) { return 100; }
+
+int snk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int snk_db_create(snk_db **out, int device_id, int64_t N, int Dt, int Dj, int multiepoch, const float *F,
+                  const float *Jc, unsigned layout_flags) {
+    SNK_CHECK(out, "out is NULL");
+    *out = nullptr;
+    SNK_CHECK(F && Jc, "F / Jc is NULL");
+    SNK_CHECK(N >= 1 && Dt >= 1 && Dj >= 1, "bad database shape N=%lld Dt=%d Dj=%d", (long long)N, Dt, Dj);
+    SNK_CHECK(N < (int64_t)2000000000, "N too large for 32-bit row ids");
+    SNK_CHECK(multiepoch >= 1, "multiepoch must be >= 1");
+    SNK_CHECK(layout_flags == SNK_LAYOUT_SIMPLE || layout_flags == SNK_LAYOUT_HALFPHONE_EPOCH, "unknown layout flag %u",
+              layout_flags);
+    SNK_CHECK(snk_device_count() > 0, "no CUDA device visible: this engine has no CPU fallback");
+    SNK_CUDA(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    SNK_CUDA(cudaGetDeviceProperties(&prop, device_id));
+    SNK_CHECK(prop.major == 10, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device_id,
+              prop.major, prop.minor);
+    snk_db *db = new snk_db();
+    db->device = device_id;
+    db->sm_count = prop.multiProcessorCount;
+    db->N = N; db->Dt = Dt; db->Dj = Dj; db->m = multiepoch; db->layout = layout_flags;
+    db->Np = N - (multiepoch - 1);
+    if (db->Np < 0) db->Np = 0;
+    if (layout_flags == SNK_LAYOUT_SIMPLE) {
+        // prev_join_rep[u] = start[u] = Jw[u];  current_join_rep[u] = end[u + m - 1] = Jw[u + m]
+        db->Djq = Dj; db->prev_row_off = 0; db->prev_col = 0; db->cur_row_off = multiepoch; db->cur_col = 0;
+    } else {
+        // prev = start[u][:Dj/2] = Jw[u][:h];  current = start[u + m - 1][h:]
+        SNK_CHECK(Dj % 2 == 0, "halfphone-epoch layout needs an even join dimension");
+        db->Djq = Dj / 2; db->prev_row_off = 0; db->prev_col = 0; db->cur_row_off = multiepoch - 1; db->cur_col = Dj / 2;
+    }
+    db->ldJ32 = (int)snk_round_up(Dj, 4);
+    db->ldG16 = (int)snk_round_up(Dt, 64);
+    db->ldS16 = (int)snk_round_up(db->Djq, 64);
+#define ALLOC(ptr, bytes)                                                                      \
+    if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) {                                 \
+        snk_set_error("cudaMalloc of %zu bytes failed: %s", (size_t)(bytes), cudaGetErrorString(cudaGetLastError())); \
+        snk_db_destroy(db);                                                                    \
+        return 1;                                                                              \
+    }
+    ALLOC(db->F_raw, (size_t)N * Dt * 4);
+    ALLOC(db->Jc_raw, (size_t)(N + 1) * Dj * 4);
+    ALLOC(db->wt, (size_t)Dt * 8);
+    ALLOC(db->wj, (size_t)Dj * 8);
+    ALLOC(db->Fw32, (size_t)N * Dt * 4);
+    ALLOC(db->Jw32, (size_t)(N + 1) * db->ldJ32 * 4);
+    ALLOC(db->G16, (size_t)N * db->ldG16 * 2);
+    ALLOC(db->S16, (size_t)(N + 1) * db->ldS16 * 2);
+    ALLOC(db->nrm_t16, (size_t)N * 4);
+    ALLOC(db->nrm_j16, (size_t)(db->Np > 0 ? db->Np : 1) * 4);
+    ALLOC(db->err_t16, 256);
+    db->err_j16 = db->err_t16 + 1;
+    db->maxn_t16 = db->err_t16 + 2;
+    db->maxn_j16 = db->err_t16 + 3;
+#undef ALLOC
+    if (cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&db->ev) != cudaSuccess) {
+        snk_set_error("stream/event creation failed");
+        snk_db_destroy(db);
+        return 1;
+    }
+    if (cudaMemcpyAsync(db->F_raw, F, (size_t)N * Dt * 4, cudaMemcpyHostToDevice, db->stream) != cudaSuccess ||
+        cudaMemcpyAsync(db->Jc_raw, Jc, (size_t)(N + 1) * Dj * 4, cudaMemcpyHostToDevice, db->stream) != cudaSuccess ||
+        cudaStreamSynchronize(db->stream) != cudaSuccess) {
+        snk_set_error("database upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        snk_db_destroy(db);
+        return 1;
+    }
+    if (snk_tc_prepare(db)) {
+        snk_db_destroy(db);
+        return 1;
+    }
+    *out = db;
+    return 0;
+}
+
+int snk_db_destroy(snk_db *db) {
+    if (!db) return 0;
+    cudaSetDevice(db->device);
+    if (db->stream) cudaStreamSynchronize(db->stream);
+    snk_tc_destroy(db);
+    cudaFree(db->F_raw); cudaFree(db->Jc_raw); cudaFree(db->wt); cudaFree(db->wj);
+    cudaFree(db->Fw32); cudaFree(db->Jw32); cudaFree(db->G16); cudaFree(db->S16);
+    cudaFree(db->nrm_t16); cudaFree(db->nrm_j16); cudaFree(db->err_t16);
+    snk_buf *bufs[] = {&db->ws_q, &db->ws_dist, &db->ws_list, &db->ws_misc, &db->ws_io, &db->ws_io2, &db->ws_tiles,
+                       &db->ws_bp, &db->ws_tc, &db->ws_h0, &db->ws_h1, &db->ws_h2, &db->ws_h3};
+    for (snk_buf *b : bufs) snk_buf_free(b);
+    if (db->ev) cudaEventDestroy(db->ev);
+    if (db->stream) cudaStreamDestroy(db->stream);
+    cudaGetLastError();
+    delete db;
+    return 0;
+}
+
+int snk_db_info(const snk_db *db, int64_t *N, int64_t *Nprime, int *Dt, int *Dj, int *multiepoch, int *joint_dim) {
+    SNK_CHECK(db, "db is NULL");
+    if (N) *N = db->N;
+    if (Nprime) *Nprime = db->Np;
+    if (Dt) *Dt = db->Dt;
+    if (Dj) *Dj = db->Dj;
+    if (multiepoch) *multiepoch = db->m;
+    if (joint_dim) *joint_dim = db->Djq + db->m * db->Dt;
+    return 0;
+}
+
+int snk_db_set_weights(snk_db *db, const double *wt, const double *wj) {
+    SNK_CHECK(db && wt && wj, "NULL argument");
+    SNK_CUDA(cudaSetDevice(db->device));
+    SNK_CUDA(cudaMemcpyAsync(db->wt, wt, (size_t)db->Dt * 8, cudaMemcpyHostToDevice, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(db->wj, wj, (size_t)db->Dj * 8, cudaMemcpyHostToDevice, db->stream));
+    SNK_TRY(snk_apply_weights(db, db->stream));
+    SNK_CUDA(cudaStreamSynchronize(db->stream));
+    db->weights_set = true;
+    return 0;
+}
+
+int snk_db_set_engine(snk_db *db, int engine) {
+    SNK_CHECK(db, "db is NULL");
+    SNK_CHECK(engine == SNK_ENGINE_AUTO || engine == SNK_ENGINE_SIMT || engine == SNK_ENGINE_TC, "unknown engine %d",
+              engine);
+    db->engine = engine;
+    return 0;
+}
+
+int snk_db_counters(const snk_db *db, int64_t counters[4], int reset) {
+    SNK_CHECK(db && counters, "NULL argument");
+    memcpy(counters, db->counters, sizeof(db->counters));
+    if (reset) memset(const_cast<snk_db *>(db)->counters, 0, sizeof(db->counters));
+    return 0;
+}
+
+int snk_knn_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist, int64_t *d_idx,
+                int64_t id_offset, void *stream) {
+    SNK_CHECK(db, "db is NULL");
+    SNK_CHECK(space == SNK_SPACE_TARGET || space == SNK_SPACE_JOINT, "unknown search space %d", space);
+    SNK_CUDA(cudaSetDevice(db->device));
+    return snk_search_dev(db, space, dQ, nq, k, d_dist, d_idx, k, id_offset, (cudaStream_t)stream);
+}
+
+int snk_knn(snk_db *db, int space, const double *Q, int64_t nq, int k, double *dist, int64_t *idx) {
+    SNK_CHECK(db && dist && idx, "NULL argument");
+    SNK_CHECK(space == SNK_SPACE_TARGET || space == SNK_SPACE_JOINT, "unknown search space %d", space);
+    SNK_CHECK(nq >= 0 && k >= 1, "bad nq / k");
+    if (nq == 0) return 0;
+    SNK_CHECK(Q, "Q is NULL");
+    SNK_CUDA(cudaSetDevice(db->device));
+    const snk_space sp = snk_make_space(db, space);
+    // queries go through in slabs so device staging stays bounded
+    const int64_t slab = 65536;
+    SNK_TRY(snk_buf_reserve(&db->ws_h0, (size_t)std::min(slab, nq) * sp.D * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_h1, (size_t)std::min(slab, nq) * k * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_h2, (size_t)std::min(slab, nq) * k * 8));
+    for (int64_t q0 = 0; q0 < nq; q0 += slab) {
+        const int64_t n = std::min(slab, nq - q0);
+        SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, Q + q0 * sp.D, (size_t)n * sp.D * 8, cudaMemcpyHostToDevice, db->stream));
+        SNK_TRY(snk_search_dev(db, space, (const double *)db->ws_h0.p, n, k, (double *)db->ws_h1.p,
+                               (int64_t *)db->ws_h2.p, k, 0, db->stream));
+        SNK_CUDA(cudaMemcpyAsync(dist + q0 * k, db->ws_h1.p, (size_t)n * k * 8, cudaMemcpyDeviceToHost, db->stream));
+        SNK_CUDA(cudaMemcpyAsync(idx + q0 * k, db->ws_h2.p, (size_t)n * k * 8, cudaMemcpyDeviceToHost, db->stream));
+        SNK_CUDA(cudaStreamSynchronize(db->stream));
+    }
+    return 0;
+}
+
+int snk_greedy_batch(snk_db *db, const double *targets, const int64_t *lens, int B, const int64_t *start_state,
+                     int64_t *paths, double *step_dist) {
+    SNK_CHECK(db && lens && paths, "NULL argument");
+    SNK_CHECK(B >= 0, "bad batch size");
+    if (B == 0) return 0;
+    SNK_CUDA(cudaSetDevice(db->device));
+    int64_t frames = 0, steps = 0;
+    for (int b = 0; b < B; ++b) {
+        SNK_CHECK(lens[b] >= 0, "negative utterance length");
+        frames += lens[b];
+        steps += lens[b] / db->m;
+    }
+    SNK_CHECK(targets || frames == 0, "targets is NULL");
+    SNK_TRY(snk_buf_reserve(&db->ws_h0, (size_t)std::max<int64_t>(frames, 1) * db->Dt * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_h1, (size_t)std::max<int64_t>(steps, 1) * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_h2, (size_t)std::max<int64_t>(steps, 1) * 8));
+    if (frames)
+        SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, targets, (size_t)frames * db->Dt * 8, cudaMemcpyHostToDevice, db->stream));
+    SNK_TRY(snk_greedy_batch_dev(db, (const double *)db->ws_h0.p, lens, B, start_state, (int64_t *)db->ws_h1.p,
+                                 step_dist ? (double *)db->ws_h2.p : nullptr, db->stream));
+    if (steps) {
+        SNK_CUDA(cudaMemcpyAsync(paths, db->ws_h1.p, (size_t)steps * 8, cudaMemcpyDeviceToHost, db->stream));
+        if (step_dist)
+            SNK_CUDA(cudaMemcpyAsync(step_dist, db->ws_h2.p, (size_t)steps * 8, cudaMemcpyDeviceToHost, db->stream));
+    }
+    SNK_CUDA(cudaStreamSynchronize(db->stream));
+    return 0;
+}
+
+int snk_candidate_distances(snk_db *db, const int64_t *cand, const double *targets, int64_t T, int K, double *dist) {
+    SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    SNK_CHECK(T >= 0 && K >= 1, "bad T / K");
+    if (T == 0) return 0;
+    SNK_CHECK(cand && targets && dist, "NULL argument");
+    SNK_CUDA(cudaSetDevice(db->device));
+    SNK_TRY(snk_buf_reserve(&db->ws_h0, (size_t)T * K * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_h1, (size_t)T * db->Dt * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_h2, (size_t)T * K * 8));
+    SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, cand, (size_t)T * K * 8, cudaMemcpyHostToDevice, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(db->ws_h1.p, targets, (size_t)T * db->Dt * 8, cudaMemcpyHostToDevice, db->stream));
+    SNK_TRY(snk_candidate_distances_dev(db, (const int64_t *)db->ws_h0.p, (const double *)db->ws_h1.p, T, K,
+                                        (double *)db->ws_h2.p, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(dist, db->ws_h2.p, (size_t)T * K * 8, cudaMemcpyDeviceToHost, db->stream));
+    SNK_CUDA(cudaStreamSynchronize(db->stream));
+    return 0;
+}
+
+static int count_frames(const int64_t *lens, int B, int64_t *frames, int64_t *tiles) {
+    *frames = 0;
+    *tiles = 0;
+    for (int b = 0; b < B; ++b) {
+        SNK_CHECK(lens[b] >= 0, "negative utterance length");
+        *frames += lens[b];
+        *tiles += lens[b] > 0 ? lens[b] - 1 : 0;
+    }
+    SNK_CHECK(*frames < (int64_t)2000000000, "too many frames in one batch");
+    return 0;
+}
+
+int snk_join_tiles(snk_db *db, const int64_t *cand, const int64_t *lens, int B, int K, float *tiles) {
+    SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    SNK_CHECK(lens && B >= 0 && K >= 1, "bad arguments");
+    SNK_CUDA(cudaSetDevice(db->device));
+    int64_t frames, ntiles;
+    SNK_TRY(count_frames(lens, B, &frames, &ntiles));
+    if (ntiles == 0) return 0;
+    SNK_CHECK(cand && tiles, "NULL argument");
+    SNK_TRY(snk_buf_reserve(&db->ws_h0, (size_t)frames * K * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_tiles, (size_t)ntiles * K * K * 4));
+    SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, cand, (size_t)frames * K * 8, cudaMemcpyHostToDevice, db->stream));
+    SNK_TRY(snk_join_tiles_dev(db, (const int64_t *)db->ws_h0.p, lens, B, K, (float *)db->ws_tiles.p, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(tiles, db->ws_tiles.p, (size_t)ntiles * K * K * 4, cudaMemcpyDeviceToHost, db->stream));
+    SNK_CUDA(cudaStreamSynchronize(db->stream));
+    return 0;
+}
+
+int snk_join_viterbi_batch(snk_db *db, const int64_t *cand, const double *tdist, const int64_t *lens, int B, int K,
+                           unsigned flags, int64_t *paths, int64_t *path_len, double *path_cost, double *tcost,
+                           double *jcost) {
+    SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    SNK_CHECK(lens && B >= 0 && K >= 1, "bad arguments");
+    if (B == 0) return 0;
+    SNK_CHECK(path_len && path_cost, "NULL output");
+    SNK_CUDA(cudaSetDevice(db->device));
+    int64_t frames, ntiles;
+    SNK_TRY(count_frames(lens, B, &frames, &ntiles));
+    SNK_CHECK(frames == 0 || (cand && tdist && paths), "NULL argument");
+    const size_t fK = (size_t)std::max<int64_t>(frames, 1) * K;
+    SNK_TRY(snk_buf_reserve(&db->ws_h0, fK * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_h1, fK * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_h2, (size_t)std::max<int64_t>(frames, 1) * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_h3, (size_t)B * 8 * 4));
+    int64_t *d_plen = (int64_t *)db->ws_h3.p;
+    double *d_pc = (double *)db->ws_h3.p + B, *d_tc = d_pc + B, *d_jc = d_tc + B;
+    if (frames) {
+        SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, cand, fK * 8, cudaMemcpyHostToDevice, db->stream));
+        SNK_CUDA(cudaMemcpyAsync(db->ws_h1.p, tdist, fK * 8, cudaMemcpyHostToDevice, db->stream));
+    }
+    SNK_TRY(snk_join_viterbi_batch_dev(db, (const int64_t *)db->ws_h0.p, (const double *)db->ws_h1.p, lens, B, K, flags,
+                                       (int64_t *)db->ws_h2.p, d_plen, d_pc, d_tc, d_jc, db->stream));
+    if (frames) SNK_CUDA(cudaMemcpyAsync(paths, db->ws_h2.p, (size_t)frames * 8, cudaMemcpyDeviceToHost, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(path_len, d_plen, (size_t)B * 8, cudaMemcpyDeviceToHost, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(path_cost, d_pc, (size_t)B * 8, cudaMemcpyDeviceToHost, db->stream));
+    if (tcost) SNK_CUDA(cudaMemcpyAsync(tcost, d_tc, (size_t)B * 8, cudaMemcpyDeviceToHost, db->stream));
+    if (jcost) SNK_CUDA(cudaMemcpyAsync(jcost, d_jc, (size_t)B * 8, cudaMemcpyDeviceToHost, db->stream));
+    SNK_CUDA(cudaStreamSynchronize(db->stream));
+    return 0;
+}
+
+int snk_greedy_path_scores(snk_db *db, const double *targets, int64_t T, const int64_t *path, int64_t P,
+                           const int *twidths, int n_tstreams, const int *jwidths, int n_jstreams, double *tscores,
+                           double *jscores) {
+    SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    SNK_CHECK(targets && path && twidths && jwidths && tscores && (jscores || P < 2), "NULL argument");
+    SNK_CHECK(P >= 1 && P * db->m <= T, "path length %lld does not fit %lld target frames", (long long)P, (long long)T);
+    int ts = 0, js = 0;
+    for (int i = 0; i < n_tstreams; ++i) ts += twidths[i];
+    for (int i = 0; i < n_jstreams; ++i) js += jwidths[i];
+    SNK_CHECK(ts == db->Dt, "target stream widths sum to %d, expected %d", ts, db->Dt);
+    SNK_CHECK(js == db->Djq, "join stream widths sum to %d, expected %d", js, db->Djq);
+    SNK_CUDA(cudaSetDevice(db->device));
+    SNK_TRY(snk_buf_reserve(&db->ws_h0, (size_t)T * db->Dt * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_h1, (size_t)P * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_h2, (size_t)(n_tstreams + n_jstreams) * 4));
+    SNK_TRY(snk_buf_reserve(&db->ws_h3, (size_t)P * (n_tstreams + n_jstreams) * 8));
+    int *d_tw = (int *)db->ws_h2.p, *d_jw = d_tw + n_tstreams;
+    double *d_ts = (double *)db->ws_h3.p, *d_js = d_ts + P * n_tstreams;
+    SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, targets, (size_t)T * db->Dt * 8, cudaMemcpyHostToDevice, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(db->ws_h1.p, path, (size_t)P * 8, cudaMemcpyHostToDevice, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(d_tw, twidths, (size_t)n_tstreams * 4, cudaMemcpyHostToDevice, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(d_jw, jwidths, (size_t)n_jstreams * 4, cudaMemcpyHostToDevice, db->stream));
+    SNK_TRY(snk_path_scores_dev(db, (const double *)db->ws_h0.p, T, (const int64_t *)db->ws_h1.p, P, d_tw, n_tstreams,
+                                d_jw, n_jstreams, d_ts, d_js, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(tscores, d_ts, (size_t)P * n_tstreams * 8, cudaMemcpyDeviceToHost, db->stream));
+    if (P > 1)
+        SNK_CUDA(cudaMemcpyAsync(jscores, d_js, (size_t)(P - 1) * n_jstreams * 8, cudaMemcpyDeviceToHost, db->stream));
+    SNK_CUDA(cudaStreamSynchronize(db->stream));
+    return 0;
+}
+
+}  // extern "C"

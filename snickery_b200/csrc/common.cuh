@@ -1,0 +1,134 @@
+// Shared declarations for the snk_b200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <math.h>
+#include "snk_b200.h"
+
+void snk_set_error(const char *fmt, ...);
+
+#define SNK_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            snk_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                  \
+                          cudaGetErrorString(e_));                                              \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+#define SNK_CHECK(cond, ...)                                                                    \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            snk_set_error(__VA_ARGS__);                                                         \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+#define SNK_TRY(expr)                                                                           \
+    do {                                                                                        \
+        int r_ = (expr);                                                                        \
+        if (r_) return r_;                                                                      \
+    } while (0)
+
+static inline int64_t snk_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int64_t snk_cdiv(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// grow-only device scratch buffer
+struct snk_buf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+int snk_buf_reserve(snk_buf *b, size_t bytes);
+void snk_buf_free(snk_buf *b);
+
+// How one searchable row is assembled from the resident matrices.
+// row u, dim d:  d <  dA : A[(u + a_row_off) * ldA + a_col + d]
+//                d >= dA : B[u * ldB + (d - dA)]         (window of m consecutive frames is contiguous)
+struct snk_space {
+    int64_t rows;   // number of searchable rows
+    int D;          // dA + dB
+    int dA, dB;
+    int a_row_off, a_col;
+    int ldA_raw, ldB_raw;   // leading dims of the raw f32 matrices (Dj, Dt)
+    int ldA32, ldB32;       // leading dims of the weighted f32 matrices
+};
+
+struct snk_db {
+    int device = 0;
+    int sm_count = 148;
+    int64_t N = 0, Np = 0;
+    int Dt = 0, Dj = 0, m = 1;
+    unsigned layout = 0;
+    // greedy join-context geometry (see SNK_LAYOUT_*)
+    int Djq = 0, prev_col = 0, prev_row_off = 0, cur_col = 0, cur_row_off = 0;
+    int engine = SNK_ENGINE_AUTO;
+    bool weights_set = false;
+    // resident arrays
+    float *F_raw = nullptr;   // [N, Dt]
+    float *Jc_raw = nullptr;  // [N+1, Dj]
+    double *wt = nullptr;     // [Dt]
+    double *wj = nullptr;     // [Dj]
+    float *Fw32 = nullptr;    // [N, Dt]       weighted, rounded to f32
+    float *Jw32 = nullptr;    // [N+1, ldJ32]  weighted, rounded to f32, zero padded
+    int ldJ32 = 0;
+    // fp16 operands of the tensor-core kernel
+    __half *G16 = nullptr;    // [N + pad, ldG16] target frames
+    __half *S16 = nullptr;    // [N+1 + pad, ldS16] join contexts
+    int ldG16 = 0, ldS16 = 0;
+    float *nrm_t16 = nullptr;   // [N]   ||fp16(Fw[u])||^2
+    float *nrm_j16 = nullptr;   // [Np]  ||fp16(joint row u)||^2
+    float *err_t16 = nullptr;   // [1]   max_u ||Fw[u] - fp16(Fw[u])||      (target space)
+    float *err_j16 = nullptr;   // [1]   max_u ||joint row - fp16(joint row)||
+    float *maxn_t16 = nullptr;  // [1]   max_u nrm_t16
+    float *maxn_j16 = nullptr;  // [1]
+    void *tc_state = nullptr;   // tensor maps etc. (knn_tc.cu)
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev = nullptr;
+    snk_buf ws_q, ws_dist, ws_list, ws_misc, ws_io, ws_io2, ws_tiles, ws_bp, ws_tc, ws_h0, ws_h1, ws_h2, ws_h3;
+    int64_t counters[4] = {0, 0, 0, 0};
+};
+
+snk_space snk_make_space(const snk_db *db, int space);
+
+// ---- weights.cu
+int snk_apply_weights(snk_db *db, cudaStream_t st);
+
+// ---- knn_simt.cu : fp32 direct-difference shortlist
+// Q32 [nq, ldq] f32 queries.  Writes the KP smallest (dist^2 f32, row id i32) per query, unsorted.
+int snk_shortlist_simt(snk_db *db, const snk_space &sp, const float *dQ32, int ldq, int64_t nq, int KP,
+                       float *d_val, int *d_id, cudaStream_t st);
+// generic row-wise top-KP scan (see knn_simt.cu)
+int snk_topk_scan(snk_db *db, const float *d_vals, const int *d_ids, int64_t nq, int64_t n, int64_t ld,
+                  int id_base, int KP, bool init, float *d_val, int *d_id, cudaStream_t st);
+
+// ---- knn_tc.cu : tcgen05 shortlist
+bool snk_tc_supported(const snk_db *db, const snk_space &sp, int KP);
+int snk_tc_prepare(snk_db *db);   // (re)build tensor maps / K-block tables after create
+void snk_tc_destroy(snk_db *db);
+int snk_tc_query_ld(const snk_db *db, int space);           // leading dim of the fp16 query operand
+const short *snk_tc_qmap(const snk_db *db, int space);      // device map: operand column -> query dim (or -1)
+// dQ16 [round_up(nq,128), ldq16] fp16 queries in K-block order.  Writes the KP smallest approximate
+// keys (||y~||^2 - 2 x~.y~, f32) with row ids per query (unsorted) and d_tau[q], a lower bound on the
+// key of every row that was dropped before the final merge (+inf if none was).
+int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64_t nq, int k, int KP,
+                     float *d_val, int *d_id, float *d_tau, cudaStream_t st);
+
+// ---- rerank.cu
+// Exact float64 distances of the shortlisted rows, sorted ascending (ties: lowest id).
+// d_cert (optional, [nq + 1]): per query 1 = certified exact / 0 = needs SIMT re-search, from the
+// approx threshold (largest shortlist key, optionally capped by d_tau_extra[q]) and the fp16
+// perturbation bounds; d_cert[nq] counts failures.  d_qsel (optional): shortlist row i belongs
+// to query d_qsel[i] (compact re-search of flagged queries).
+int snk_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, const float *d_val,
+               const int *d_id, int KP, int k, double *d_dist, int64_t *d_idx, int64_t out_stride,
+               int64_t id_offset, const float *d_qerr, const float *d_dberr, const float *d_qn,
+               const float *d_maxn, const float *d_tau_extra, int *d_cert, const int *d_qsel,
+               cudaStream_t st);
+
+// ---- search.cu : k-NN driver shared by snk_knn and the greedy loop
+// dQ float64 [nq, D] device; results device.
+int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist,
+                   int64_t *d_idx, int64_t out_stride, int64_t id_offset, cudaStream_t st);

@@ -1,0 +1,287 @@
+// fp32 direct-difference distance tiles on CUDA cores + warp top-k scan.
+//
+// This is the engine's exact-arithmetic shortlist path: sum_d (x_d - y_d)^2 is
+// evaluated without the norm expansion, so it has full relative accuracy for
+// near neighbours.  It serves (a) searches whose shape the tensor-core kernel
+// does not take, (b) the re-search of queries whose tensor-core shortlist
+// fails the exactness certificate (rerank.cu).
+//
+// Replaces (with rerank.cu): cKDTree.query -- reference script/synth_simple.py:490,
+// script/synth_halfphone.py:1364.
+#include "common.cuh"
+#include <limits.h>
+#include <algorithm>
+
+namespace {
+
+constexpr int TQ = 64;   // queries per CTA tile
+constexpr int TR = 64;   // rows per CTA tile
+constexpr int BK = 16;   // dims per smem stage
+constexpr int PADW = 4;
+
+struct space_dev {
+    const float *A;   // weighted join matrix (may be null when dA == 0)
+    const float *B;   // weighted target matrix
+    int dA, D, a_row_off, a_col, ldA, ldB;
+};
+
+__device__ __forceinline__ float row_elem(const space_dev &sp, int64_t u, int d) {
+    if (d < sp.dA) return __ldg(sp.A + (u + sp.a_row_off) * (int64_t)sp.ldA + sp.a_col + d);
+    return __ldg(sp.B + u * (int64_t)sp.ldB + (d - sp.dA));
+}
+
+// out[q, r - row0] = sum_d (Q[q,d] - row[r,d])^2   (+inf for r >= row_end)
+__global__ void __launch_bounds__(256)
+dist_f32_kernel(space_dev sp, const float *__restrict__ Q, int ldq, int64_t nq, int64_t row0,
+                int64_t row_end, float *__restrict__ out, int64_t ldo) {
+    __shared__ float Qs[BK][TQ + PADW];
+    __shared__ float Rs[BK][TR + PADW];
+    const int tid = threadIdx.x;
+    const int tr = tid % 16, tq = tid / 16;
+    const int64_t q0 = (int64_t)blockIdx.y * TQ;
+    const int64_t r0 = row0 + (int64_t)blockIdx.x * TR;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int lk = tid % BK, lr = tid / BK;   // loader mapping: 16 dims x 16 rows per pass
+    for (int k0 = 0; k0 < sp.D; k0 += BK) {
+        const int d = k0 + lk;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int qq = lr + 16 * i;
+            const int64_t q = q0 + qq;
+            float v = 0.f;
+            if (q < nq && d < sp.D) v = __ldg(Q + q * (int64_t)ldq + d);
+            Qs[lk][qq] = v;
+            const int64_t r = r0 + qq;
+            float w = 0.f;
+            if (r < row_end && d < sp.D) w = row_elem(sp, r, d);
+            Rs[lk][qq] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a = *reinterpret_cast<const float4 *>(&Qs[k][tq * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Rs[k][tr * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float df = av[i] - bv[j];
+                    acc[i][j] = fmaf(df, df, acc[i][j]);
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t q = q0 + tq * 4 + i;
+        if (q >= nq) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t r = r0 + tr * 4 + j;
+            const int64_t col = r - row0;
+            if (col < ldo) out[q * ldo + col] = (r < row_end) ? acc[i][j] : INFINITY;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Warp top-KP scan: one warp keeps the KP = 32*E smallest (value, id) pairs of a row
+// segment in registers; order inside the list is arbitrary.  Ties: lower id wins.
+__device__ __forceinline__ bool pair_lt(float v1, int i1, float v2, int i2) {
+    return v1 < v2 || (v1 == v2 && i1 < i2);
+}
+
+template <int E>
+struct warp_list {
+    float lv[E];
+    int li[E];
+    float tv;   // current worst (largest) pair in the list, warp-uniform
+    int ti;
+    int tpos;   // e * 32 + lane of the worst pair
+
+    __device__ __forceinline__ void recompute() {
+        float bv = lv[0];
+        int bi = li[0], bp = threadIdx.x & 31;
+#pragma unroll
+        for (int e = 1; e < E; ++e)
+            if (pair_lt(bv, bi, lv[e], li[e])) { bv = lv[e]; bi = li[e]; bp = e * 32 + (threadIdx.x & 31); }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            const int op = __shfl_xor_sync(0xffffffffu, bp, off);
+            if (pair_lt(bv, bi, ov, oi)) { bv = ov; bi = oi; bp = op; }
+        }
+        tv = bv; ti = bi; tpos = bp;
+    }
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int e = 0; e < E; ++e) { lv[e] = INFINITY; li[e] = INT_MAX; }
+        tv = INFINITY; ti = INT_MAX; tpos = 0;
+    }
+    // cv, ci warp-uniform
+    __device__ __forceinline__ void offer(float cv, int ci) {
+        if (pair_lt(cv, ci, tv, ti)) {
+            if ((threadIdx.x & 31) == (tpos & 31)) {
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (e == (tpos >> 5)) { lv[e] = cv; li[e] = ci; }
+            }
+            recompute();
+        }
+    }
+    // per-lane candidate; all lanes must call
+    __device__ __forceinline__ void offer_lanes(float v, int id) {
+        unsigned mask = __ballot_sync(0xffffffffu, v < INFINITY && pair_lt(v, id, tv, ti));
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            const float cv = __shfl_sync(0xffffffffu, v, src);
+            const int ci = __shfl_sync(0xffffffffu, id, src);
+            offer(cv, ci);
+            mask &= mask - 1;
+        }
+    }
+};
+
+// grid (nsplit, nq), block 32.  vals [nq, ld] (first n valid); ids optional (same layout).
+// out [nq, nsplit, KP].  If init == false and nsplit == 1 the existing out list is merged in.
+template <int E>
+__global__ void __launch_bounds__(32)
+topk_scan_kernel(const float *__restrict__ vals, const int *__restrict__ ids, int64_t n, int64_t ld,
+                 int id_base, bool init, float *__restrict__ oval, int *__restrict__ oid) {
+    constexpr int KP = 32 * E;
+    const int lane = threadIdx.x;
+    const int64_t q = blockIdx.y;
+    const int nsplit = gridDim.x, s = blockIdx.x;
+    const int64_t len = (n + nsplit - 1) / nsplit;
+    const int64_t beg = s * len, end = min(n, beg + len);
+    warp_list<E> L;
+    L.init();
+    float *ov = oval + (q * nsplit + s) * KP;
+    int *oi = oid + (q * nsplit + s) * KP;
+    if (!init) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            L.lv[e] = ov[e * 32 + lane];
+            const int id = oi[e * 32 + lane];
+            L.li[e] = id < 0 ? INT_MAX : id;
+        }
+        L.recompute();
+    }
+    const float *row = vals + q * ld;
+    const int *irow = ids ? ids + q * ld : nullptr;
+    for (int64_t base = beg; base < end; base += 128) {
+        float v[4];
+        int id[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t p = base + j * 32 + lane;
+            v[j] = INFINITY;
+            id[j] = INT_MAX;
+            if (p < end) {
+                v[j] = __ldg(row + p);
+                id[j] = irow ? __ldg(irow + p) : (int)(id_base + p);
+                if (id[j] < 0) v[j] = INFINITY;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) L.offer_lanes(v[j], id[j]);
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        ov[e * 32 + lane] = L.lv[e];
+        oi[e * 32 + lane] = (L.lv[e] < INFINITY) ? L.li[e] : -1;
+    }
+}
+
+template <int E>
+void launch_scan(const float *vals, const int *ids, int64_t nq, int64_t n, int64_t ld, int id_base,
+                 int nsplit, bool init, float *oval, int *oid, cudaStream_t st) {
+    dim3 grid(nsplit, (unsigned)nq);
+    topk_scan_kernel<E><<<grid, 32, 0, st>>>(vals, ids, n, ld, id_base, init, oval, oid);
+}
+
+int scan_dispatch(int KP, const float *vals, const int *ids, int64_t nq, int64_t n, int64_t ld, int id_base,
+                  int nsplit, bool init, float *oval, int *oid, cudaStream_t st) {
+    switch (KP) {
+    case 32: launch_scan<1>(vals, ids, nq, n, ld, id_base, nsplit, init, oval, oid, st); break;
+    case 64: launch_scan<2>(vals, ids, nq, n, ld, id_base, nsplit, init, oval, oid, st); break;
+    case 128: launch_scan<4>(vals, ids, nq, n, ld, id_base, nsplit, init, oval, oid, st); break;
+    case 256: launch_scan<8>(vals, ids, nq, n, ld, id_base, nsplit, init, oval, oid, st); break;
+    default: snk_set_error("shortlist size %d not supported (32/64/128/256)", KP); return 1;
+    }
+    SNK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int snk_topk_scan(snk_db *db, const float *d_vals, const int *d_ids, int64_t nq, int64_t n, int64_t ld,
+                  int id_base, int KP, bool init, float *d_val, int *d_id, cudaStream_t st) {
+    if (nq <= 0) return 0;
+    SNK_CHECK(nq <= 65535, "topk scan: too many queries per launch (%lld)", (long long)nq);
+    // split long rows over several warps when there are few queries
+    int nsplit = 1;
+    const int64_t want_warps = (int64_t)db->sm_count * 16;
+    if (nq < want_warps && n > 4096) {
+        nsplit = (int)std::min<int64_t>(snk_cdiv(want_warps, nq), snk_cdiv(n, 2048));
+        if (nsplit < 1) nsplit = 1;
+    }
+    if (nsplit == 1) {
+        db->counters[2] += 1;
+        return scan_dispatch(KP, d_vals, d_ids, nq, n, ld, id_base, 1, init, d_val, d_id, st);
+    }
+    // two-level: partial lists, then merge them (together with the carried-in list)
+    SNK_TRY(snk_buf_reserve(&db->ws_misc, (size_t)nq * (nsplit + 1) * KP * 8));
+    float *pv = (float *)db->ws_misc.p;
+    int *pi = (int *)(pv + (size_t)nq * (nsplit + 1) * KP);
+    // partials occupy columns [0, nsplit*KP) of rows of length (nsplit+1)*KP; the carried list is
+    // copied behind them so one merge pass sees everything.
+    const int64_t pld = (int64_t)(nsplit + 1) * KP;
+    // level 1 writes [nq, nsplit, KP] contiguous; use a temp view with stride nsplit*KP then merge
+    // with the carried list via a second scan that is not "init".
+    (void)pld;
+    db->counters[2] += 2;
+    SNK_TRY(scan_dispatch(KP, d_vals, d_ids, nq, n, ld, id_base, nsplit, true, pv, pi, st));
+    SNK_TRY(scan_dispatch(KP, pv, pi, nq, (int64_t)nsplit * KP, (int64_t)nsplit * KP, 0, 1, init, d_val, d_id, st));
+    return 0;
+}
+
+int snk_shortlist_simt(snk_db *db, const snk_space &sp, const float *dQ32, int ldq, int64_t nq, int KP,
+                       float *d_val, int *d_id, cudaStream_t st) {
+    if (nq <= 0) return 0;
+    space_dev sd;
+    sd.A = db->Jw32; sd.B = db->Fw32;
+    sd.dA = sp.dA; sd.D = sp.D; sd.a_row_off = sp.a_row_off; sd.a_col = sp.a_col;
+    sd.ldA = sp.ldA32; sd.ldB = sp.ldB32;
+    // distance workspace: at most ~256 MiB, chunked over rows and over queries
+    const size_t WS = (size_t)256 << 20;
+    const int64_t qchunk = std::min<int64_t>(nq, 8192);
+    int64_t rchunk = (int64_t)(WS / 4 / qchunk);
+    rchunk = std::max<int64_t>(TR, rchunk / TR * TR);
+    rchunk = std::min<int64_t>(rchunk, snk_round_up(sp.rows, TR));
+    SNK_TRY(snk_buf_reserve(&db->ws_dist, (size_t)qchunk * rchunk * 4));
+    float *dist = (float *)db->ws_dist.p;
+    for (int64_t qb = 0; qb < nq; qb += qchunk) {
+        const int64_t qn = std::min<int64_t>(qchunk, nq - qb);
+        bool first = true;
+        for (int64_t rb = 0; rb < sp.rows; rb += rchunk) {
+            const int64_t rn = std::min<int64_t>(rchunk, sp.rows - rb);
+            dim3 grid((unsigned)snk_cdiv(rn, TR), (unsigned)snk_cdiv(qn, TQ));
+            dist_f32_kernel<<<grid, 256, 0, st>>>(sd, dQ32 + qb * ldq, ldq, qn, rb, rb + rn, dist, rchunk);
+            SNK_CUDA(cudaGetLastError());
+            db->counters[2] += 1;
+            SNK_TRY(snk_topk_scan(db, dist, nullptr, qn, rn, rchunk, (int)rb, KP, first, d_val + qb * KP,
+                                  d_id + qb * KP, st));
+            first = false;
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,284 @@
+// k-NN search driver and the batched greedy joint search.
+//
+// snk_search_dev  : tree.query(X, k) replacement (reference script/synth_halfphone.py:1364,
+//                   script/synth_simple.py:490) -- shortlist (tensor-core or SIMT) then float64 re-rank.
+// greedy batch    : Synthesiser.greedy_joint_search (reference script/synth_simple.py:458-503)
+//                   for B utterances at once; the chain over time steps stays sequential, the
+//                   B queries of one step form one batched search over the whole database.
+#include "common.cuh"
+#include <algorithm>
+#include <vector>
+
+snk_space snk_make_space(const snk_db *db, int space) {
+    snk_space sp{};
+    if (space == SNK_SPACE_TARGET) {
+        sp.rows = db->N;
+        sp.dA = 0;
+        sp.dB = db->Dt;
+    } else {
+        sp.rows = db->Np;
+        sp.dA = db->Djq;
+        sp.dB = db->m * db->Dt;
+    }
+    sp.D = sp.dA + sp.dB;
+    sp.a_row_off = db->prev_row_off;
+    sp.a_col = db->prev_col;
+    sp.ldA_raw = db->Dj;
+    sp.ldB_raw = db->Dt;
+    sp.ldA32 = db->ldJ32;
+    sp.ldB32 = db->Dt;
+    return sp;
+}
+
+namespace {
+
+// f64 -> f32 query copy, optionally gathering rows through qsel
+__global__ void cvt_q32_kernel(const double *__restrict__ Q, int D, int64_t nq, const int *__restrict__ qsel,
+                               float *__restrict__ out) {
+    const int64_t total = nq * D;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / D;
+        const int c = (int)(i - r * D);
+        const int64_t src = qsel ? qsel[r] : r;
+        out[i] = (float)Q[src * D + c];
+    }
+}
+
+// fp16 query operand in K-block order + squared norm of the rounded query + rounding error norm.
+// One warp per (padded) query row.
+__global__ void cvt_q16_kernel(const double *__restrict__ Q, int D, int64_t nq, int64_t nq_pad,
+                               const short *__restrict__ qmap, int ld16, __half *__restrict__ out,
+                               float *__restrict__ qn, float *__restrict__ qerr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = warp; q < nq_pad; q += nwarp) {
+        float n2 = 0.f, e2 = 0.f;
+        for (int c = lane; c < ld16; c += 32) {
+            __half h = __float2half_rn(0.f);
+            const int d = qmap[c];
+            if (q < nq && d >= 0) {
+                const double x = Q[q * D + d];
+                h = __double2half(x);
+                const float hf = __half2float(h);
+                n2 = fmaf(hf, hf, n2);
+                const float df = (float)(x - (double)hf);
+                e2 = fmaf(df, df, e2);
+            }
+            out[q * ld16 + c] = h;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+            e2 += __shfl_xor_sync(0xffffffffu, e2, off);
+        }
+        if (lane == 0 && q < nq) {
+            qn[q] = n2;
+            qerr[q] = sqrtf(e2);
+        }
+    }
+}
+
+// compact the indices of uncertified queries
+__global__ void compact_fail_kernel(const int *__restrict__ cert, int64_t nq, int *__restrict__ qsel,
+                                    int *__restrict__ count) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nq; i += (int64_t)gridDim.x * blockDim.x)
+        if (!cert[i]) qsel[atomicAdd(count, 1)] = (int)i;
+}
+
+int shortlist_size(int k) {
+    const int want = k + 8;
+    if (want <= 32) return 32;
+    if (want <= 64) return 64;
+    if (want <= 128) return 128;
+    if (want <= 256) return 256;
+    return -1;
+}
+
+int search_simt(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, const int *d_qsel, int k,
+                double *d_dist, int64_t *d_idx, int64_t out_stride, int64_t id_offset, cudaStream_t st) {
+    const int KP = shortlist_size(k);
+    SNK_CHECK(KP > 0, "k = %d too large (max 248)", k);
+    SNK_TRY(snk_buf_reserve(&db->ws_q, (size_t)nq * sp.D * 4));
+    SNK_TRY(snk_buf_reserve(&db->ws_list, (size_t)nq * KP * 8));
+    float *q32 = (float *)db->ws_q.p;
+    float *val = (float *)db->ws_list.p;
+    int *id = (int *)(val + (size_t)nq * KP);
+    cvt_q32_kernel<<<db->sm_count * 4, 256, 0, st>>>(dQ, sp.D, nq, d_qsel, q32);
+    SNK_CUDA(cudaGetLastError());
+    db->counters[2] += 1;
+    SNK_TRY(snk_shortlist_simt(db, sp, q32, sp.D, nq, KP, val, id, st));
+    SNK_TRY(snk_rerank(db, sp, dQ, nq, val, id, KP, k, d_dist, d_idx, out_stride, id_offset, nullptr, nullptr,
+                       nullptr, nullptr, nullptr, nullptr, d_qsel, st));
+    return 0;
+}
+
+}  // namespace
+
+int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist,
+                   int64_t *d_idx, int64_t out_stride, int64_t id_offset, cudaStream_t st) {
+    SNK_CHECK(db->weights_set, "snk_db_set_weights has not been called");
+    SNK_CHECK(k >= 1, "k must be >= 1");
+    if (nq <= 0) return 0;
+    const snk_space sp = snk_make_space(db, space);
+    SNK_CHECK(sp.rows > 0, "search space is empty (N=%lld, multiepoch=%d)", (long long)db->N, db->m);
+    db->counters[0] += nq;
+    const int KP = shortlist_size(k);
+    SNK_CHECK(KP > 0, "k = %d too large (max 248)", k);
+    const bool use_tc = db->engine != SNK_ENGINE_SIMT && snk_tc_supported(db, sp, KP);
+    SNK_CHECK(use_tc || db->engine != SNK_ENGINE_TC, "tensor-core engine requested but this search shape is not supported by it");
+    if (!use_tc) return search_simt(db, sp, dQ, nq, nullptr, k, d_dist, d_idx, out_stride, id_offset, st);
+
+    // ---- tensor-core shortlist + float64 re-rank + certificate, in query batches
+    const int ld16 = snk_tc_query_ld(db, space);
+    const int64_t QB = 16384;
+    for (int64_t qb = 0; qb < nq; qb += QB) {
+        const int64_t qn_ = std::min(QB, nq - qb);
+        const int64_t qpad = snk_round_up(qn_, 128);
+        // ws_q layout: Q16 [qpad, ld16] | qn [qpad] | qerr [qpad] | tau [qpad] | cert [qpad+1] | qsel [qpad] | cnt
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+        const size_t o_q16 = take((size_t)qpad * ld16 * 2), o_qn = take(qpad * 4), o_qe = take(qpad * 4),
+                     o_tau = take(qpad * 4), o_cert = take((qpad + 1) * 4), o_sel = take(qpad * 4), o_cnt = take(4);
+        SNK_TRY(snk_buf_reserve(&db->ws_io2, off));
+        char *base = (char *)db->ws_io2.p;
+        __half *q16 = (__half *)(base + o_q16);
+        float *qn = (float *)(base + o_qn), *qerr = (float *)(base + o_qe), *tau = (float *)(base + o_tau);
+        int *cert = (int *)(base + o_cert), *qsel = (int *)(base + o_sel), *cnt = (int *)(base + o_cnt);
+        SNK_TRY(snk_buf_reserve(&db->ws_list, (size_t)qn_ * KP * 8));
+        float *val = (float *)db->ws_list.p;
+        int *id = (int *)(val + (size_t)qn_ * KP);
+        const double *Qb = dQ + qb * sp.D;
+
+        cvt_q16_kernel<<<db->sm_count * 4, 256, 0, st>>>(Qb, sp.D, qn_, qpad, snk_tc_qmap(db, space), ld16, q16, qn,
+                                                         qerr);
+        SNK_CUDA(cudaGetLastError());
+        db->counters[2] += 1;
+        SNK_TRY(snk_shortlist_tc(db, space, q16, ld16, qn_, k, KP, val, id, tau, st));
+        SNK_CUDA(cudaMemsetAsync(cert + qn_, 0, 4, st));
+        const bool joint = space == SNK_SPACE_JOINT;
+        SNK_TRY(snk_rerank(db, sp, Qb, qn_, val, id, KP, k, d_dist + qb * out_stride, d_idx + qb * out_stride,
+                           out_stride, id_offset, qerr, joint ? db->err_j16 : db->err_t16, qn,
+                           joint ? db->maxn_j16 : db->maxn_t16, tau, cert, nullptr, st));
+        int nfail = 0;
+        SNK_CUDA(cudaMemcpyAsync(&nfail, cert + qn_, 4, cudaMemcpyDeviceToHost, st));
+        SNK_CUDA(cudaStreamSynchronize(st));
+        if (nfail > 0) {
+            db->counters[1] += nfail;
+            SNK_CUDA(cudaMemsetAsync(cnt, 0, 4, st));
+            compact_fail_kernel<<<64, 256, 0, st>>>(cert, qn_, qsel, cnt);
+            SNK_CUDA(cudaGetLastError());
+            db->counters[2] += 1;
+            SNK_TRY(search_simt(db, sp, Qb, nfail, qsel, k, d_dist + qb * out_stride, d_idx + qb * out_stride,
+                                out_stride, id_offset, st));
+        }
+    }
+    return 0;
+}
+
+// =====================================================================================
+// greedy joint search
+namespace {
+
+struct greedy_meta {
+    int64_t tgt_off;    // first frame of the utterance in the concatenated targets
+    int64_t path_off;   // first step of the utterance in the concatenated paths
+    int64_t nsteps;
+    int64_t start_state;
+};
+
+// Query b of step t = [ prev_join_vector || m consecutive target frames ]   (synth_simple.py:467-470,488,501)
+// Also scatters the previous step's result into the output path.
+__global__ void greedy_assemble_kernel(const greedy_meta *__restrict__ meta, int nact_prev, int nact, int64_t t,
+                                       const double *__restrict__ targets, int Dt, int m,
+                                       const float *__restrict__ Jc_raw, const double *__restrict__ wj, int Dj,
+                                       int Djq, int prev_row_off, int prev_col, int cur_row_off, int cur_col,
+                                       const int64_t *__restrict__ ix_prev, const double *__restrict__ dist_prev,
+                                       int64_t *__restrict__ paths, double *__restrict__ step_dist,
+                                       double *__restrict__ Q) {
+    const int b = blockIdx.x;
+    const greedy_meta mt = meta[b];
+    const int D = Djq + m * Dt;
+    if (t > 0 && b < nact_prev && threadIdx.x == 0) {
+        paths[mt.path_off + t - 1] = ix_prev[b];
+        if (step_dist) step_dist[mt.path_off + t - 1] = dist_prev[b];
+    }
+    if (b >= nact) return;
+    double *q = Q + (int64_t)b * D;
+    int64_t row = -1;
+    int col = 0;
+    if (t == 0) {
+        if (mt.start_state >= 0) { row = mt.start_state + prev_row_off; col = prev_col; }
+    } else {
+        row = ix_prev[b] + cur_row_off;
+        col = cur_col;
+    }
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        double v;
+        if (d < Djq) {
+            v = row >= 0 ? (double)Jc_raw[row * Dj + col + d] * wj[col + d] : 0.0;
+        } else {
+            v = targets[(mt.tgt_off + t * m) * Dt + (d - Djq)];
+        }
+        q[d] = v;
+    }
+}
+
+}  // namespace
+
+int snk_greedy_batch_dev(snk_db *db, const double *d_targets, const int64_t *lens, int B,
+                         const int64_t *start_state, int64_t *d_paths, double *d_step_dist, void *stream) {
+    SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    SNK_CUDA(cudaSetDevice(db->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0) return 0;
+    const int m = db->m;
+    // utterance order: longest first so the active set of every step is a prefix
+    std::vector<greedy_meta> meta(B);
+    int64_t toff = 0, poff = 0, maxsteps = 0;
+    for (int b = 0; b < B; ++b) {
+        SNK_CHECK(lens[b] >= m, "utterance %d has %lld frames, fewer than multiepoch=%d "
+                  "(the reference's segment_axis raises ValueError here)", b, (long long)lens[b], m);
+        meta[b].tgt_off = toff;
+        meta[b].path_off = poff;
+        meta[b].nsteps = lens[b] / m;
+        meta[b].start_state = start_state ? start_state[b] : -1;
+        if (meta[b].start_state >= db->Np) {
+            snk_set_error("start_state %lld out of range", (long long)meta[b].start_state);
+            return 1;
+        }
+        toff += lens[b];
+        poff += meta[b].nsteps;
+        maxsteps = std::max(maxsteps, meta[b].nsteps);
+    }
+    std::stable_sort(meta.begin(), meta.end(),
+                     [](const greedy_meta &a, const greedy_meta &b) { return a.nsteps > b.nsteps; });
+    const snk_space sp = snk_make_space(db, SNK_SPACE_JOINT);
+    // ws_io: meta | Q [B, D] | ix [B] | dist [B]
+    const size_t meta_bytes = snk_round_up(sizeof(greedy_meta) * B, 256);
+    const size_t q_bytes = snk_round_up((size_t)B * sp.D * 8, 256);
+    SNK_TRY(snk_buf_reserve(&db->ws_io, meta_bytes + q_bytes + (size_t)B * 16 + 512));
+    char *base = (char *)db->ws_io.p;
+    greedy_meta *d_meta = (greedy_meta *)base;
+    double *Q = (double *)(base + meta_bytes);
+    int64_t *ix = (int64_t *)(base + meta_bytes + q_bytes);
+    double *dist = (double *)(base + meta_bytes + q_bytes + snk_round_up((size_t)B * 8, 256));
+    SNK_CUDA(cudaMemcpyAsync(d_meta, meta.data(), sizeof(greedy_meta) * B, cudaMemcpyHostToDevice, st));
+    SNK_CUDA(cudaStreamSynchronize(st));   // meta is a stack-lifetime host vector
+    int nact_prev = 0;
+    for (int64_t t = 0; t <= maxsteps; ++t) {
+        int nact = 0;
+        while (nact < B && meta[nact].nsteps > t) ++nact;
+        const int grid = std::max(nact, nact_prev);
+        if (grid == 0) break;
+        greedy_assemble_kernel<<<grid, 128, 0, st>>>(d_meta, nact_prev, nact, t, d_targets, db->Dt, m, db->Jc_raw,
+                                                     db->wj, db->Dj, db->Djq, db->prev_row_off, db->prev_col,
+                                                     db->cur_row_off, db->cur_col, ix, dist, d_paths, d_step_dist, Q);
+        SNK_CUDA(cudaGetLastError());
+        db->counters[2] += 1;
+        if (nact > 0) SNK_TRY(snk_search_dev(db, SNK_SPACE_JOINT, Q, nact, 1, dist, ix, 1, 0, st));
+        nact_prev = nact;
+    }
+    return 0;
+}

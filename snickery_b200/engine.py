@@ -1,0 +1,240 @@
+"""ctypes binding of the C ABI in include/snk_b200.h.
+
+This is the only place the Python host touches the CUDA engine.  There is no CPU
+fallback: if the shared library is missing or no B200 is visible, construction of
+a UnitDatabase raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libsnk_b200.so")
+
+LAYOUT_SIMPLE = 0
+LAYOUT_HALFPHONE_EPOCH = 1
+SPACE_TARGET = 0
+SPACE_JOINT = 1
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
+VITERBI_BEAM1 = 1
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype)) if a is not None else None
+
+
+def load_library(path=None):
+    """Loads libsnk_b200.so (building is the job of `python -m snickery_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise EngineError("CUDA engine not built: %s is missing (run `python -m snickery_b200.build`). "
+                          "There is no CPU fallback." % path)
+    lib = C.CDLL(path)
+    i64, i32, dbl, flt, vp = C.c_int64, C.c_int, C.c_double, C.c_float, C.c_void_p
+    P = C.POINTER
+    lib.snk_last_error.restype = C.c_char_p
+    lib.snk_version.restype = i32
+    lib.snk_device_count.restype = i32
+    sigs = {
+        "snk_db_create": [P(vp), i32, i64, i32, i32, i32, P(flt), P(flt), C.c_uint],
+        "snk_db_destroy": [vp],
+        "snk_db_info": [vp, P(i64), P(i64), P(i32), P(i32), P(i32), P(i32)],
+        "snk_db_set_weights": [vp, P(dbl), P(dbl)],
+        "snk_db_set_engine": [vp, i32],
+        "snk_db_counters": [vp, P(i64), i32],
+        "snk_knn": [vp, i32, P(dbl), i64, i32, P(dbl), P(i64)],
+        "snk_knn_dev": [vp, i32, vp, i64, i32, vp, vp, i64, vp],
+        "snk_topk_merge_dev": [i32, vp, vp, i32, i64, i32, vp, vp, vp],
+        "snk_greedy_batch": [vp, P(dbl), P(i64), i32, P(i64), P(i64), P(dbl)],
+        "snk_greedy_batch_dev": [vp, vp, P(i64), i32, P(i64), vp, vp, vp],
+        "snk_candidate_distances": [vp, P(i64), P(dbl), i64, i32, P(dbl)],
+        "snk_join_tiles": [vp, P(i64), P(i64), i32, i32, P(flt)],
+        "snk_join_viterbi_batch": [vp, P(i64), P(dbl), P(i64), i32, i32, C.c_uint, P(i64), P(i64), P(dbl), P(dbl), P(dbl)],
+        "snk_join_viterbi_batch_dev": [vp, vp, vp, P(i64), i32, i32, C.c_uint, vp, vp, vp, vp, vp, vp],
+        "snk_greedy_path_scores": [vp, P(dbl), i64, P(i64), i64, P(i32), i32, P(i32), i32, P(dbl), P(dbl)],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = i32
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ["snk_last_error", "snk_version", "snk_device_count", "snk_db_create", "snk_db_destroy",
+                    "snk_db_info", "snk_db_set_weights", "snk_db_set_engine", "snk_db_counters", "snk_knn",
+                    "snk_knn_dev", "snk_topk_merge_dev", "snk_greedy_batch", "snk_greedy_batch_dev",
+                    "snk_candidate_distances", "snk_join_tiles", "snk_join_viterbi_batch",
+                    "snk_join_viterbi_batch_dev", "snk_greedy_path_scores"]
+
+
+def _check(rc):
+    if rc != 0:
+        raise EngineError(load_library().snk_last_error().decode("utf-8", "replace"))
+
+
+def device_count():
+    return load_library().snk_device_count()
+
+
+class UnitDatabase:
+    """A unit database resident in one GPU's HBM (F [N,Dt] f32, Jc [N+1,Dj] f32, unweighted)."""
+
+    def __init__(self, F, Jc, multiepoch=1, layout=LAYOUT_SIMPLE, device=0):
+        lib = load_library()
+        F = np.ascontiguousarray(F, dtype=np.float32)
+        Jc = np.ascontiguousarray(Jc, dtype=np.float32)
+        if F.ndim != 2 or Jc.ndim != 2 or Jc.shape[0] != F.shape[0] + 1:
+            raise ValueError("expected F [N,Dt] and Jc [N+1,Dj], got %s and %s" % (F.shape, Jc.shape))
+        self.N, self.Dt = F.shape
+        self.Dj = Jc.shape[1]
+        self.multiepoch = int(multiepoch)
+        self.device = int(device)
+        self._h = C.c_void_p()
+        _check(lib.snk_db_create(C.byref(self._h), self.device, self.N, self.Dt, self.Dj, self.multiepoch,
+                                 _ptr(F, C.c_float), _ptr(Jc, C.c_float), layout))
+        n, npr, dt, dj, m, jd = C.c_int64(), C.c_int64(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(lib.snk_db_info(self._h, C.byref(n), C.byref(npr), C.byref(dt), C.byref(dj), C.byref(m), C.byref(jd)))
+        self.Nprime, self.joint_dim = npr.value, jd.value
+        self.Djq = self.joint_dim - self.multiepoch * self.Dt
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            load_library().snk_db_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    # -- configuration
+    def set_weights(self, wt, wj):
+        wt = np.ascontiguousarray(wt, dtype=np.float64).ravel()
+        wj = np.ascontiguousarray(wj, dtype=np.float64).ravel()
+        if wt.size != self.Dt or wj.size != self.Dj:
+            raise ValueError("weight vectors must have %d and %d entries" % (self.Dt, self.Dj))
+        _check(load_library().snk_db_set_weights(self._h, _ptr(wt, C.c_double), _ptr(wj, C.c_double)))
+
+    def set_engine(self, engine):
+        _check(load_library().snk_db_set_engine(self._h, int(engine)))
+
+    def counters(self, reset=False):
+        out = np.zeros(4, dtype=np.int64)
+        _check(load_library().snk_db_counters(self._h, _ptr(out, C.c_int64), int(reset)))
+        return {"queries": int(out[0]), "recertified": int(out[1]), "launches": int(out[2])}
+
+    # -- searches (host arrays in, host arrays out)
+    def knn(self, Q, k, space=SPACE_TARGET):
+        D = self.Dt if space == SPACE_TARGET else self.joint_dim
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        if Q.ndim != 2 or Q.shape[1] != D:
+            raise ValueError("queries must be [nq, %d], got %s" % (D, Q.shape))
+        nq = Q.shape[0]
+        dist = np.empty((nq, k), dtype=np.float64)
+        idx = np.empty((nq, k), dtype=np.int64)
+        _check(load_library().snk_knn(self._h, space, _ptr(Q, C.c_double), nq, int(k), _ptr(dist, C.c_double),
+                                      _ptr(idx, C.c_int64)))
+        return dist, idx
+
+    def greedy_batch(self, targets_list, start_states=None, return_dists=False):
+        m = self.multiepoch
+        lens = np.array([t.shape[0] for t in targets_list], dtype=np.int64)
+        for t in targets_list:
+            if t.ndim != 2 or t.shape[1] != self.Dt:
+                raise ValueError("each target utterance must be [T, %d]" % self.Dt)
+            if t.shape[0] < m:
+                raise ValueError("Not enough data points to segment array in 'cut' mode")  # segmentaxis.py:94-96
+        B = len(targets_list)
+        if B == 0:
+            return ([], []) if return_dists else []
+        cat = np.ascontiguousarray(np.concatenate(targets_list, axis=0), dtype=np.float64)
+        steps = lens // m
+        paths = np.empty(int(steps.sum()), dtype=np.int64)
+        dists = np.empty(int(steps.sum()), dtype=np.float64) if return_dists else None
+        ss = None
+        if start_states is not None:
+            ss = np.ascontiguousarray(start_states, dtype=np.int64)
+        _check(load_library().snk_greedy_batch(self._h, _ptr(cat, C.c_double), _ptr(lens, C.c_int64), B,
+                                               _ptr(ss, C.c_int64), _ptr(paths, C.c_int64), _ptr(dists, C.c_double)))
+        cuts = np.cumsum(steps)[:-1]
+        p = [x.tolist() for x in np.split(paths, cuts)]
+        if return_dists:
+            return p, np.split(dists, cuts)
+        return p
+
+    def candidate_distances(self, cand, targets):
+        cand = np.ascontiguousarray(cand, dtype=np.int64)
+        targets = np.ascontiguousarray(targets, dtype=np.float64)
+        T, K = cand.shape
+        if targets.shape != (T, self.Dt):
+            raise ValueError("targets must be [%d, %d]" % (T, self.Dt))
+        dist = np.empty((T, K), dtype=np.float64)
+        _check(load_library().snk_candidate_distances(self._h, _ptr(cand, C.c_int64), _ptr(targets, C.c_double), T, K,
+                                                      _ptr(dist, C.c_double)))
+        return dist
+
+    def join_tiles(self, cand_list):
+        K = cand_list[0].shape[1]
+        lens = np.array([c.shape[0] for c in cand_list], dtype=np.int64)
+        cat = np.ascontiguousarray(np.concatenate(cand_list, axis=0), dtype=np.int64)
+        ntiles = int(np.maximum(lens - 1, 0).sum())
+        tiles = np.empty((ntiles, K, K), dtype=np.float32)
+        _check(load_library().snk_join_tiles(self._h, _ptr(cat, C.c_int64), _ptr(lens, C.c_int64), len(cand_list), K,
+                                             _ptr(tiles, C.c_float)))
+        return tiles
+
+    def join_viterbi_batch(self, cand_list, dist_list, flags=0):
+        B = len(cand_list)
+        if B == 0:
+            return [], np.zeros(0), np.zeros(0), np.zeros(0)
+        K = cand_list[0].shape[1]
+        lens = np.array([c.shape[0] for c in cand_list], dtype=np.int64)
+        cand = np.ascontiguousarray(np.concatenate(cand_list, axis=0), dtype=np.int64).reshape(-1, K)
+        dist = np.ascontiguousarray(np.concatenate(dist_list, axis=0), dtype=np.float64).reshape(-1, K)
+        if cand.shape != dist.shape:
+            raise ValueError("candidates and distances differ in shape")
+        paths = np.empty(max(int(lens.sum()), 1), dtype=np.int64)
+        plen = np.empty(B, dtype=np.int64)
+        pcost, tcost, jcost = (np.empty(B, dtype=np.float64) for _ in range(3))
+        _check(load_library().snk_join_viterbi_batch(self._h, _ptr(cand, C.c_int64), _ptr(dist, C.c_double),
+                                                     _ptr(lens, C.c_int64), B, K, flags, _ptr(paths, C.c_int64),
+                                                     _ptr(plen, C.c_int64), _ptr(pcost, C.c_double),
+                                                     _ptr(tcost, C.c_double), _ptr(jcost, C.c_double)))
+        out, off = [], 0
+        for b in range(B):
+            out.append(paths[off:off + plen[b]].tolist() if plen[b] > 0 else [])
+            off += lens[b]
+        return out, pcost, tcost, jcost
+
+    def greedy_path_scores(self, targets, path, twidths, jwidths):
+        targets = np.ascontiguousarray(targets, dtype=np.float64)
+        path = np.ascontiguousarray(path, dtype=np.int64)
+        tw = np.ascontiguousarray(twidths, dtype=np.int32)
+        jw = np.ascontiguousarray(jwidths, dtype=np.int32)
+        P = path.size
+        ts = np.empty((P, tw.size), dtype=np.float64)
+        js = np.empty((max(P - 1, 0), jw.size), dtype=np.float64)
+        _check(load_library().snk_greedy_path_scores(self._h, _ptr(targets, C.c_double), targets.shape[0],
+                                                     _ptr(path, C.c_int64), P, _ptr(tw, C.c_int32), tw.size,
+                                                     _ptr(jw, C.c_int32), jw.size, _ptr(ts, C.c_double),
+                                                     _ptr(js, C.c_double)))
+        return ts, js

@@ -1,0 +1,325 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed
+golden vectors.  Tolerances are BASELINE.json's: unit sequences bit-exact except at cost ties
+within 1e-6 relative, costs within 1e-5 relative."""
+import numpy as np
+import pytest
+
+from conftest import epoch_config, halfphone_config
+from oracle import snickery_oracle as O
+from snickery_b200 import GpuKDTree, GpuStashableKDTree, Synthesiser, engine, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+TIE_RTOL = 1e-6    # north_star: index mismatches allowed only at cost ties within 1e-6 relative
+COST_RTOL = 1e-5   # north_star: target / join / path costs within 1e-5 relative
+
+ENGINES = [engine.ENGINE_SIMT, engine.ENGINE_AUTO]
+
+
+def assert_knn_matches(dist, idx, ref_dist, ref_idx):
+    """Same neighbours except where distances tie within TIE_RTOL; distances agree to COST_RTOL."""
+    np.testing.assert_allclose(dist, ref_dist, rtol=COST_RTOL, atol=1e-12)
+    bad = idx != ref_idx
+    if bad.any():
+        rel = np.abs(dist - ref_dist)[bad] / np.maximum(ref_dist[bad], 1e-300)
+        assert np.all(rel <= TIE_RTOL), "index mismatch that is not a tie"
+        # a tie may permute neighbours: each row must still hold the same multiset up to ties
+        for q in np.flatnonzero(bad.any(axis=1)):
+            for j in np.flatnonzero(bad[q]):
+                tied = np.abs(ref_dist[q] - ref_dist[q, j]) <= TIE_RTOL * max(ref_dist[q, j], 1e-300)
+                assert idx[q, j] in ref_idx[q, tied] or tied[-1], "neighbour set differs beyond a tie"
+
+
+def assert_greedy_path_ok(oracle, uf, path, dists, start_state=-1):
+    """Every GPU step must be optimal (within a tie) given the GPU's own previous choice."""
+    ref_path, ref_d = oracle.greedy_joint_search(uf, start_state=start_state, return_dists=True)
+    if path == ref_path:
+        np.testing.assert_allclose(dists, ref_d, rtol=COST_RTOL, atol=1e-12)
+        return 0
+    wt = oracle.window_targets(np.asarray(uf, dtype=np.float64))
+    n = oracle.current_join_rep.shape[1]
+    prev = np.zeros(n) if start_state < 0 else oracle.prev_join_rep[start_state]
+    assert len(path) == len(ref_path)
+    ndiff = 0
+    for t, ix in enumerate(path):
+        d_all = oracle.greedy_step_distances(prev, wt[t])
+        best = d_all.min()
+        assert d_all[ix] <= best * (1 + TIE_RTOL) + 1e-300, "step %d: chose %d (%.17g) over optimum %.17g" % (t, ix, d_all[ix], best)
+        assert abs(dists[t] - d_all[ix]) <= COST_RTOL * max(d_all[ix], 1e-12)
+        ndiff += int(ix != int(np.argmin(d_all)))
+        prev = oracle.current_join_rep[ix]
+    return ndiff
+
+
+@pytest.fixture(scope="module")
+def epoch_pair(golden_epoch):
+    cfg = epoch_config()
+    o = O.OracleSynthesiser(cfg, golden_epoch["F"], golden_epoch["Jc"])
+    o.get_tree_for_greedy_search()
+    g = Synthesiser(cfg, golden_epoch["F"], golden_epoch["Jc"])
+    return o, g
+
+
+@pytest.fixture(scope="module")
+def hp_pair(golden_halfphone):
+    cfg = halfphone_config(n_candidates=12)
+    o = O.OracleSynthesiser(cfg, golden_halfphone["F"], golden_halfphone["Jc"])
+    o.build_acoustic_tree()
+    g = Synthesiser(cfg, golden_halfphone["F"], golden_halfphone["Jc"])
+    return o, g
+
+
+# ------------------------------------------------------------------------------------ k-NN
+@pytest.mark.parametrize("eng", ENGINES)
+def test_knn_golden_halfphone(hp_pair, golden_halfphone, eng):
+    o, g = hp_pair
+    g.db.set_engine(eng)
+    cand, dist = g.preselect_units_acoustic(golden_halfphone["targets"])
+    assert cand.dtype == np.int64 and dist.dtype == np.float64 and cand.shape == (30, 12)
+    assert_knn_matches(dist, cand, golden_halfphone["knn_dist"], golden_halfphone["knn_idx"])
+    assert np.all(np.diff(dist, axis=1) >= 0)
+
+
+@pytest.mark.parametrize("eng", ENGINES)
+@pytest.mark.parametrize("k", [1, 7, 50])
+def test_knn_joint_space_vs_ckdtree(epoch_pair, k, eng):
+    o, g = epoch_pair
+    g.db.set_engine(eng)
+    rng = np.random.default_rng(k)
+    combined = o.combined_rep()
+    q = combined[rng.integers(0, combined.shape[0], 37)] + 0.05 * rng.standard_normal((37, combined.shape[1]))
+    rd, ri = o.joint_tree.query(q, k=k)
+    d, i = g.joint_tree.query(q, k=k)
+    assert d.shape == rd.shape and i.shape == ri.shape
+    assert_knn_matches(d.reshape(37, -1), i.reshape(37, -1), rd.reshape(37, -1), ri.reshape(37, -1))
+
+
+def test_kdtree_adapter_scipy_conventions():
+    rng = np.random.default_rng(1)
+    data = rng.standard_normal((500, 14)).astype(np.float32).astype(np.float64)
+    import scipy.spatial
+    ref = scipy.spatial.cKDTree(data, leafsize=100, balanced_tree=False)
+    t = GpuKDTree(data, leafsize=100, balanced_tree=False)
+    assert t.exact_storage and t.n == 500 and t.m == 14
+    x = rng.standard_normal((9, 14))
+    for k in (1, 3):
+        rd, ri = ref.query(x, k=k, eps=0.0)
+        d, i = t.query(x, k=k, eps=10.0)          # eps is honoured trivially by an exact answer
+        assert d.shape == rd.shape and i.shape == ri.shape
+        assert np.array_equal(i, ri)
+        np.testing.assert_allclose(d, rd, rtol=1e-12)
+    rd, ri = ref.query(x[0], k=1)
+    d, i = t.query(x[0], k=1)
+    assert np.isscalar(d) and i == ri and abs(d - rd) <= 1e-12 * rd
+    rd, ri = ref.query(x[0].reshape(1, -1), k=1)   # the shape greedy_joint_search uses (synth_simple.py:488-490)
+    d, i = t.query(x[0].reshape(1, -1), k=1)
+    assert d.shape == rd.shape == (1,) and i[0] == ri[0]
+    # k larger than n: scipy pads with (inf, n)
+    small = GpuKDTree(data[:5])
+    d, i = small.query(x[:2], k=8)
+    rd, ri = scipy.spatial.cKDTree(data[:5]).query(x[:2], k=8)
+    assert np.array_equal(i, ri) and np.array_equal(np.isinf(d), np.isinf(rd))
+    # exact duplicates: lowest index first
+    dup = GpuKDTree(np.vstack([data[:10], data[:10]]))
+    d, i = dup.query(data[3], k=2)
+    assert i.tolist() == [3, 13] and np.all(d == 0.0)
+    # sklearn-style wrapper
+    s = GpuStashableKDTree(data, leaf_size=100, metric="euclidean")
+    d, i = s.query(x, k=1)
+    assert d.shape == (9, 1) and i.shape == (9, 1)
+
+
+# ------------------------------------------------------------------------------------ greedy
+@pytest.mark.parametrize("eng", ENGINES)
+def test_greedy_golden(epoch_pair, golden_epoch, eng):
+    o, g = epoch_pair
+    g.db.set_engine(eng)
+    utts = [golden_epoch["targets_%d" % i] for i in range(3)]
+    paths, dists = g.greedy_joint_search_batch(utts, return_dists=True)
+    for i in range(3):
+        assert len(paths[i]) == 121 // 6
+        if paths[i] == golden_epoch["path_%d" % i].tolist():
+            np.testing.assert_allclose(dists[i], golden_epoch["dist_%d" % i], rtol=COST_RTOL)
+        else:
+            assert_greedy_path_ok(o, utts[i], paths[i], dists[i])
+    # single-utterance call site (synth_simple.py:413)
+    assert g.greedy_joint_search(utts[0]) == paths[0]
+
+
+@pytest.mark.parametrize("eng", ENGINES)
+def test_greedy_identity_known_answer(epoch_pair, golden_epoch, eng):
+    """The reference's own assertion (synth_simple.py:909-928): DB frames in, identity path out."""
+    o, g = epoch_pair
+    g.db.set_engine(eng)
+    start, m, n = int(golden_epoch["identity_start"]), 6, 12
+    tf = o.train_unit_features[start:start + m * n]
+    path, d = g.greedy_joint_search_batch([tf], [start], return_dists=True)
+    assert path[0] == golden_epoch["identity_path"].tolist()
+    assert np.all(d[0] == 0.0)
+
+
+@pytest.mark.parametrize("eng", ENGINES)
+def test_greedy_ragged_batch_and_multiepoch1(golden_epoch, eng):
+    cfg = epoch_config(multiepoch=1)
+    o = O.OracleSynthesiser(cfg, golden_epoch["F"], golden_epoch["Jc"])
+    o.get_tree_for_greedy_search()
+    g = Synthesiser(cfg, golden_epoch["F"], golden_epoch["Jc"])
+    g.db.set_engine(eng)
+    p = g.greedy_joint_search(golden_epoch["m1_targets"])
+    assert p == golden_epoch["m1_path"].tolist()
+    tg = syn.make_targets(golden_epoch["F"], 5, 33, seed=21)
+    utts = [O.weight(x[: n], o.target_weight_vector) for x, n in zip(tg, (33, 1, 17, 33, 8))]
+    paths, dists = g.greedy_joint_search_batch(utts, return_dists=True)
+    for u, p, d in zip(utts, paths, dists):
+        assert len(p) == u.shape[0]
+        assert_greedy_path_ok(o, u, p, d)
+
+
+def test_greedy_too_short_utterance_raises(epoch_pair, golden_epoch):
+    o, g = epoch_pair
+    with pytest.raises(ValueError):
+        g.greedy_joint_search(golden_epoch["targets_0"][:5])
+
+
+def test_reweighting_matches_fresh_oracle(golden_epoch):
+    """balance_stream_weights.py:84-88: new weights, rebuilt 'tree', search again."""
+    cfg = epoch_config()
+    g = Synthesiser(cfg, golden_epoch["F"], golden_epoch["Jc"])
+    new = {"target_stream_weights": [0.7, 0.3], "join_stream_weights": [0.4, 0.1, 0.1, 0.4], "join_cost_weight": 0.35}
+    g.reconfigure_settings(new)
+    cfg2 = dict(cfg, **new)
+    o = O.OracleSynthesiser(cfg2, golden_epoch["F"], golden_epoch["Jc"])
+    o.get_tree_for_greedy_search()
+    x = syn.make_targets(golden_epoch["F"], 1, 60, seed=33)[0]
+    uf = O.weight(x, o.target_weight_vector)
+    assert np.array_equal(g.target_weight_vector, o.target_weight_vector)
+    paths, dists = g.greedy_joint_search_batch([uf], return_dists=True)
+    assert_greedy_path_ok(o, uf, paths[0], dists[0])
+
+
+def test_per_stream_scores(epoch_pair, golden_epoch):
+    o, g = epoch_pair
+    uf = golden_epoch["targets_0"]
+    p = golden_epoch["path_0"].tolist()
+    ts, js = g.get_scores_per_stream(uf, p)
+    np.testing.assert_allclose(js, golden_epoch["jscores_0"], rtol=1e-12, atol=1e-300)
+    # target scores: sum over the m frames of the step (equals the reference for m = 1)
+    wt = o.window_targets(uf)
+    sq = (o.windowed_unit_features[p] - wt) ** 2
+    want = np.zeros((len(p), 2))
+    for j in range(6):
+        want[:, 0] += sq[:, j * 61: j * 61 + 60].sum(axis=1)
+        want[:, 1] += sq[:, j * 61 + 60]
+    np.testing.assert_allclose(ts, want, rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------ join + Viterbi
+def test_candidate_distances_golden(hp_pair, golden_halfphone):
+    o, g = hp_pair
+    d = g.candidate_target_distances(golden_halfphone["q_cand"], golden_halfphone["targets"])
+    np.testing.assert_allclose(d, golden_halfphone["q_dist"], rtol=1e-12)
+
+
+def test_join_tiles_vs_oracle(hp_pair, golden_halfphone):
+    o, g = hp_pair
+    cand = golden_halfphone["q_cand"]
+    tiles = g.db.join_tiles([cand])
+    assert tiles.shape == (cand.shape[0] - 1, 12, 12) and tiles.dtype == np.float32
+    cache = o.join_cost_cache(cand)
+    for t in range(cand.shape[0] - 1):
+        want = np.array([[cache.get((int(a), int(b)), np.inf) for b in cand[t + 1]] for a in cand[t]])
+        assert np.array_equal(np.isinf(tiles[t]), np.isinf(want))
+        fin = np.isfinite(want)
+        np.testing.assert_allclose(tiles[t][fin], want[fin], rtol=COST_RTOL, atol=0)
+        assert np.all(tiles[t][fin & (want == 0)] == 0)         # natural joins stay exactly free
+    np.testing.assert_allclose(tiles[0], golden_halfphone["tile_0"], rtol=COST_RTOL)
+
+
+def check_viterbi(o, cand, dist, path, pcost, tcost, jcost):
+    ref_path, ref_cost = O.viterbi_search_numpy(o, cand, dist, return_cost=True)
+    if not ref_path:
+        assert path == []
+        return
+    assert len(path) == len(ref_path)
+    tc, jc, tot = o.path_costs(cand, dist, path)       # float64 cost of the GPU's path
+    assert tot <= ref_cost * (1 + TIE_RTOL), "GPU path is worse than the optimum beyond a tie"
+    if path != ref_path:
+        assert abs(tot - ref_cost) <= TIE_RTOL * ref_cost
+    assert abs(pcost - tot) <= COST_RTOL * tot
+    assert abs(tcost - tc) <= COST_RTOL * max(tc, 1e-12) and abs(jcost - jc) <= COST_RTOL * max(jc, 1e-12) + 1e-12
+
+
+def test_viterbi_golden(hp_pair, golden_halfphone):
+    o, g = hp_pair
+    gh = golden_halfphone
+    paths, pc, tc, jc = g.viterbi_search_batch([gh["knn_idx"], gh["q_cand"]], [gh["knn_dist"], gh["q_dist"]],
+                                               return_costs=True)
+    assert paths[0] == gh["vit_path_f64"].tolist() or paths[0] == gh["vit_path_fst32"].tolist()
+    assert abs(pc[0] - float(gh["vit_cost_f64"])) <= COST_RTOL * float(gh["vit_cost_f64"])
+    assert paths[1] == gh["q_path"].tolist()
+    assert abs(pc[1] - float(gh["q_cost"])) <= COST_RTOL * float(gh["q_cost"])
+    assert abs(tc[1] - float(gh["q_tcost"])) <= COST_RTOL * float(gh["q_tcost"])
+    assert abs(jc[1] - float(gh["q_jcost"])) <= COST_RTOL * float(gh["q_jcost"])
+    tiny = g.viterbi_search(gh["knn_idx"][:5, :4], gh["knn_dist"][:5, :4])
+    assert tiny == gh["tiny_path"].tolist()
+    # the single-utterance call site (synth_halfphone.py:1625)
+    assert g.viterbi_search(gh["knn_idx"], gh["knn_dist"]) == paths[0]
+
+
+def test_viterbi_quirks(hp_pair):
+    o, g = hp_pair
+    n = o.unit_end_data.shape[0]
+    d = np.ones((3, 2))
+    assert g.viterbi_search(np.array([[5, 6]]), np.ones((1, 2))) == []
+    assert g.viterbi_search(np.array([[0, 0], [5, 6], [7, 8]]), d) == []
+    assert g.viterbi_search(np.array([[4, 5], [n - 1, n - 1], [7, 8]]), d) == []
+    assert g.viterbi_search(np.array([[4, -1], [5, 5], [-1, 6]]), d) == [4, 5, 6]
+    paths, pc, tc, jc = g.viterbi_search_batch([np.array([[4, 900], [5, 901], [6, 902]])], [np.zeros((3, 2))], True)
+    assert pc[0] == 0.0 and paths[0] == [4, 5, 6]         # lowest column wins the exact tie
+
+
+@pytest.mark.parametrize("K", [1, 5, 30, 50, 64])
+def test_viterbi_random_lattices(hp_pair, K):
+    o, g = hp_pair
+    rng = np.random.default_rng(100 + K)
+    n = o.unit_end_data.shape[0]
+    cands, dists = [], []
+    for b in range(6):
+        T = int(rng.integers(2, 40))
+        c = rng.integers(1, n - 1, size=(T, K))
+        c[rng.random((T, K)) < 0.15] = -1
+        if b % 2:
+            runs = rng.integers(1, n - T - 2)
+            c[:, 0] = np.arange(runs, runs + T)               # a natural run is always available
+        if b == 3:
+            c[rng.integers(0, T)] = -1                         # a fully padded frame blocks every path
+        c[0, -1] = 0
+        c[-1, -1] = n - 1
+        cands.append(c)
+        dists.append(o.candidate_distances(c, rng.standard_normal((T, 184))) if b % 3 else rng.random((T, K)))
+    paths, pc, tc, jc = g.viterbi_search_batch(cands, dists, return_costs=True)
+    for b in range(6):
+        check_viterbi(o, cands[b], dists[b], paths[b], pc[b], tc[b], jc[b])
+
+
+def test_viterbi_beam1_is_greedy_over_candidates(hp_pair, golden_halfphone):
+    o, g = hp_pair
+    cand, dist = golden_halfphone["knn_idx"], golden_halfphone["knn_dist"]
+    path = g.viterbi_search_batch([cand], [dist], greedy=True)[0]
+    # restate: keep only the cheapest reachable state after every step
+    T, K = cand.shape
+    cache = o.join_cost_cache(cand)
+    cur = {j: 0.0 for j in range(K)}
+    chosen = []
+    for t in range(T - 1):
+        nxt = {}
+        for jb in range(K):
+            best = min(((cur[ja] + dist[t, ja] + cache[(int(cand[t, ja]), int(cand[t + 1, jb]))], ja)
+                        for ja in cur if (int(cand[t, ja]), int(cand[t + 1, jb])) in cache), default=None)
+            if best is not None:
+                nxt[jb] = best
+        jb = min(nxt, key=lambda j: (nxt[j][0], j))
+        chosen.append(nxt[jb][1])
+        cur = {jb: nxt[jb][0]}
+    chosen.append(list(cur)[0])
+    assert path[1:] == [int(cand[t, j]) for t, j in enumerate(chosen)][1:]
