@@ -70,6 +70,17 @@ int snk_db_set_engine(snk_db *db, int engine);
  * [2] kernels launched, [3] reserved */
 int snk_db_counters(const snk_db *db, int64_t counters[4], int reset);
 
+/* ---- kernel timing for bench.py -----------------------------------------------------------
+ * When enabled, CUDA events bracket every launch of the three hot kernels on the launching
+ * stream.  snk_db_profile_read synchronises, then returns the summed device time, the number
+ * of launches and the algorithmic work (SNK_PROF_KNN: FLOPs 2*nq*rows*D; SNK_PROF_JOIN /
+ * SNK_PROF_VITERBI: bytes) since the last reset.                      */
+#define SNK_PROF_KNN 0
+#define SNK_PROF_JOIN 1
+#define SNK_PROF_VITERBI 2
+int snk_db_profile_enable(snk_db *db, int enable);
+int snk_db_profile_read(snk_db *db, int which, double *total_ms, int64_t *launches, double *work, int reset);
+
 /* ---- k-NN: tree.query(X, k) ------------------------------------------------------------
  * Replaces cKDTree.query / sklearn KDTree.query (synth_halfphone.py:1364,1384;
  * synth_simple.py:490; StashableKDTree.py).  Q is float64 [nq, D] already weighted like

@@ -135,6 +135,7 @@ int snk_db_destroy(snk_db *db) {
     cudaSetDevice(db->device);
     if (db->stream) cudaStreamSynchronize(db->stream);
     snk_tc_destroy(db);
+    for (auto &r : db->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     cudaFree(db->F_raw); cudaFree(db->Jc_raw); cudaFree(db->wt); cudaFree(db->wj);
     cudaFree(db->Fw32); cudaFree(db->Jw32); cudaFree(db->G16); cudaFree(db->S16);
     cudaFree(db->nrm_t16); cudaFree(db->nrm_j16); cudaFree(db->err_t16);
@@ -182,6 +183,38 @@ int snk_db_counters(const snk_db *db, int64_t counters[4], int reset) {
     SNK_CHECK(db && counters, "NULL argument");
     memcpy(counters, db->counters, sizeof(db->counters));
     if (reset) memset(const_cast<snk_db *>(db)->counters, 0, sizeof(db->counters));
+    return 0;
+}
+
+int snk_db_profile_enable(snk_db *db, int enable) {
+    SNK_CHECK(db, "db is NULL");
+    db->prof_on = enable != 0;
+    return 0;
+}
+
+int snk_db_profile_read(snk_db *db, int which, double *total_ms, int64_t *launches, double *work, int reset) {
+    SNK_CHECK(db, "db is NULL");
+    SNK_CUDA(cudaSetDevice(db->device));
+    SNK_CUDA(cudaDeviceSynchronize());
+    double ms = 0.0, w = 0.0;
+    int64_t n = 0;
+    for (auto &r : db->prof) {
+        if (r.which != which) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms += t; w += r.work; ++n; }
+    }
+    cudaGetLastError();
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = n;
+    if (work) *work = w;
+    if (reset) {
+        std::vector<snk_db::prof_rec> keep;
+        for (auto &r : db->prof) {
+            if (r.which == which) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+            else keep.push_back(r);
+        }
+        db->prof.swap(keep);
+    }
     return 0;
 }
 

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <math.h>
+#include <vector>
 #include "snk_b200.h"
 
 void snk_set_error(const char *fmt, ...);
@@ -89,6 +90,24 @@ struct snk_db {
     cudaEvent_t ev = nullptr;
     snk_buf ws_q, ws_dist, ws_list, ws_misc, ws_io, ws_io2, ws_tiles, ws_bp, ws_tc, ws_h0, ws_h1, ws_h2, ws_h3;
     int64_t counters[4] = {0, 0, 0, 0};
+    // optional kernel timing (snk_db_profile_*)
+    bool prof_on = false;
+    struct prof_rec { int which; cudaEvent_t e0, e1; double work; };
+    std::vector<prof_rec> prof;
+};
+
+// bracket a hot-kernel launch with events when profiling is enabled
+struct snk_prof_scope {
+    snk_db *db; cudaStream_t st; int idx;
+    snk_prof_scope(snk_db *d, int which, double work, cudaStream_t s) : db(d), st(s), idx(-1) {
+        if (!db->prof_on) return;
+        snk_db::prof_rec r{which, nullptr, nullptr, work};
+        if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+        cudaEventRecord(r.e0, st);
+        db->prof.push_back(r);
+        idx = (int)db->prof.size() - 1;
+    }
+    ~snk_prof_scope() { if (idx >= 0) cudaEventRecord(db->prof[idx].e1, st); }
 };
 
 snk_space snk_make_space(const snk_db *db, int space);

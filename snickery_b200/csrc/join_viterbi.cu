@@ -336,8 +336,11 @@ int launch_tiles(snk_db *db, const int64_t *d_cand, int K, const int *d_tile2fra
     const size_t smem = tile_smem_bytes(K, db->ldJ32);
     SNK_CHECK(smem <= 227 * 1024, "n_candidates = %d needs %zu bytes of shared memory", K, smem);
     SNK_CUDA(cudaFuncSetAttribute(join_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    join_tile_kernel<<<(unsigned)ntiles, threads, smem, st>>>(db->Jw32, db->ldJ32, db->N, d_cand, K, d_tile2frame,
-                                                              d_tiles);
+    {   // algorithmic bytes per tile: 2*K*Dj*4 gathered + K*K*4 written + 2*K*8 ids
+        snk_prof_scope prof(db, SNK_PROF_JOIN, (double)ntiles * (2.0 * K * db->Dj * 4 + (double)K * K * 4 + 2.0 * K * 8), st);
+        join_tile_kernel<<<(unsigned)ntiles, threads, smem, st>>>(db->Jw32, db->ldJ32, db->N, d_cand, K, d_tile2frame,
+                                                                  d_tiles);
+    }
     SNK_CUDA(cudaGetLastError());
     db->counters[2] += 1;
     return 0;
@@ -370,9 +373,12 @@ int snk_join_viterbi_batch_dev(snk_db *db, const int64_t *d_cand, const double *
     SNK_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope
     SNK_TRY(launch_tiles(db, d_cand, K, d_t2f, ntiles, (float *)db->ws_tiles.p, st));
     const int threads = (int)snk_round_up(K, 32);
-    viterbi_kernel<<<B, threads, 3 * K * sizeof(float), st>>>(d_meta, d_cand, d_tdist, (const float *)db->ws_tiles.p, K,
-                                                              db->N, flags, (short *)db->ws_bp.p, d_paths, d_path_len,
-                                                              d_path_cost, d_tcost, d_jcost);
+    {   // per (utt, t): K*K*4 tile read + K*8 target costs + K*2 backpointers
+        snk_prof_scope prof(db, SNK_PROF_VITERBI, (double)ntiles * ((double)K * K * 4 + K * 8.0 + K * 2.0), st);
+        viterbi_kernel<<<B, threads, 3 * K * sizeof(float), st>>>(d_meta, d_cand, d_tdist, (const float *)db->ws_tiles.p,
+                                                                  K, db->N, flags, (short *)db->ws_bp.p, d_paths,
+                                                                  d_path_len, d_path_cost, d_tcost, d_jcost);
+    }
     SNK_CUDA(cudaGetLastError());
     db->counters[2] += 1;
     return 0;

@@ -117,7 +117,8 @@ struct warp_list {
             const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
             const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
             const int op = __shfl_xor_sync(0xffffffffu, bp, off);
-            if (pair_lt(bv, bi, ov, oi)) { bv = ov; bi = oi; bp = op; }
+            // ties (e.g. several still-empty slots) must resolve identically in every lane
+            if (pair_lt(bv, bi, ov, oi) || (bv == ov && bi == oi && op < bp)) { bv = ov; bi = oi; bp = op; }
         }
         tv = bv; ti = bi; tpos = bp;
     }
@@ -275,7 +276,10 @@ int snk_shortlist_simt(snk_db *db, const snk_space &sp, const float *dQ32, int l
         for (int64_t rb = 0; rb < sp.rows; rb += rchunk) {
             const int64_t rn = std::min<int64_t>(rchunk, sp.rows - rb);
             dim3 grid((unsigned)snk_cdiv(rn, TR), (unsigned)snk_cdiv(qn, TQ));
-            dist_f32_kernel<<<grid, 256, 0, st>>>(sd, dQ32 + qb * ldq, ldq, qn, rb, rb + rn, dist, rchunk);
+            {
+                snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)qn * (double)rn * sp.D, st);
+                dist_f32_kernel<<<grid, 256, 0, st>>>(sd, dQ32 + qb * ldq, ldq, qn, rb, rb + rn, dist, rchunk);
+            }
             SNK_CUDA(cudaGetLastError());
             db->counters[2] += 1;
             SNK_TRY(snk_topk_scan(db, dist, nullptr, qn, rn, rchunk, (int)rb, KP, first, d_val + qb * KP,

@@ -1,11 +1,509 @@
-// placeholder until the tcgen05 kernel lands
+// Tensor-core shortlist kernel: brute-force target/joint cost as a dense contraction on tcgen05.
+//
+// Replaces the KD-tree lookup of the reference (cKDTree.query at script/synth_simple.py:490 and
+// script/synth_halfphone.py:1364) with an exact scan: for a tile of 128 queries x 128 database
+// rows the kernel accumulates x~ . y~ in TMEM (fp16 operands, fp32 accumulate), turns it into the
+// key ||y~||^2 - 2 x~.y~ in the epilogue and keeps, per query, the smallest keys it has seen.
+//
+//  * operands are fp16 copies of the weighted rows (weights.cu); their squared norms are taken
+//    from the ROUNDED values, so key + ||x~||^2 is the squared distance between the rounded
+//    vectors and |sqrt(key + ||x~||^2) - true distance| <= ||x - x~|| + ||y - y~|| (triangle
+//    inequality).  rerank.cu uses that bound to certify the float64 re-ranked answer exact.
+//  * the multiepoch joint row [start_join(u) || F(u) .. F(u+m-1)] is never materialised: K-block j
+//    of the target part is the TMA box of rows u0+j .. u0+j+127 of the frame matrix G16.
+//  * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread) + TMEM allocator,
+//    warps 2..5 = epilogue (one thread per query / TMEM lane).  The 128-query operand tile stays
+//    resident in shared memory; database tiles stream through a 4-stage mbarrier ring; two TMEM
+//    accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+//  * each CTA scans one (query tile, database chunk) pair; per-chunk results are merged by
+//    snk_topk_scan.
 #include "common.cuh"
-bool snk_tc_supported(const snk_db *, const snk_space &, int) { return false; }
-int snk_tc_prepare(snk_db *) { return 0; }
-void snk_tc_destroy(snk_db *) {}
-int snk_tc_query_ld(const snk_db *, int) { return 0; }
-const short *snk_tc_qmap(const snk_db *, int) { return nullptr; }
-int snk_shortlist_tc(snk_db *, int, const __half *, int, int64_t, int, int, float *, int *, float *, cudaStream_t) {
-    snk_set_error("tensor-core engine not built");
-    return 1;
+#include <cuda.h>
+#include <algorithm>
+#include <string.h>
+
+namespace {
+
+constexpr int BM = 128;        // queries per tile (UMMA M)
+constexpr int BN = 128;        // database rows per tile (UMMA N)
+constexpr int BK = 64;         // fp16 elements per K-block = one 128-byte swizzle row
+constexpr int STAGES = 4;
+constexpr int MAXKB = 10;
+constexpr int LSZ = 8;         // per-(query, chunk) list length of the fused epilogue
+constexpr int TILE_BYTES = BM * BK * 2;   // 16 KiB (A and B tiles have the same shape)
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 256;       // two 128-column fp32 accumulators
+
+struct tc_params {
+    int nkb;
+    int kb_map[MAXKB];      // 0: join-context map (S16), 1: target-frame map (G16)
+    int kb_rowoff[MAXKB];
+    int kb_col[MAXKB];
+    int kb_ksteps[MAXKB];
+    int64_t row_lo, row_hi; // rows scanned by this launch
+    int64_t chunk_rows;     // multiple of BN
+    int nchunks;
+    int64_t nq;
+    const float *nrm;       // [rows] squared norms of the fp16 rows
+    float *oval;            // fused : [nq_pad, nchunks, LSZ] keys (ascending)
+    int *oid;               //         row ids
+    float *odist;           // store : [nq, ldo] keys of rows row_lo ..
+    int64_t ldo;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// A wait that cannot hang the GPU: a barrier that never completes (bad tensor map, lost commit)
+// traps after ~2 s instead of spinning forever.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 x fp16 -> fp32
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzled operand tile: rows of 64 fp16 (128 B), 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
+    d |= (uint64_t)0 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=128
+constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// ---------------------------------------------------------------- kernel
+template <bool kStore>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapS,
+              const __grid_constant__ CUtensorMap mapG, const tc_params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles need 1024 B alignment
+    uint8_t *gbase = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t sA = sbase;
+    const uint32_t sB = sA + (uint32_t)p.nkb * TILE_BYTES;
+    const uint32_t sBar = sB + STAGES * TILE_BYTES;
+    // barriers: full[STAGES] empty[STAGES] a_full tmem_full[2] tmem_empty[2]
+    const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_a = sBar + 16 * STAGES;
+    const uint32_t bar_tfull = bar_a + 8, bar_tempty = bar_tfull + 16;
+    const uint32_t s_tmem_ptr = bar_tempty + 16;
+    uint8_t *g_after = gbase + (size_t)(p.nkb + STAGES) * TILE_BYTES + 16 * STAGES + 8 + 32;
+    volatile uint32_t *tmem_ptr_g = reinterpret_cast<volatile uint32_t *>(g_after);
+    float *nrm_s = reinterpret_cast<float *>(g_after + 16);           // [2][BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x / p.nchunks, chunk = blockIdx.x % p.nchunks;
+    const int64_t row_beg = p.row_lo + (int64_t)chunk * p.chunk_rows;
+    const int64_t row_end = min(p.row_hi, row_beg + p.chunk_rows);
+    const int ntiles = row_end > row_beg ? (int)((row_end - row_beg + BN - 1) / BN) : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_a, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(s_tmem_ptr, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_g;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&mapQ);
+            tma_prefetch_desc(&mapS);
+            tma_prefetch_desc(&mapG);
+            mbar_expect_tx(bar_a, (uint32_t)p.nkb * TILE_BYTES);
+            for (int kb = 0; kb < p.nkb; ++kb)
+                tma_load_2d(sA + kb * TILE_BYTES, &mapQ, kb * BK, qt * BM, bar_a);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                const int64_t r0 = row_beg + (int64_t)t * BN;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(bar_full + 8 * stage, TILE_BYTES);
+                    tma_load_2d(sB + stage * TILE_BYTES, p.kb_map[kb] ? &mapG : &mapS, p.kb_col[kb],
+                                (int)(r0 + p.kb_rowoff[kb]), bar_full + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0) {
+            mbar_wait(bar_a, 0);
+            tc_fence_after();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                const int acc = t & 1;
+                const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);       // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_smem_desc(sA + kb * TILE_BYTES);
+                    const uint64_t b_desc = make_smem_desc(sB + stage * TILE_BYTES);
+                    const int ks_n = p.kb_ksteps[kb];
+                    for (int ks = 0; ks < ks_n; ++ks)   // +32 B along K inside the swizzle row = +2 in the address field
+                        umma_f16(d_tmem, a_desc + 2u * ks, b_desc + 2u * ks, IDESC, (kb | ks) != 0);
+                    umma_commit(bar_empty + 8 * stage);               // smem slot reusable once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * acc);                     // accumulator complete
+            }
+        }
+    } else {
+        // ===================== epilogue: one thread per query =====================
+        const int quarter = warp & 3;                 // TMEM lanes this warp may read
+        const int ql = quarter * 32 + lane;           // query row inside the tile == TMEM lane
+        const int64_t q = (int64_t)qt * BM + ql;
+        const int et = (warp - 2) * 32 + lane;        // 0..127 among the epilogue threads
+        float lv[LSZ];
+        int li[LSZ];
+#pragma unroll
+        for (int i = 0; i < LSZ; ++i) { lv[i] = INFINITY; li[i] = -1; }
+        for (int t = 0; t < ntiles; ++t) {
+            const int acc = t & 1;
+            const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
+            const int64_t r0 = row_beg + (int64_t)t * BN;
+            nrm_s[acc * BN + et] = (r0 + et < row_end) ? __ldg(p.nrm + r0 + et) : INFINITY;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                __syncwarp();
+                tmem_ld32(taddr + c0, v);
+                if (c0 + 32 == BN) {                  // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty + 8 * acc);
+                }
+                if (kStore) {
+                    if (q < p.nq) {
+                        float *dst = p.odist + q * p.ldo + (r0 - p.row_lo) + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 o;
+                            o.x = fmaf(-2.f, v[j + 0], nrm_s[acc * BN + c0 + j + 0]);
+                            o.y = fmaf(-2.f, v[j + 1], nrm_s[acc * BN + c0 + j + 1]);
+                            o.z = fmaf(-2.f, v[j + 2], nrm_s[acc * BN + c0 + j + 2]);
+                            o.w = fmaf(-2.f, v[j + 3], nrm_s[acc * BN + c0 + j + 3]);
+                            *reinterpret_cast<float4 *>(dst + j) = o;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float key = fmaf(-2.f, v[j], nrm_s[acc * BN + c0 + j]);
+                        if (__any_sync(0xffffffffu, key < lv[LSZ - 1])) {
+                            if (key < lv[LSZ - 1]) {
+                                int id = (int)(r0 + c0 + j);
+#pragma unroll
+                                for (int i = 0; i < LSZ; ++i) {   // bubble into the ascending list; ties keep the lower row
+                                    if (key < lv[i]) {
+                                        const float tv = lv[i]; lv[i] = key; key = tv;
+                                        const int ti = li[i]; li[i] = id; id = ti;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (!kStore) {
+            float *ov = p.oval + ((size_t)q * p.nchunks + chunk) * LSZ;
+            int *oi = p.oid + ((size_t)q * p.nchunks + chunk) * LSZ;
+#pragma unroll
+            for (int i = 0; i < LSZ; ++i) { ov[i] = lv[i]; oi[i] = li[i]; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// per query: tau = min over chunks of the chunk list's largest key (a row dropped inside a chunk has a
+// key >= that chunk's LSZ-th smallest)
+__global__ void chunk_tau_kernel(const float *__restrict__ oval, int64_t nq, int nchunks, float *__restrict__ tau) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        float t = INFINITY;
+        for (int c = 0; c < nchunks; ++c) t = fminf(t, oval[((size_t)q * nchunks + c) * LSZ + LSZ - 1]);
+        tau[q] = t;
+    }
+}
+__global__ void fill_kernel(float *p, int64_t n, float v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ---------------------------------------------------------------- host state
+typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct tc_space_host {
+    int nkb = 0;
+    int kb_map[MAXKB], kb_rowoff[MAXKB], kb_col[MAXKB], kb_ksteps[MAXKB];
+    short *d_qmap = nullptr;
+    int ldq = 0;
+    bool ok = false;
+};
+struct tc_state {
+    encode_fn encode = nullptr;
+    CUtensorMap mapS, mapG;
+    tc_space_host sp[2];
+    size_t smem[2] = {0, 0};
+};
+
+int make_map(encode_fn enc, CUtensorMap *map, const void *base, uint64_t cols, uint64_t rows, uint64_t ld_elems,
+             uint32_t box_rows) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SNK_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return 0;
+}
+
+size_t smem_bytes(int nkb) { return 1024 + (size_t)(nkb + STAGES) * TILE_BYTES + 16 * STAGES + 8 + 32 + 16 + 2 * BN * 4 + 64; }
+
+int build_space(snk_db *db, int space, tc_space_host *h) {
+    const int Dt = db->Dt;
+    const int tblocks = (Dt + BK - 1) / BK;       // K-blocks per target frame
+    std::vector<short> qmap;
+    h->nkb = 0;
+    auto push = [&](int map, int rowoff, int col, int valid, int dim0) {
+        if (h->nkb >= MAXKB) { h->nkb = MAXKB + 1; return; }
+        const int i = h->nkb++;
+        h->kb_map[i] = map; h->kb_rowoff[i] = rowoff; h->kb_col[i] = col; h->kb_ksteps[i] = (valid + 15) / 16;
+        for (int c = 0; c < BK; ++c) qmap.push_back(c < valid ? (short)(dim0 + c) : (short)-1);
+    };
+    int dim = 0;
+    if (space == SNK_SPACE_JOINT) {
+        for (int c = 0; c < db->Djq; c += BK) push(0, 0, c, std::min(BK, db->Djq - c), c);
+        dim = db->Djq;
+        for (int j = 0; j < db->m; ++j)
+            for (int b = 0; b < tblocks; ++b) push(1, j, b * BK, std::min(BK, Dt - b * BK), dim + j * Dt + b * BK);
+    } else {
+        for (int b = 0; b < tblocks; ++b) push(1, 0, b * BK, std::min(BK, Dt - b * BK), b * BK);
+    }
+    h->ok = h->nkb >= 1 && h->nkb <= MAXKB;
+    if (!h->ok) return 0;
+    h->ldq = h->nkb * BK;
+    SNK_CUDA(cudaMalloc((void **)&h->d_qmap, qmap.size() * sizeof(short)));
+    SNK_CUDA(cudaMemcpy(h->d_qmap, qmap.data(), qmap.size() * sizeof(short), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+}  // namespace
+
+int snk_tc_prepare(snk_db *db) {
+    tc_state *s = new tc_state();
+    db->tc_state = s;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        snk_set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return 1;
+    }
+    s->encode = (encode_fn)fn;
+    SNK_TRY(make_map(s->encode, &s->mapS, db->S16, (uint64_t)db->ldS16, (uint64_t)db->N + 1, (uint64_t)db->ldS16, BN));
+    SNK_TRY(make_map(s->encode, &s->mapG, db->G16, (uint64_t)db->ldG16, (uint64_t)db->N, (uint64_t)db->ldG16, BN));
+    for (int sp = 0; sp < 2; ++sp) {
+        SNK_TRY(build_space(db, sp, &s->sp[sp]));
+        if (s->sp[sp].ok) {
+            s->smem[sp] = smem_bytes(s->sp[sp].nkb);
+            if (s->smem[sp] > 227 * 1024) s->sp[sp].ok = false;
+        }
+    }
+    SNK_CUDA(cudaFuncSetAttribute(knn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SNK_CUDA(cudaFuncSetAttribute(knn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return 0;
+}
+
+void snk_tc_destroy(snk_db *db) {
+    tc_state *s = (tc_state *)db->tc_state;
+    if (!s) return;
+    for (int sp = 0; sp < 2; ++sp)
+        if (s->sp[sp].d_qmap) cudaFree(s->sp[sp].d_qmap);
+    delete s;
+    db->tc_state = nullptr;
+}
+
+bool snk_tc_supported(const snk_db *db, const snk_space &sp, int KP) {
+    const tc_state *s = (const tc_state *)db->tc_state;
+    if (!s) return false;
+    const int space = sp.dA > 0 ? SNK_SPACE_JOINT : SNK_SPACE_TARGET;
+    (void)KP;
+    return s->sp[space].ok && sp.rows >= 1;
+}
+
+int snk_tc_query_ld(const snk_db *db, int space) { return ((const tc_state *)db->tc_state)->sp[space].ldq; }
+const short *snk_tc_qmap(const snk_db *db, int space) { return ((const tc_state *)db->tc_state)->sp[space].d_qmap; }
+
+int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64_t nq, int k, int KP, float *d_val,
+                     int *d_id, float *d_tau, cudaStream_t st) {
+    tc_state *s = (tc_state *)db->tc_state;
+    const tc_space_host &h = s->sp[space];
+    SNK_CHECK(h.ok, "tensor-core engine does not support this search space");
+    const snk_space sp = snk_make_space(db, space);
+    const int64_t nq_pad = snk_round_up(nq, BM);
+    const int nqt = (int)(nq_pad / BM);
+    CUtensorMap mapQ;
+    SNK_TRY(make_map(s->encode, &mapQ, dQ16, (uint64_t)ldq16, (uint64_t)nq_pad, (uint64_t)ldq16, BM));
+    tc_params p;
+    memset(&p, 0, sizeof(p));
+    p.nkb = h.nkb;
+    for (int i = 0; i < h.nkb; ++i) {
+        p.kb_map[i] = h.kb_map[i]; p.kb_rowoff[i] = h.kb_rowoff[i]; p.kb_col[i] = h.kb_col[i]; p.kb_ksteps[i] = h.kb_ksteps[i];
+    }
+    p.nq = nq;
+    p.nrm = space == SNK_SPACE_JOINT ? db->nrm_j16 : db->nrm_t16;
+    const size_t smem = s->smem[space];
+    const int64_t row_tiles = snk_cdiv(sp.rows, BN);
+    const bool fused = k <= LSZ / 2;    // per-chunk lists of LSZ cover the k best with slack; larger k goes through the scan
+
+    if (fused) {
+        int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(db->sm_count / std::max(nqt, 1), row_tiles));
+        if (nqt > db->sm_count) nchunks = 1;
+        p.row_lo = 0; p.row_hi = sp.rows; p.nchunks = nchunks;
+        p.chunk_rows = snk_cdiv(row_tiles, nchunks) * BN;
+        const size_t nlist = (size_t)nq_pad * nchunks * LSZ;
+        SNK_TRY(snk_buf_reserve(&db->ws_tc, nlist * 8));
+        p.oval = (float *)db->ws_tc.p;
+        p.oid = (int *)(p.oval + nlist);
+        {
+            snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)sp.rows * sp.D, st);
+            knn_tc_kernel<false><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, p);
+        }
+        SNK_CUDA(cudaGetLastError());
+        chunk_tau_kernel<<<64, 256, 0, st>>>(p.oval, nq, nchunks, d_tau);
+        SNK_CUDA(cudaGetLastError());
+        db->counters[2] += 2;
+        for (int64_t q0 = 0; q0 < nq; q0 += 32768) {
+            const int64_t n = std::min<int64_t>(32768, nq - q0);
+            SNK_TRY(snk_topk_scan(db, p.oval + (size_t)q0 * nchunks * LSZ, p.oid + (size_t)q0 * nchunks * LSZ, n,
+                                  (int64_t)nchunks * LSZ, (int64_t)nchunks * LSZ, 0, KP, true, d_val + q0 * KP,
+                                  d_id + q0 * KP, st));
+        }
+        return 0;
+    }
+    // store mode: keys of a row span go to HBM, the warp scan selects the KP smallest per query
+    const size_t WS = (size_t)512 << 20;
+    int64_t span = (int64_t)(WS / 4 / (size_t)nq_pad) / BN * BN;
+    span = std::max<int64_t>(BN, std::min<int64_t>(span, row_tiles * BN));
+    SNK_TRY(snk_buf_reserve(&db->ws_dist, (size_t)nq_pad * span * 4));
+    p.odist = (float *)db->ws_dist.p;
+    p.ldo = span;
+    fill_kernel<<<64, 256, 0, st>>>(d_tau, nq, INFINITY);
+    SNK_CUDA(cudaGetLastError());
+    bool first = true;
+    for (int64_t rb = 0; rb < sp.rows; rb += span) {
+        const int64_t rn = std::min<int64_t>(span, sp.rows - rb);
+        const int64_t tiles = snk_cdiv(rn, BN);
+        int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(db->sm_count / std::max(nqt, 1), tiles));
+        if (nqt > db->sm_count) nchunks = 1;
+        p.row_lo = rb; p.row_hi = rb + rn; p.nchunks = nchunks;
+        p.chunk_rows = snk_cdiv(tiles, nchunks) * BN;
+        {
+            snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)rn * sp.D, st);
+            knn_tc_kernel<true><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, p);
+        }
+        SNK_CUDA(cudaGetLastError());
+        db->counters[2] += 1;
+        for (int64_t q0 = 0; q0 < nq; q0 += 32768) {
+            const int64_t n = std::min<int64_t>(32768, nq - q0);
+            SNK_TRY(snk_topk_scan(db, p.odist + q0 * span, nullptr, n, snk_cdiv(rn, BN) * BN, span, (int)rb, KP, first,
+                                  d_val + q0 * KP, d_id + q0 * KP, st));
+        }
+        first = false;
+    }
+    return 0;
 }

@@ -68,7 +68,8 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
         const double v = d2[t];
         const int i = ids[t];
         int rank = 0;
-        for (int j = 0; j < KP; ++j) rank += dpair_lt(d2[j], ids[j], v, i) ? 1 : 0;
+        for (int j = 0; j < KP; ++j)   // equal pairs (only the empty slots) keep their list order
+            rank += (dpair_lt(d2[j], ids[j], v, i) || (d2[j] == v && ids[j] == i && j < t)) ? 1 : 0;
         if (rank < k) {
             const bool ok = i != INT_MAX;
             odist[q * ostride + rank] = ok ? sqrt(v) : INFINITY;
@@ -76,6 +77,7 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
             if (cert && rank == k - 1) {
                 // every row outside the shortlist has approx distance >= tau; its true distance is
                 // >= tau - (||dx|| + ||dy||) by the triangle inequality (fp16 rounding of both sides)
+                // tau: smallest approximate key any row OUTSIDE the shortlist can have
                 float mx = -INFINITY;
                 bool full = true;
                 for (int j = 0; j < KP; ++j) {
@@ -83,11 +85,12 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
                     if (id[ql * KP + j] < 0) full = false;
                     else mx = fmaxf(mx, a);
                 }
+                if (!full) mx = INFINITY;                       // the final merge dropped nothing
+                if (tau_extra) mx = fminf(mx, tau_extra[q]);    // ... but an earlier stage may have
                 int good = 1;
-                if (full) {
+                if (mx < INFINITY) {
                     const float qq = qn ? qn[q] : 0.f;
                     const float eps = 4e-6f * (qq + (maxn ? *maxn : 0.f));
-                    if (tau_extra) mx = fminf(mx, tau_extra[q]);
                     const double tau2 = (double)mx + (double)qq - (double)eps;
                     const double tau = tau2 > 0.0 ? sqrt(tau2) : 0.0;
                     const double delta = (double)(qerr ? qerr[q] : 0.f) + (double)(dberr ? *dberr : 0.f);

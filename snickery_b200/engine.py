@@ -20,6 +20,7 @@ SPACE_TARGET = 0
 SPACE_JOINT = 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 VITERBI_BEAM1 = 1
+PROF_KNN, PROF_JOIN, PROF_VITERBI = 0, 1, 2
 
 _lib = None
 
@@ -54,6 +55,8 @@ def load_library(path=None):
         "snk_db_set_weights": [vp, P(dbl), P(dbl)],
         "snk_db_set_engine": [vp, i32],
         "snk_db_counters": [vp, P(i64), i32],
+        "snk_db_profile_enable": [vp, i32],
+        "snk_db_profile_read": [vp, i32, P(dbl), P(i64), P(dbl), i32],
         "snk_knn": [vp, i32, P(dbl), i64, i32, P(dbl), P(i64)],
         "snk_knn_dev": [vp, i32, vp, i64, i32, vp, vp, i64, vp],
         "snk_topk_merge_dev": [i32, vp, vp, i32, i64, i32, vp, vp, vp],
@@ -74,7 +77,8 @@ def load_library(path=None):
 
 
 EXPORTED_SYMBOLS = ["snk_last_error", "snk_version", "snk_device_count", "snk_db_create", "snk_db_destroy",
-                    "snk_db_info", "snk_db_set_weights", "snk_db_set_engine", "snk_db_counters", "snk_knn",
+                    "snk_db_info", "snk_db_set_weights", "snk_db_set_engine", "snk_db_counters", "snk_db_profile_enable",
+                    "snk_db_profile_read", "snk_knn",
                     "snk_knn_dev", "snk_topk_merge_dev", "snk_greedy_batch", "snk_greedy_batch_dev",
                     "snk_candidate_distances", "snk_join_tiles", "snk_join_viterbi_batch",
                     "snk_join_viterbi_batch_dev", "snk_greedy_path_scores"]
@@ -141,6 +145,14 @@ class UnitDatabase:
         out = np.zeros(4, dtype=np.int64)
         _check(load_library().snk_db_counters(self._h, _ptr(out, C.c_int64), int(reset)))
         return {"queries": int(out[0]), "recertified": int(out[1]), "launches": int(out[2])}
+
+    def profile_enable(self, on=True):
+        _check(load_library().snk_db_profile_enable(self._h, int(on)))
+
+    def profile_read(self, which, reset=True):
+        ms, n, w = C.c_double(), C.c_int64(), C.c_double()
+        _check(load_library().snk_db_profile_read(self._h, int(which), C.byref(ms), C.byref(n), C.byref(w), int(reset)))
+        return {"ms": ms.value, "launches": n.value, "work": w.value}
 
     # -- searches (host arrays in, host arrays out)
     def knn(self, Q, k, space=SPACE_TARGET):

