@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- target frames/sec through the unit-selection search hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle restatement)
+
+Workload (BASELINE.json configs[1], IS2018_nick_simplified.cfg): a full SLT-Arctic-sized epoch
+database (700k units, 61-dim target / 151-dim join streams, multiepoch 6 => 517-dim joint rows),
+exact greedy joint search (search_epsilon = 0).  One "step" = one pass of the hot path over one
+batch of B synthetic target utterances of 648 frames (108 greedy steps each) per GPU.  With N
+GPUs the database is replicated and utterances are sharded (weak scaling, no data-path
+collective).  Data are synthetic magphase-shaped features
+(snickery_b200/synthetic.py); there are no published reference numbers.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+DB_UNITS = 700_000
+UTT_FRAMES = 648
+MULTIEPOCH = 6
+METRIC = "target_frames_per_sec"
+UNIT = "frames/s"
+
+
+def workload_config():
+    from conftest import epoch_config
+    # config/IS2018_nick_simplified.cfg:77-78,97,103: equal stream weights, jcw 0.2, multiepoch 6
+    return epoch_config(multiepoch=MULTIEPOCH, jcw=0.2, tsw=(0.5, 0.5), jsw=(0.25, 0.25, 0.25, 0.25))
+
+
+def make_database(units):
+    from snickery_b200 import synthetic as syn
+    return syn.make_epoch_db(n_units=units, seed=1234 + 2)
+
+
+def make_batch(F, wt, n_utts, frames, seed):
+    """Weighted float64 target utterances concatenated [n_utts * frames, Dt] (what the reference
+    hands to greedy_joint_search, synth_simple.py:381-390,413)."""
+    rng = np.random.default_rng(seed)
+    n = F.shape[0]
+    starts = rng.integers(0, n - frames, size=n_utts)
+    idx = (starts[:, None] + np.arange(frames)[None, :]).reshape(-1)
+    seg = F[idx].astype(np.float64)
+    uv = seg == -20.0
+    seg += 0.3 * rng.standard_normal(seg.shape)
+    seg[uv] = -20.0
+    seg = seg.astype(np.float32).astype(np.float64)     # targets come from float32 files
+    return seg * wt[None, :]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_rate(db, cfg, wt, cores, budget_s, seed):
+    """The reference's CPU path: scipy cKDTree(leafsize=100, balanced_tree=False) over the joint
+    rows + the sequential greedy loop (synth_simple.py:229,458-503), eps = 0.  Utterance-parallel
+    over `cores` forked workers like the reference's Pool (synth_halfphone.py:897-903).
+    Returns frames/s on a bounded sample, plus a description."""
+    from oracle import snickery_oracle as O
+    t0 = time.time()
+    o = O.OracleSynthesiser(cfg, db["F"], db["Jc"])
+    o.get_tree_for_greedy_search()
+    build_s = time.time() - t0
+    # calibrate: a handful of steps of one utterance
+    probe = make_batch(db["F"], wt, 1, MULTIEPOCH * 4, seed)
+    t0 = time.time()
+    o.greedy_joint_search(probe)
+    per_step = (time.time() - t0) / 4
+    steps_per_utt = int(max(4, min(UTT_FRAMES // MULTIEPOCH, budget_s / max(per_step, 1e-4))))
+    frames = steps_per_utt * MULTIEPOCH
+    utts = make_batch(db["F"], wt, cores, frames, seed + 1).reshape(cores, frames, -1)
+    global _CPU_ORACLE
+    _CPU_ORACLE = o
+
+    def run():
+        t0 = time.time()
+        if cores == 1:
+            o.greedy_joint_search(utts[0])
+        else:
+            import multiprocessing as mp
+            with mp.get_context("fork").Pool(cores) as pool:
+                pool.map(_cpu_worker, [utts[i] for i in range(cores)])
+        return time.time() - t0
+
+    return run, cores * frames, {"tree_build_s": round(build_s, 2), "steps_per_utt": steps_per_utt,
+                                 "utts": cores, "probe_s_per_query": round(per_step, 4)}
+
+
+_CPU_ORACLE = None
+
+
+def _cpu_worker(utt):
+    return _CPU_ORACLE.greedy_joint_search(utt)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = workload_config()
+    db = make_database(args.db_units)
+    from oracle import snickery_oracle as O
+    wt = O.per_coeff_weights(np.array(cfg["target_stream_weights"]) * (1 - cfg["join_cost_weight"]),
+                             cfg["stream_list_target"], cfg["datadims_target"])
+    cores = os.cpu_count() or 1
+    run, frames, info = cpu_reference_rate(db, cfg, wt, cores, budget_s=4.0, seed=99)
+    for _ in range(args.warmup):
+        run()
+    times = [run() for _ in range(args.steps)]
+    total = sum(times)
+    value = frames * args.steps / total
+    sample = "%d utts x %d greedy steps (of %d) per step, one forked worker per core; tree build %.1fs excluded" % (
+        info["utts"], info["steps_per_utt"], UTT_FRAMES // MULTIEPOCH, info["tree_build_s"])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_description(args, 0),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference is Python 2 + pywrapfst and cannot run here; this is oracle/ (its Python 3 restatement "
+                "driving the reference's own scipy cKDTree engine) on the host cores",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_description(args, utts):
+    return {"workload": "IS2018_nick_simplified greedy joint search (configs[1])", "db_units": args.db_units,
+            "target_dim": 61, "join_dim": 151, "multiepoch": MULTIEPOCH, "joint_dim": 151 + 61 * MULTIEPOCH,
+            "utts_per_gpu": utts, "frames_per_utt": UTT_FRAMES, "search_epsilon": 0.0,
+            "parallelism": "utterance-sharded, database replicated",
+            "l2": "database operands (S16+G16, 0.36 GB) exceed the 126 MB L2 and are re-streamed every greedy step"}
+
+
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from snickery_b200 import Synthesiser, engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    cfg = workload_config()
+    db = make_database(args.db_units)
+    syn = Synthesiser(cfg, db["F"], db["Jc"], device=local)
+    syn.get_tree_for_greedy_search()
+    if args.engine:
+        syn.db.set_engine({"auto": 0, "simt": 1, "tc": 2}[args.engine])
+    wt = syn.target_weight_vector
+    B, T = args.utts, UTT_FRAMES
+    lens = np.full(B, T, dtype=np.int64)
+    steps_per_utt = T // MULTIEPOCH
+    lib = engine.load_library()
+    import ctypes as C
+
+    # per-step batches: distinct inputs per step, resident in HBM for `value`, pinned on the host for `e2e`
+    nbatch = min(args.steps + args.warmup, 4)
+    host_batches, dev_batches = [], []
+    for i in range(nbatch):
+        cat = make_batch(db["F"], wt, B, T, seed=1000 + 17 * rank + i)
+        pinned = torch.empty(cat.shape, dtype=torch.float64).pin_memory()
+        pinned.numpy()[...] = cat
+        host_batches.append(pinned)
+        dev_batches.append(pinned.to(dev))
+    d_paths = torch.empty(B * steps_per_utt, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_dev(i):
+        t = dev_batches[i % nbatch]
+        rc = lib.snk_greedy_batch_dev(syn.db.handle, C.c_void_p(t.data_ptr()), lens.ctypes.data_as(C.POINTER(C.c_int64)),
+                                      B, None, C.c_void_p(d_paths.data_ptr()), None, C.c_void_p(stream.cuda_stream))
+        if rc:
+            raise RuntimeError(lib.snk_last_error().decode())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    c0 = syn.db.counters()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step_dev(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    c1 = syn.db.counters()
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    frames_per_step_all = world * B * T
+    value = frames_per_step_all * args.steps / (ms_max / 1000.0)
+
+    # ---- e2e: host (pinned) arrays in, host lists out, through the reference-facing Python API
+    e2e_steps = max(1, min(args.steps, 3))
+    lens_list = lens
+
+    def step_e2e(i):
+        cat = host_batches[i % nbatch].numpy()
+        return syn.db.greedy_batch_cat(cat, lens_list)
+
+    step_e2e(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        paths = step_e2e(i + 1)
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = frames_per_step_all * e2e_steps / float(te.item())
+    h2d = int(B * T * 61 * 8)
+    d2h = int(B * steps_per_utt * 8)
+
+    # ---- kernel time of the dominant kernel (profiled pass, outside the timed region)
+    syn.db.profile_enable(True)
+    step_dev(0)
+    torch.cuda.synchronize()
+    prof = syn.db.profile_read(engine.PROF_KNN)
+    syn.db.profile_enable(False)
+
+    out = None
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        tf = prof["work"] / (prof["ms"] / 1e3) / 1e12 if prof["ms"] > 0 else 0.0
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("knn_tc_kernel_bytes_per_launch")
+        recert = c1["recertified"] - c0["recertified"]
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16 tensor-core shortlist (fp32 accumulate) + f64 re-rank", "data": "synthetic",
+            "config": workload_description(args, B),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": int(c1["launches"] - c0["launches"]),
+            "roofline": {"bound": "tensor", "kernel": "knn_tc_kernel<false> (tcgen05 distance GEMM + fused top-k)",
+                         "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak if peak else None,
+                         "traffic": traffic, "peak_kind": peak_kind + " (bf16 sustained; fp16 runs at the same rate)",
+                         "launches": prof["launches"], "avg_launch_ms": prof["ms"] / max(prof["launches"], 1),
+                         "flops_per_launch": prof["work"] / max(prof["launches"], 1),
+                         "kernel_share_of_step": prof["ms"] / (ms_max / args.steps)},
+            "exactness": {"queries": int(c1["queries"] - c0["queries"]), "recertified_by_simt": int(recert)},
+        }
+    if world > 1:
+        dist.barrier()
+
+    # ---- secondary: join tiles + Viterbi (config 3 shape) kernel rooflines, N = 1 only
+    if rank == 0 and world == 1 and not args.no_secondary:
+        out["secondary"] = secondary_viterbi(local)
+    # ---- CPU baseline (rank 0, N = 1 only)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        run, frames, info = cpu_reference_rate(db, cfg, wt, 1, budget_s=12.0, seed=99)
+        t = run()
+        out["cpu_baseline"] = {"value": frames / t, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": "1 utt x %d greedy steps, scipy cKDTree eps=0 single thread as the reference "
+                                         "runs (synth_simple.py:279-284); tree build %.1fs excluded" %
+                                         (info["steps_per_utt"], info["tree_build_s"])}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def secondary_viterbi(device):
+    """hybrid_halfphone_default.cfg shape: 90k halfphones, 1024 utts x 80 targets x 50 candidates."""
+    import torch
+    from conftest import halfphone_config
+    from snickery_b200 import Synthesiser, engine, synthetic as syn
+    hp = syn.make_halfphone_db(n_units=90000, seed=1237)
+    g = Synthesiser(halfphone_config(n_candidates=50, preselection="quinphone"), hp["F"], hp["Jc"], device=device)
+    rng = np.random.default_rng(5)
+    B, T, K = 1024, 80, 50
+    cands = [rng.integers(1, 89998, size=(T, K)) for _ in range(B)]
+    dists = [rng.random((T, K)) for _ in range(B)]
+    g.viterbi_search_batch(cands[:8], dists[:8])
+    g.db.profile_enable(True)
+    t0 = time.perf_counter()
+    g.viterbi_search_batch(cands, dists)
+    wall = time.perf_counter() - t0
+    pj = g.db.profile_read(engine.PROF_JOIN)
+    pv = g.db.profile_read(engine.PROF_VITERBI)
+    g.db.profile_enable(False)
+    peaks, kind = measured_peaks()
+    hbm = float(peaks["hbm_gbs"])
+    res = {"workload": "hybrid_halfphone_default shape: %d utts x %d targets x %d candidates, 90k halfphones" % (B, T, K),
+           "e2e_frames_per_s": B * T / wall}
+    for name, p in (("join_tiles", pj), ("viterbi", pv)):
+        gbs = p["work"] / (p["ms"] / 1e3) / 1e9 if p["ms"] > 0 else 0.0
+        res[name] = {"ms": p["ms"], "achieved_GBps": gbs, "peak_GBps": hbm, "frac": gbs / hbm, "peak_kind": kind,
+                     "frames_per_s": B * T / (p["ms"] / 1e3) if p["ms"] > 0 else None}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--utts", type=int, default=1024, help="target utterances per GPU per step")
+    ap.add_argument("--db-units", type=int, default=DB_UNITS)
+    ap.add_argument("--engine", default="", choices=["", "auto", "simt", "tc"])
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -167,18 +167,18 @@ class UnitDatabase:
                                       _ptr(idx, C.c_int64)))
         return dist, idx
 
-    def greedy_batch(self, targets_list, start_states=None, return_dists=False):
+    def greedy_batch_cat(self, cat, lens, start_states=None, return_dists=False):
+        """Batch given as one concatenated float64 array [sum T_b, Dt] (may be pinned) + lengths."""
         m = self.multiepoch
-        lens = np.array([t.shape[0] for t in targets_list], dtype=np.int64)
-        for t in targets_list:
-            if t.ndim != 2 or t.shape[1] != self.Dt:
-                raise ValueError("each target utterance must be [T, %d]" % self.Dt)
-            if t.shape[0] < m:
-                raise ValueError("Not enough data points to segment array in 'cut' mode")  # segmentaxis.py:94-96
-        B = len(targets_list)
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        B = lens.size
         if B == 0:
             return ([], []) if return_dists else []
-        cat = np.ascontiguousarray(np.concatenate(targets_list, axis=0), dtype=np.float64)
+        if np.any(lens < m):
+            raise ValueError("Not enough data points to segment array in 'cut' mode")  # segmentaxis.py:94-96
+        cat = np.ascontiguousarray(cat, dtype=np.float64)
+        if cat.ndim != 2 or cat.shape[1] != self.Dt or cat.shape[0] != int(lens.sum()):
+            raise ValueError("targets must be [sum(lens), %d]" % self.Dt)
         steps = lens // m
         paths = np.empty(int(steps.sum()), dtype=np.int64)
         dists = np.empty(int(steps.sum()), dtype=np.float64) if return_dists else None
@@ -192,6 +192,16 @@ class UnitDatabase:
         if return_dists:
             return p, np.split(dists, cuts)
         return p
+
+    def greedy_batch(self, targets_list, start_states=None, return_dists=False):
+        for t in targets_list:
+            if t.ndim != 2 or t.shape[1] != self.Dt:
+                raise ValueError("each target utterance must be [T, %d]" % self.Dt)
+        if len(targets_list) == 0:
+            return ([], []) if return_dists else []
+        lens = np.array([t.shape[0] for t in targets_list], dtype=np.int64)
+        cat = np.concatenate(targets_list, axis=0)
+        return self.greedy_batch_cat(cat, lens, start_states, return_dists)
 
     def candidate_distances(self, cand, targets):
         cand = np.ascontiguousarray(cand, dtype=np.int64)
