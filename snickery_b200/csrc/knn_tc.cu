@@ -21,25 +21,35 @@
 #include <cuda.h>
 #include <algorithm>
 #include <string.h>
+#include <stdlib.h>
+#include <vector>
 
 namespace {
 
 constexpr int BM = 128;        // queries per tile (UMMA M)
 constexpr int BN = 128;        // database rows per tile (UMMA N)
 constexpr int BK = 64;         // fp16 elements per K-block = one 128-byte swizzle row
-constexpr int STAGES = 4;
-constexpr int MAXKB = 10;
+constexpr int MAX_STAGES = 4;
+constexpr int MAXKB = 10;      // resident query K-blocks
+constexpr int MAXLOAD = 10;    // TMA loads per database tile
+constexpr int MAXSUB = 16;     // MMA K-blocks per database tile
+constexpr int SLAB_EXTRA = 8;  // extra rows of a frame slab: serves window offsets 0..8
 constexpr int LSZ = 8;         // per-(query, chunk) list length of the fused epilogue
-constexpr int TILE_BYTES = BM * BK * 2;   // 16 KiB (A and B tiles have the same shape)
+constexpr int TILE_BYTES = BM * BK * 2;                    // 16 KiB query K-block
+constexpr int SLOT_BYTES = (BN + SLAB_EXTRA) * BK * 2;     // 17 KiB ring slot (plain tile or frame slab)
 constexpr int NUM_THREADS = 192;
 constexpr uint32_t TMEM_COLS = 256;       // two 128-column fp32 accumulators
 
+// One TMA load per ring slot; it feeds nsub MMA K-blocks.  A frame slab (BN + 8 rows of G16) feeds the
+// m window offsets of the multiepoch row: K-block j reads the slab from row j on, so the sliding
+// window is never materialised and each frame row is fetched once per tile instead of m times.
+struct tc_load { int map, rowoff, col, bytes, sub0, nsub; };
+struct tc_sub { int a_blk, b_off, base_off, ksteps; };
 struct tc_params {
-    int nkb;
-    int kb_map[MAXKB];      // 0: join-context map (S16), 1: target-frame map (G16)
-    int kb_rowoff[MAXKB];
-    int kb_col[MAXKB];
-    int kb_ksteps[MAXKB];
+    int nkb;                // resident query K-blocks
+    int nload, nsub, stages;
+    tc_load load[MAXLOAD];  // map: 0 join-context tile (S16), 1 frame tile (G16), 2 frame slab (G16, BN+8 rows)
+    tc_sub sub[MAXSUB];
     int64_t row_lo, row_hi; // rows scanned by this launch
     int64_t chunk_rows;     // multiple of BN
     int nchunks;
@@ -127,9 +137,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// three-input minimum (sm_100)
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 // K-major, 128-byte swizzled operand tile: rows of 64 fp16 (128 B), 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t base_off = 0) {
     uint64_t d = 0;
+    d |= (uint64_t)(base_off & 7u) << 49;              // start row inside the 8-row swizzle atom
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
     d |= (uint64_t)0 << 16;                            // leading byte offset (unused for swizzled K-major)
     d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
@@ -144,18 +162,20 @@ constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >
 template <bool kStore>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapS,
-              const __grid_constant__ CUtensorMap mapG, const tc_params p) {
+              const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapGslab,
+              const tc_params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t *gbase = smem_raw + (sbase - smem_u32(smem_raw));
     const uint32_t sA = sbase;
     const uint32_t sB = sA + (uint32_t)p.nkb * TILE_BYTES;
-    const uint32_t sBar = sB + STAGES * TILE_BYTES;
-    // barriers: full[STAGES] empty[STAGES] a_full tmem_full[2] tmem_empty[2]
-    const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_a = sBar + 16 * STAGES;
+    const int STAGES = p.stages;
+    const uint32_t sBar = sB + (uint32_t)STAGES * SLOT_BYTES;
+    // barriers: full[MAX_STAGES] empty[MAX_STAGES] a_full tmem_full[2] tmem_empty[2]
+    const uint32_t bar_full = sBar, bar_empty = sBar + 8 * MAX_STAGES, bar_a = sBar + 16 * MAX_STAGES;
     const uint32_t bar_tfull = bar_a + 8, bar_tempty = bar_tfull + 16;
     const uint32_t s_tmem_ptr = bar_tempty + 16;
-    uint8_t *g_after = gbase + (size_t)(p.nkb + STAGES) * TILE_BYTES + 16 * STAGES + 8 + 32;
+    uint8_t *g_after = gbase + (size_t)p.nkb * TILE_BYTES + (size_t)STAGES * SLOT_BYTES + 16 * MAX_STAGES + 8 + 32;
     volatile uint32_t *tmem_ptr_g = reinterpret_cast<volatile uint32_t *>(g_after);
     float *nrm_s = reinterpret_cast<float *>(g_after + 16);           // [2][BN]
 
@@ -166,7 +186,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     const int ntiles = row_end > row_beg ? (int)((row_end - row_beg + BN - 1) / BN) : 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < MAX_STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
@@ -189,6 +209,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             tma_prefetch_desc(&mapQ);
             tma_prefetch_desc(&mapS);
             tma_prefetch_desc(&mapG);
+            tma_prefetch_desc(&mapGslab);
             mbar_expect_tx(bar_a, (uint32_t)p.nkb * TILE_BYTES);
             for (int kb = 0; kb < p.nkb; ++kb)
                 tma_load_2d(sA + kb * TILE_BYTES, &mapQ, kb * BK, qt * BM, bar_a);
@@ -196,11 +217,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             uint32_t phase = 0;
             for (int t = 0; t < ntiles; ++t) {
                 const int64_t r0 = row_beg + (int64_t)t * BN;
-                for (int kb = 0; kb < p.nkb; ++kb) {
+                for (int l = 0; l < p.nload; ++l) {
+                    const tc_load ld = p.load[l];
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(bar_full + 8 * stage, TILE_BYTES);
-                    tma_load_2d(sB + stage * TILE_BYTES, p.kb_map[kb] ? &mapG : &mapS, p.kb_col[kb],
-                                (int)(r0 + p.kb_rowoff[kb]), bar_full + 8 * stage);
+                    mbar_expect_tx(bar_full + 8 * stage, (uint32_t)ld.bytes);
+                    const CUtensorMap *map = ld.map == 0 ? &mapS : (ld.map == 1 ? &mapG : &mapGslab);
+                    tma_load_2d(sB + stage * SLOT_BYTES, map, ld.col, (int)(r0 + ld.rowoff), bar_full + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -218,14 +240,20 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);       // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
-                for (int kb = 0; kb < p.nkb; ++kb) {
+                uint32_t accumulate = 0;
+                for (int l = 0; l < p.nload; ++l) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint64_t a_desc = make_smem_desc(sA + kb * TILE_BYTES);
-                    const uint64_t b_desc = make_smem_desc(sB + stage * TILE_BYTES);
-                    const int ks_n = p.kb_ksteps[kb];
-                    for (int ks = 0; ks < ks_n; ++ks)   // +32 B along K inside the swizzle row = +2 in the address field
-                        umma_f16(d_tmem, a_desc + 2u * ks, b_desc + 2u * ks, IDESC, (kb | ks) != 0);
+                    const int s0 = p.load[l].sub0, s1 = s0 + p.load[l].nsub;
+                    for (int sb = s0; sb < s1; ++sb) {
+                        const tc_sub su = p.sub[sb];
+                        const uint64_t a_desc = make_smem_desc(sA + su.a_blk * TILE_BYTES);
+                        const uint64_t b_desc = make_smem_desc(sB + stage * SLOT_BYTES + su.b_off, su.base_off);
+                        for (int ks = 0; ks < su.ksteps; ++ks) {   // +32 B along K inside the swizzle row = +2 in the address field
+                            umma_f16(d_tmem, a_desc + 2u * ks, b_desc + 2u * ks, IDESC, accumulate);
+                            accumulate = 1;
+                        }
+                    }
                     umma_commit(bar_empty + 8 * stage);               // smem slot reusable once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -274,17 +302,46 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                         }
                     }
                 } else {
+                    // keys of this 32-column chunk, then a min tree: almost every chunk holds nothing that
+                    // beats any lane's current list, and one vote dismisses it.  Otherwise votes narrow
+                    // down to the 8-column group and the columns that matter (all votes of a level are
+                    // independent instructions, so they pipeline) before any lane touches its list.
+                    float key[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float key = fmaf(-2.f, v[j], nrm_s[acc * BN + c0 + j]);
-                        if (__any_sync(0xffffffffu, key < lv[LSZ - 1])) {
-                            if (key < lv[LSZ - 1]) {
-                                int id = (int)(r0 + c0 + j);
+                    for (int j = 0; j < 32; ++j) key[j] = fmaf(-2.f, v[j], nrm_s[acc * BN + c0 + j]);
+                    float g[4];
 #pragma unroll
-                                for (int i = 0; i < LSZ; ++i) {   // bubble into the ascending list; ties keep the lower row
-                                    if (key < lv[i]) {
-                                        const float tv = lv[i]; lv[i] = key; key = tv;
-                                        const int ti = li[i]; li[i] = id; id = ti;
+                    for (int gi = 0; gi < 4; ++gi) {
+                        const float *k8 = key + 8 * gi;
+                        g[gi] = min3(min3(k8[0], k8[1], k8[2]), min3(k8[3], k8[4], k8[5]), fminf(k8[6], k8[7]));
+                    }
+                    const float cmin = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
+                    if (__any_sync(0xffffffffu, cmin < lv[LSZ - 1])) {
+                        unsigned gm = 0;
+#pragma unroll
+                        for (int gi = 0; gi < 4; ++gi)
+                            gm |= (__ballot_sync(0xffffffffu, g[gi] < lv[LSZ - 1]) != 0u ? 1u : 0u) << gi;
+#pragma unroll
+                        for (int gi = 0; gi < 4; ++gi) {
+                            if (gm & (1u << gi)) {
+                                unsigned em = 0;
+#pragma unroll
+                                for (int e = 0; e < 8; ++e)
+                                    em |= (__ballot_sync(0xffffffffu, key[gi * 8 + e] < lv[LSZ - 1]) != 0u ? 1u : 0u) << e;
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    if (em & (1u << e)) {
+                                        float kk = key[gi * 8 + e];
+                                        if (kk < lv[LSZ - 1]) {
+                                            int id = (int)(r0 + c0 + gi * 8 + e);
+#pragma unroll
+                                            for (int i = 0; i < LSZ; ++i) {   // bubble into the ascending list; ties keep the lower row
+                                                if (kk < lv[i]) {
+                                                    const float tv = lv[i]; lv[i] = kk; kk = tv;
+                                                    const int ti = li[i]; li[i] = id; id = ti;
+                                                }
+                                            }
+                                        }
                                     }
                                 }
                             }
@@ -324,15 +381,16 @@ typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, vo
                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct tc_space_host {
-    int nkb = 0;
-    int kb_map[MAXKB], kb_rowoff[MAXKB], kb_col[MAXKB], kb_ksteps[MAXKB];
+    int nkb = 0, nload = 0, nsub = 0, stages = 0;
+    tc_load load[MAXLOAD];
+    tc_sub sub[MAXSUB];
     short *d_qmap = nullptr;
     int ldq = 0;
     bool ok = false;
 };
 struct tc_state {
     encode_fn encode = nullptr;
-    CUtensorMap mapS, mapG;
+    CUtensorMap mapS, mapG, mapGslab;
     tc_space_host sp[2];
     size_t smem[2] = {0, 0};
 };
@@ -350,31 +408,64 @@ int make_map(encode_fn enc, CUtensorMap *map, const void *base, uint64_t cols, u
     return 0;
 }
 
-size_t smem_bytes(int nkb) { return 1024 + (size_t)(nkb + STAGES) * TILE_BYTES + 16 * STAGES + 8 + 32 + 16 + 2 * BN * 4 + 64; }
-
 int build_space(snk_db *db, int space, tc_space_host *h) {
     const int Dt = db->Dt;
     const int tblocks = (Dt + BK - 1) / BK;       // K-blocks per target frame
+    const int m = space == SNK_SPACE_JOINT ? db->m : 1;
+    const bool slab = m > 1 && m <= SLAB_EXTRA + 1 && !getenv("SNK_TC_NOSLAB");
     std::vector<short> qmap;
-    h->nkb = 0;
-    auto push = [&](int map, int rowoff, int col, int valid, int dim0) {
-        if (h->nkb >= MAXKB) { h->nkb = MAXKB + 1; return; }
-        const int i = h->nkb++;
-        h->kb_map[i] = map; h->kb_rowoff[i] = rowoff; h->kb_col[i] = col; h->kb_ksteps[i] = (valid + 15) / 16;
+    h->nkb = h->nload = h->nsub = 0;
+    bool overflow = false;
+    auto add_ablock = [&](int valid, int dim0) {      // next resident query K-block: operand columns -> query dims
         for (int c = 0; c < BK; ++c) qmap.push_back(c < valid ? (short)(dim0 + c) : (short)-1);
+        return h->nkb++;
     };
-    int dim = 0;
+    auto add_load = [&](int map, int rowoff, int col, int bytes) {
+        if (h->nload >= MAXLOAD) { overflow = true; return; }
+        h->load[h->nload++] = tc_load{map, rowoff, col, bytes, h->nsub, 0};
+    };
+    auto add_sub = [&](int a_blk, int b_off, int base_off, int valid) {
+        if (h->nsub >= MAXSUB || h->nload == 0) { overflow = true; return; }
+        h->sub[h->nsub++] = tc_sub{a_blk, b_off, base_off, (valid + 15) / 16};
+        h->load[h->nload - 1].nsub++;
+    };
+    int nS = 0;
     if (space == SNK_SPACE_JOINT) {
-        for (int c = 0; c < db->Djq; c += BK) push(0, 0, c, std::min(BK, db->Djq - c), c);
-        dim = db->Djq;
-        for (int j = 0; j < db->m; ++j)
-            for (int b = 0; b < tblocks; ++b) push(1, j, b * BK, std::min(BK, Dt - b * BK), dim + j * Dt + b * BK);
-    } else {
-        for (int b = 0; b < tblocks; ++b) push(1, 0, b * BK, std::min(BK, Dt - b * BK), b * BK);
+        for (int c = 0; c < db->Djq; c += BK) {
+            const int valid = std::min(BK, db->Djq - c);
+            add_load(0, 0, c, TILE_BYTES);
+            add_sub(add_ablock(valid, c), 0, 0, valid);
+            ++nS;
+        }
     }
-    h->ok = h->nkb >= 1 && h->nkb <= MAXKB;
+    const int dim0 = space == SNK_SPACE_JOINT ? db->Djq : 0;
+    // query K-block order of the target part: frame-major, then column block
+    std::vector<int> ablk((size_t)m * tblocks);
+    for (int j = 0; j < m; ++j)
+        for (int b = 0; b < tblocks; ++b)
+            ablk[(size_t)j * tblocks + b] = add_ablock(std::min(BK, Dt - b * BK), dim0 + j * Dt + b * BK);
+    for (int b = 0; b < tblocks; ++b) {
+        const int valid = std::min(BK, Dt - b * BK);
+        if (slab) {
+            add_load(2, 0, b * BK, SLOT_BYTES);
+            // K-block j starts j rows (j * 128 B) into the slab.  The swizzle atoms themselves stay
+            // 1024-byte aligned (TMA wrote them), so the descriptor's base offset stays 0.
+            const bool use_base = getenv("SNK_TC_SLAB_BASE") != nullptr;
+            for (int j = 0; j < m; ++j) add_sub(ablk[(size_t)j * tblocks + b], j * BK * 2, use_base ? (j & 7) : 0, valid);
+        } else {
+            for (int j = 0; j < m; ++j) {
+                add_load(1, j, b * BK, TILE_BYTES);
+                add_sub(ablk[(size_t)j * tblocks + b], 0, 0, valid);
+            }
+        }
+    }
+    (void)nS;
+    h->ok = !overflow && h->nkb >= 1 && h->nkb <= MAXKB;
     if (!h->ok) return 0;
     h->ldq = h->nkb * BK;
+    const size_t fixed = 1024 + (size_t)h->nkb * TILE_BYTES + 16 * MAX_STAGES + 8 + 32 + 16 + 2 * BN * 4 + 64;
+    h->stages = (int)std::min<size_t>(MAX_STAGES, (227 * 1024 - fixed) / SLOT_BYTES);
+    if (h->stages < 2) { h->ok = false; return 0; }
     SNK_CUDA(cudaMalloc((void **)&h->d_qmap, qmap.size() * sizeof(short)));
     SNK_CUDA(cudaMemcpy(h->d_qmap, qmap.data(), qmap.size() * sizeof(short), cudaMemcpyHostToDevice));
     return 0;
@@ -396,10 +487,13 @@ int snk_tc_prepare(snk_db *db) {
     s->encode = (encode_fn)fn;
     SNK_TRY(make_map(s->encode, &s->mapS, db->S16, (uint64_t)db->ldS16, (uint64_t)db->N + 1, (uint64_t)db->ldS16, BN));
     SNK_TRY(make_map(s->encode, &s->mapG, db->G16, (uint64_t)db->ldG16, (uint64_t)db->N, (uint64_t)db->ldG16, BN));
+    SNK_TRY(make_map(s->encode, &s->mapGslab, db->G16, (uint64_t)db->ldG16, (uint64_t)db->N, (uint64_t)db->ldG16,
+                     BN + SLAB_EXTRA));
     for (int sp = 0; sp < 2; ++sp) {
         SNK_TRY(build_space(db, sp, &s->sp[sp]));
         if (s->sp[sp].ok) {
-            s->smem[sp] = smem_bytes(s->sp[sp].nkb);
+            s->smem[sp] = 1024 + (size_t)s->sp[sp].nkb * TILE_BYTES + (size_t)s->sp[sp].stages * SLOT_BYTES +
+                          16 * MAX_STAGES + 8 + 32 + 16 + 2 * BN * 4 + 64;
             if (s->smem[sp] > 227 * 1024) s->sp[sp].ok = false;
         }
     }
@@ -440,10 +534,9 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
     SNK_TRY(make_map(s->encode, &mapQ, dQ16, (uint64_t)ldq16, (uint64_t)nq_pad, (uint64_t)ldq16, BM));
     tc_params p;
     memset(&p, 0, sizeof(p));
-    p.nkb = h.nkb;
-    for (int i = 0; i < h.nkb; ++i) {
-        p.kb_map[i] = h.kb_map[i]; p.kb_rowoff[i] = h.kb_rowoff[i]; p.kb_col[i] = h.kb_col[i]; p.kb_ksteps[i] = h.kb_ksteps[i];
-    }
+    p.nkb = h.nkb; p.nload = h.nload; p.nsub = h.nsub; p.stages = h.stages;
+    memcpy(p.load, h.load, sizeof(h.load));
+    memcpy(p.sub, h.sub, sizeof(h.sub));
     p.nq = nq;
     p.nrm = space == SNK_SPACE_JOINT ? db->nrm_j16 : db->nrm_t16;
     const size_t smem = s->smem[space];
@@ -461,7 +554,7 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         p.oid = (int *)(p.oval + nlist);
         {
             snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)sp.rows * sp.D, st);
-            knn_tc_kernel<false><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, p);
+            knn_tc_kernel<false><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
         }
         SNK_CUDA(cudaGetLastError());
         chunk_tau_kernel<<<64, 256, 0, st>>>(p.oval, nq, nchunks, d_tau);
@@ -494,7 +587,7 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         p.chunk_rows = snk_cdiv(tiles, nchunks) * BN;
         {
             snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)rn * sp.D, st);
-            knn_tc_kernel<true><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, p);
+            knn_tc_kernel<true><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
         }
         SNK_CUDA(cudaGetLastError());
         db->counters[2] += 1;

@@ -1,0 +1,119 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink) for the exchange.
+
+Two shardings exist on this path:
+
+* greedy / join+Viterbi shard by UTTERANCE with the database replicated -- no data-path collective,
+  only a final gather of the (tiny) integer paths to rank 0;
+* k-NN over a database too large or too slow for one GPU shards the database ROWS: every rank
+  searches its block with the replicated queries, the per-shard top-k (float64 distance, int64
+  global row id) are all-gathered (nq*k*16 bytes per rank -- latency bound) and k-way merged on the
+  GPU by snk_topk_merge_dev with the lowest-global-id tie rule.
+
+The reference has no distributed code at all (only multiprocessing.Pool over utterances,
+script/synth_halfphone.py:897-903), so there is no reference interface to mirror here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import engine
+
+
+def shard_rows(n_rows, rank, world):
+    """Contiguous block partition [lo, hi) of database rows; blocks differ by at most one row."""
+    base, rem = divmod(int(n_rows), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_utterances(n_utts, rank, world):
+    """Round-robin utterance assignment (keeps long/short utterances balanced after a length sort)."""
+    return list(range(rank, int(n_utts), int(world)))
+
+
+def merge_topk_reference(dist_all, idx_all):
+    """Pure-torch k-way merge of [R, nq, k] ascending lists (ties: lowest id).  Used for CPU tensors in
+    the gloo tests and as the checker of the CUDA merge kernel; the GPU path uses snk_topk_merge_dev."""
+    import torch
+    R, nq, k = dist_all.shape
+    d = dist_all.permute(1, 0, 2).reshape(nq, R * k)
+    i = idx_all.permute(1, 0, 2).reshape(nq, R * k)
+    order = torch.argsort(i, dim=1, stable=True)
+    d, i = torch.gather(d, 1, order), torch.gather(i, 1, order)
+    order = torch.argsort(d, dim=1, stable=True)[:, :k]
+    return torch.gather(d, 1, order), torch.gather(i, 1, order)
+
+
+def allgather_merge_topk(dist_local, idx_local, group=None):
+    """All-gather per-shard [nq, k] results and merge them; every rank returns the global top-k."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    nq, k = dist_local.shape
+    d_all = torch.empty((world * nq, k), dtype=dist_local.dtype, device=dist_local.device)
+    i_all = torch.empty((world * nq, k), dtype=idx_local.dtype, device=idx_local.device)
+    dist.all_gather_into_tensor(d_all, dist_local.contiguous(), group=group)
+    dist.all_gather_into_tensor(i_all, idx_local.contiguous(), group=group)
+    d_all, i_all = d_all.view(world, nq, k), i_all.view(world, nq, k)
+    if not dist_local.is_cuda:
+        return merge_topk_reference(d_all, i_all)
+    out_d = torch.empty_like(dist_local)
+    out_i = torch.empty_like(idx_local)
+    lib = engine.load_library()
+    stream = torch.cuda.current_stream(dist_local.device)
+    rc = lib.snk_topk_merge_dev(dist_local.device.index, C.c_void_p(d_all.data_ptr()), C.c_void_p(i_all.data_ptr()),
+                                world, nq, k, C.c_void_p(out_d.data_ptr()), C.c_void_p(out_i.data_ptr()),
+                                C.c_void_p(stream.cuda_stream))
+    if rc:
+        raise engine.EngineError(lib.snk_last_error().decode())
+    return out_d, out_i
+
+
+class ShardedKnn:
+    """Database rows block-partitioned over the ranks of a process group; `.query` returns the same
+    (dist, idx) on every rank as a single-GPU search of the whole matrix would."""
+
+    def __init__(self, F_full_or_shard, weights, n_rows_total, rank, world, device, is_shard=False, group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.lo, self.hi = shard_rows(n_rows_total, rank, world)
+        F = F_full_or_shard if is_shard else F_full_or_shard[self.lo:self.hi]
+        F = np.ascontiguousarray(F, dtype=np.float32)
+        self.db = engine.UnitDatabase(F, np.zeros((F.shape[0] + 1, 1), np.float32), multiepoch=1, device=device)
+        self.db.set_weights(np.asarray(weights, dtype=np.float64), np.ones(1))
+        self.device = device
+
+    def query_local_dev(self, q_dev, k):
+        """q_dev: torch float64 CUDA tensor [nq, D]; returns local top-k with GLOBAL row ids."""
+        import torch
+        nq = q_dev.shape[0]
+        d = torch.empty((nq, k), dtype=torch.float64, device=q_dev.device)
+        i = torch.empty((nq, k), dtype=torch.int64, device=q_dev.device)
+        lib = engine.load_library()
+        stream = torch.cuda.current_stream(q_dev.device)
+        rc = lib.snk_knn_dev(self.db.handle, engine.SPACE_TARGET, C.c_void_p(q_dev.data_ptr()), nq, k,
+                             C.c_void_p(d.data_ptr()), C.c_void_p(i.data_ptr()), self.lo, C.c_void_p(stream.cuda_stream))
+        if rc:
+            raise engine.EngineError(lib.snk_last_error().decode())
+        return d, i
+
+    def query(self, q_dev, k):
+        d, i = self.query_local_dev(q_dev, k)
+        if self.world == 1:
+            return d, i
+        return allgather_merge_topk(d, i, self.group)
+
+
+def gather_paths(paths_local, utt_ids_local, n_utts, group=None):
+    """Collect utterance-sharded path lists on every rank in utterance order (object all-gather: the
+    payload is a few KB of integers)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    box = [None] * world
+    dist.all_gather_object(box, (list(utt_ids_local), list(paths_local)), group=group)
+    out = [None] * n_utts
+    for ids, paths in box:
+        for u, p in zip(ids, paths):
+            out[u] = p
+    return out
