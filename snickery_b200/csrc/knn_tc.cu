@@ -137,6 +137,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// one lane of the (fully active) warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // three-input minimum (sm_100)
 __device__ __forceinline__ float min3(float a, float b, float c) {
     float r;
@@ -144,17 +151,11 @@ __device__ __forceinline__ float min3(float a, float b, float c) {
     return r;
 }
 
-// K-major, 128-byte swizzled operand tile: rows of 64 fp16 (128 B), 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t base_off = 0) {
-    uint64_t d = 0;
-    d |= (uint64_t)(base_off & 7u) << 49;              // start row inside the 8-row swizzle atom
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
-    d |= (uint64_t)0 << 16;                            // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
-    return d;
-}
+// Shared-memory operand descriptors (K-major, 128-byte swizzle: rows of 64 fp16 = 128 B, 8-row groups
+// 1024 B apart) are assembled in the MMA warp: start address >> 4 in bits 0-13, stride byte offset
+// 1024 >> 4 in bits 32-45, version 1 in bits 46-47, SWIZZLE_128B (2) in bits 61-63.  The hardware
+// applies the swizzle to absolute address bits, so an operand may start on any row of a slab
+// (base offset field stays 0) and advance along K by +32 B per UMMA_K step.
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=128
 constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -177,7 +178,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     const uint32_t s_tmem_ptr = bar_tempty + 16;
     uint8_t *g_after = gbase + (size_t)p.nkb * TILE_BYTES + (size_t)STAGES * SLOT_BYTES + 16 * MAX_STAGES + 8 + 32;
     volatile uint32_t *tmem_ptr_g = reinterpret_cast<volatile uint32_t *>(g_after);
-    float *nrm_s = reinterpret_cast<float *>(g_after + 16);           // [2][BN]
+    float *nrm_s = reinterpret_cast<float *>(g_after + 24);           // [2][BN], 16-byte aligned
+    uint4 *sub_s = reinterpret_cast<uint4 *>(g_after + 24 + 2 * BN * 4);   // [MAXSUB] {a start addr >> 4, b byte offset, ksteps, -}
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x / p.nchunks, chunk = blockIdx.x % p.nchunks;
@@ -205,7 +207,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             tma_prefetch_desc(&mapQ);
             tma_prefetch_desc(&mapS);
             tma_prefetch_desc(&mapG);
@@ -213,51 +215,65 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             mbar_expect_tx(bar_a, (uint32_t)p.nkb * TILE_BYTES);
             for (int kb = 0; kb < p.nkb; ++kb)
                 tma_load_2d(sA + kb * TILE_BYTES, &mapQ, kb * BK, qt * BM, bar_a);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = 0; t < ntiles; ++t) {
-                const int64_t r0 = row_beg + (int64_t)t * BN;
-                for (int l = 0; l < p.nload; ++l) {
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int64_t r0 = row_beg + (int64_t)t * BN;
+            for (int l = 0; l < p.nload; ++l) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                if (elect_one()) {
                     const tc_load ld = p.load[l];
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     mbar_expect_tx(bar_full + 8 * stage, (uint32_t)ld.bytes);
                     const CUtensorMap *map = ld.map == 0 ? &mapS : (ld.map == 1 ? &mapG : &mapGslab);
                     tma_load_2d(sB + stage * SLOT_BYTES, map, ld.col, (int)(r0 + ld.rowoff), bar_full + 8 * stage);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (single thread) =====================
-        if (lane == 0) {
-            mbar_wait(bar_a, 0);
+        // ===================== MMA issuer (whole warp walks the pipeline, one elected lane issues) ==========
+        if (lane < p.nsub) {
+            const tc_sub su = p.sub[lane];
+            sub_s[lane] = make_uint4((sA + (uint32_t)su.a_blk * TILE_BYTES) >> 4, (uint32_t)su.b_off, (uint32_t)su.ksteps, 0u);
+        }
+        __syncwarp();
+        mbar_wait(bar_a, 0);
+        tc_fence_after();
+        constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int acc = t & 1;
+            const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
+            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);       // epilogue has drained this accumulator
             tc_fence_after();
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = 0; t < ntiles; ++t) {
-                const int acc = t & 1;
-                const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
-                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);       // epilogue has drained this accumulator
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+            int sb = 0;
+            for (int l = 0; l < p.nload; ++l) {
+                const int sb_end = sb + p.load[l].nsub;
+                mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
-                uint32_t accumulate = 0;
-                for (int l = 0; l < p.nload; ++l) {
-                    mbar_wait(bar_full + 8 * stage, phase);
-                    tc_fence_after();
-                    const int s0 = p.load[l].sub0, s1 = s0 + p.load[l].nsub;
-                    for (int sb = s0; sb < s1; ++sb) {
-                        const tc_sub su = p.sub[sb];
-                        const uint64_t a_desc = make_smem_desc(sA + su.a_blk * TILE_BYTES);
-                        const uint64_t b_desc = make_smem_desc(sB + stage * SLOT_BYTES + su.b_off, su.base_off);
-                        for (int ks = 0; ks < su.ksteps; ++ks) {   // +32 B along K inside the swizzle row = +2 in the address field
-                            umma_f16(d_tmem, a_desc + 2u * ks, b_desc + 2u * ks, IDESC, accumulate);
-                            accumulate = 1;
-                        }
+                if (elect_one()) {
+                    const uint32_t bbase = sB + (uint32_t)stage * SLOT_BYTES;
+                    for (int i = sb; i < sb_end; ++i) {
+                        const uint4 su = sub_s[i];
+                        const uint64_t a_desc = DESC_HI | (uint64_t)(su.x & 0x3FFFu);
+                        const uint64_t b_desc = DESC_HI | (uint64_t)(((bbase + su.y) >> 4) & 0x3FFFu);
+                        // +32 B along K inside the 128 B swizzle row = +2 in the start-address field
+                        umma_f16(d_tmem, a_desc, b_desc, IDESC, (uint32_t)(l | i) != 0u);
+                        if (su.z > 1) umma_f16(d_tmem, a_desc + 2, b_desc + 2, IDESC, 1u);
+                        if (su.z > 2) umma_f16(d_tmem, a_desc + 4, b_desc + 4, IDESC, 1u);
+                        if (su.z > 3) umma_f16(d_tmem, a_desc + 6, b_desc + 6, IDESC, 1u);
                     }
-                    umma_commit(bar_empty + 8 * stage);               // smem slot reusable once these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(bar_empty + 8 * stage);           // smem slot reusable once these MMAs retire
+                    if (l == p.nload - 1) umma_commit(bar_tfull + 8 * acc);   // accumulator complete
                 }
-                umma_commit(bar_tfull + 8 * acc);                     // accumulator complete
+                __syncwarp();
+                sb = sb_end;
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else {
@@ -270,11 +286,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         int li[LSZ];
 #pragma unroll
         for (int i = 0; i < LSZ; ++i) { lv[i] = INFINITY; li[i] = -1; }
+        float nrm_next = (ntiles > 0 && row_beg + et < row_end) ? __ldg(p.nrm + row_beg + et) : INFINITY;
         for (int t = 0; t < ntiles; ++t) {
             const int acc = t & 1;
             const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
             const int64_t r0 = row_beg + (int64_t)t * BN;
-            nrm_s[acc * BN + et] = (r0 + et < row_end) ? __ldg(p.nrm + r0 + et) : INFINITY;
+            nrm_s[acc * BN + et] = nrm_next;
+            nrm_next = (t + 1 < ntiles && r0 + BN + et < row_end) ? __ldg(p.nrm + r0 + BN + et) : INFINITY;   // next tile's norm, a tile early
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
@@ -463,7 +481,7 @@ int build_space(snk_db *db, int space, tc_space_host *h) {
     h->ok = !overflow && h->nkb >= 1 && h->nkb <= MAXKB;
     if (!h->ok) return 0;
     h->ldq = h->nkb * BK;
-    const size_t fixed = 1024 + (size_t)h->nkb * TILE_BYTES + 16 * MAX_STAGES + 8 + 32 + 16 + 2 * BN * 4 + 64;
+    const size_t fixed = 1024 + (size_t)h->nkb * TILE_BYTES + 16 * MAX_STAGES + 8 + 32 + 16 + 2 * BN * 4 + MAXSUB * 16 + 64;
     h->stages = (int)std::min<size_t>(MAX_STAGES, (227 * 1024 - fixed) / SLOT_BYTES);
     if (h->stages < 2) { h->ok = false; return 0; }
     SNK_CUDA(cudaMalloc((void **)&h->d_qmap, qmap.size() * sizeof(short)));
@@ -493,7 +511,7 @@ int snk_tc_prepare(snk_db *db) {
         SNK_TRY(build_space(db, sp, &s->sp[sp]));
         if (s->sp[sp].ok) {
             s->smem[sp] = 1024 + (size_t)s->sp[sp].nkb * TILE_BYTES + (size_t)s->sp[sp].stages * SLOT_BYTES +
-                          16 * MAX_STAGES + 8 + 32 + 16 + 2 * BN * 4 + 64;
+                          16 * MAX_STAGES + 8 + 32 + 16 + 2 * BN * 4 + MAXSUB * 16 + 64;
             if (s->smem[sp] > 227 * 1024) s->sp[sp].ok = false;
         }
     }
