@@ -34,10 +34,11 @@ constexpr int MAXKB = 10;      // resident query K-blocks
 constexpr int MAXLOAD = 10;    // TMA loads per database tile
 constexpr int MAXSUB = 16;     // MMA K-blocks per database tile
 constexpr int SLAB_EXTRA = 8;  // extra rows of a frame slab: serves window offsets 0..8
-constexpr int LSZ = 8;         // per-(query, chunk) list length of the fused epilogue
+constexpr int EPI_SPLIT = 2;   // epilogue warps per TMEM lane quarter: each takes BN / EPI_SPLIT columns of a tile
 constexpr int TILE_BYTES = BM * BK * 2;                    // 16 KiB query K-block
 constexpr int SLOT_BYTES = (BN + SLAB_EXTRA) * BK * 2;     // 17 KiB ring slot (plain tile or frame slab)
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_THREADS = 128 * EPI_SPLIT;
+constexpr int NUM_THREADS = 64 + NUM_EPI_THREADS;
 constexpr uint32_t TMEM_COLS = 256;       // two 128-column fp32 accumulators
 
 // One TMA load per ring slot; it feeds nsub MMA K-blocks.  A frame slab (BN + 8 rows of G16) feeds the
@@ -55,7 +56,7 @@ struct tc_params {
     int nchunks;
     int64_t nq;
     const float *nrm;       // [rows] squared norms of the fp16 rows
-    float *oval;            // fused : [nq_pad, nchunks, LSZ] keys (ascending)
+    float *oval;            // fused : [nq_pad, nchunks * EPI_SPLIT, LSZ] keys (ascending)
     int *oid;               //         row ids
     float *odist;           // store : [nq, ldo] keys of rows row_lo ..
     int64_t ldo;
@@ -160,7 +161,7 @@ __device__ __forceinline__ float min3(float a, float b, float c) {
 constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 // ---------------------------------------------------------------- kernel
-template <bool kStore>
+template <bool kStore, int LSZ>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapS,
               const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapGslab,
@@ -195,7 +196,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         mbar_init(bar_a, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
-            mbar_init(bar_tempty + 8 * a, 128);
+            mbar_init(bar_tempty + 8 * a, NUM_EPI_THREADS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -279,30 +280,34 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     } else {
         // ===================== epilogue: one thread per query =====================
         const int quarter = warp & 3;                 // TMEM lanes this warp may read
+        const int half = (warp - 2) >> 2;             // which BN / EPI_SPLIT column range of every tile
         const int ql = quarter * 32 + lane;           // query row inside the tile == TMEM lane
         const int64_t q = (int64_t)qt * BM + ql;
-        const int et = (warp - 2) * 32 + lane;        // 0..127 among the epilogue threads
+        const int et = (warp - 2) * 32 + lane;        // 0 .. NUM_EPI_THREADS-1 among the epilogue threads
+        constexpr int COLS = BN / EPI_SPLIT;
         float lv[LSZ];
         int li[LSZ];
 #pragma unroll
         for (int i = 0; i < LSZ; ++i) { lv[i] = INFINITY; li[i] = -1; }
-        float nrm_next = (ntiles > 0 && row_beg + et < row_end) ? __ldg(p.nrm + row_beg + et) : INFINITY;
+        float nrm_next = (et < BN && ntiles > 0 && row_beg + et < row_end) ? __ldg(p.nrm + row_beg + et) : INFINITY;
         for (int t = 0; t < ntiles; ++t) {
             const int acc = t & 1;
             const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
             const int64_t r0 = row_beg + (int64_t)t * BN;
-            nrm_s[acc * BN + et] = nrm_next;
-            nrm_next = (t + 1 < ntiles && r0 + BN + et < row_end) ? __ldg(p.nrm + r0 + BN + et) : INFINITY;   // next tile's norm, a tile early
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et < BN) {
+                nrm_s[acc * BN + et] = nrm_next;
+                nrm_next = (t + 1 < ntiles && r0 + BN + et < row_end) ? __ldg(p.nrm + r0 + BN + et) : INFINITY;   // next tile's norm, a tile early
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * BN;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += 32) {
                 float v[32];
                 __syncwarp();
                 tmem_ld32(taddr + c0, v);
-                if (c0 + 32 == BN) {                  // accumulator fully read: hand it back to the MMA warp
+                if (c0 + 32 == (half + 1) * COLS) {   // this thread's part of the accumulator is read: hand it back
                     tc_fence_before();
                     mbar_arrive(bar_tempty + 8 * acc);
                 }
@@ -353,11 +358,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                                         if (kk < lv[LSZ - 1]) {
                                             int id = (int)(r0 + c0 + gi * 8 + e);
 #pragma unroll
-                                            for (int i = 0; i < LSZ; ++i) {   // bubble into the ascending list; ties keep the lower row
-                                                if (kk < lv[i]) {
-                                                    const float tv = lv[i]; lv[i] = kk; kk = tv;
-                                                    const int ti = li[i]; li[i] = id; id = ti;
-                                                }
+                                            for (int i = 0; i < LSZ; ++i) {   // sink into the ascending list; ties keep the lower row
+                                                const bool c = kk < lv[i];
+                                                const float lo = fminf(kk, lv[i]), hi = fmaxf(kk, lv[i]);
+                                                const int ilo = c ? id : li[i], ihi = c ? li[i] : id;
+                                                lv[i] = lo; li[i] = ilo; kk = hi; id = ihi;
                                             }
                                         }
                                     }
@@ -369,8 +374,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             }
         }
         if (!kStore) {
-            float *ov = p.oval + ((size_t)q * p.nchunks + chunk) * LSZ;
-            int *oi = p.oid + ((size_t)q * p.nchunks + chunk) * LSZ;
+            float *ov = p.oval + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * LSZ;
+            int *oi = p.oid + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * LSZ;
 #pragma unroll
             for (int i = 0; i < LSZ; ++i) { ov[i] = lv[i]; oi[i] = li[i]; }
         }
@@ -382,10 +387,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
 
 // per query: tau = min over chunks of the chunk list's largest key (a row dropped inside a chunk has a
 // key >= that chunk's LSZ-th smallest)
-__global__ void chunk_tau_kernel(const float *__restrict__ oval, int64_t nq, int nchunks, float *__restrict__ tau) {
+__global__ void chunk_tau_kernel(const float *__restrict__ oval, int64_t nq, int nlists, int lsz, float *__restrict__ tau) {
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
         float t = INFINITY;
-        for (int c = 0; c < nchunks; ++c) t = fminf(t, oval[((size_t)q * nchunks + c) * LSZ + LSZ - 1]);
+        for (int c = 0; c < nlists; ++c) t = fminf(t, oval[((size_t)q * nlists + c) * lsz + lsz - 1]);
         tau[q] = t;
     }
 }
@@ -515,8 +520,9 @@ int snk_tc_prepare(snk_db *db) {
             if (s->smem[sp] > 227 * 1024) s->sp[sp].ok = false;
         }
     }
-    SNK_CUDA(cudaFuncSetAttribute(knn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SNK_CUDA(cudaFuncSetAttribute(knn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SNK_CUDA(cudaFuncSetAttribute(knn_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SNK_CUDA(cudaFuncSetAttribute(knn_tc_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SNK_CUDA(cudaFuncSetAttribute(knn_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return 0;
 }
 
@@ -559,29 +565,35 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
     p.nrm = space == SNK_SPACE_JOINT ? db->nrm_j16 : db->nrm_t16;
     const size_t smem = s->smem[space];
     const int64_t row_tiles = snk_cdiv(sp.rows, BN);
-    const bool fused = k <= LSZ / 2;    // per-chunk lists of LSZ cover the k best with slack; larger k goes through the scan
-
+    // Fused lists hold the LSZ best keys per (query, chunk, column half); they cover the k best with slack
+    // (anything they miss is caught by the certificate).  Larger k goes through the key scan below.
+    const bool fused = k <= 4;
     if (fused) {
+        const int lsz = k <= 2 ? 4 : 8;
         int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(db->sm_count / std::max(nqt, 1), row_tiles));
         if (nqt > db->sm_count) nchunks = 1;
         p.row_lo = 0; p.row_hi = sp.rows; p.nchunks = nchunks;
         p.chunk_rows = snk_cdiv(row_tiles, nchunks) * BN;
-        const size_t nlist = (size_t)nq_pad * nchunks * LSZ;
+        const int nlists = nchunks * EPI_SPLIT;
+        const size_t nlist = (size_t)nq_pad * nlists * lsz;
         SNK_TRY(snk_buf_reserve(&db->ws_tc, nlist * 8));
         p.oval = (float *)db->ws_tc.p;
         p.oid = (int *)(p.oval + nlist);
         {
             snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)sp.rows * sp.D, st);
-            knn_tc_kernel<false><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
+            if (lsz == 4)
+                knn_tc_kernel<false, 4><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
+            else
+                knn_tc_kernel<false, 8><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
         }
         SNK_CUDA(cudaGetLastError());
-        chunk_tau_kernel<<<64, 256, 0, st>>>(p.oval, nq, nchunks, d_tau);
+        chunk_tau_kernel<<<64, 256, 0, st>>>(p.oval, nq, nlists, lsz, d_tau);
         SNK_CUDA(cudaGetLastError());
         db->counters[2] += 2;
         for (int64_t q0 = 0; q0 < nq; q0 += 32768) {
             const int64_t n = std::min<int64_t>(32768, nq - q0);
-            SNK_TRY(snk_topk_scan(db, p.oval + (size_t)q0 * nchunks * LSZ, p.oid + (size_t)q0 * nchunks * LSZ, n,
-                                  (int64_t)nchunks * LSZ, (int64_t)nchunks * LSZ, 0, KP, true, d_val + q0 * KP,
+            SNK_TRY(snk_topk_scan(db, p.oval + (size_t)q0 * nlists * lsz, p.oid + (size_t)q0 * nlists * lsz, n,
+                                  (int64_t)nlists * lsz, (int64_t)nlists * lsz, 0, KP, true, d_val + q0 * KP,
                                   d_id + q0 * KP, st));
         }
         return 0;
@@ -605,7 +617,7 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         p.chunk_rows = snk_cdiv(tiles, nchunks) * BN;
         {
             snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)rn * sp.D, st);
-            knn_tc_kernel<true><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
+            knn_tc_kernel<true, 4><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
         }
         SNK_CUDA(cudaGetLastError());
         db->counters[2] += 1;
