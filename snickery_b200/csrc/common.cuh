@@ -132,8 +132,11 @@ const short *snk_tc_qmap(const snk_db *db, int space);      // device map: opera
 // dQ16 [round_up(nq,128), ldq16] fp16 queries in K-block order.  Writes the KP smallest approximate
 // keys (||y~||^2 - 2 x~.y~, f32) with row ids per query (unsorted) and d_tau[q], a lower bound on the
 // key of every row that was dropped before the final merge (+inf if none was).
+// If `lists` is given and the per-chunk lists are small enough for the fused merge+re-rank kernel, the
+// merge is skipped: lists->valid is set and the raw [nq, nlists, lsz] lists are returned instead.
+struct snk_tc_lists { bool valid; const float *val; const int *id; int nlists, lsz; };
 int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64_t nq, int k, int KP,
-                     float *d_val, int *d_id, float *d_tau, cudaStream_t st);
+                     float *d_val, int *d_id, float *d_tau, snk_tc_lists *lists, cudaStream_t st);
 
 // ---- rerank.cu
 // Exact float64 distances of the shortlisted rows, sorted ascending (ties: lowest id).
@@ -146,6 +149,12 @@ int snk_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, co
                int64_t id_offset, const float *d_qerr, const float *d_dberr, const float *d_qn,
                const float *d_maxn, const float *d_tau_extra, int *d_cert, const int *d_qsel,
                cudaStream_t st);
+
+bool snk_merge_rerank_fits(int nlists, int lsz);
+int snk_merge_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, const float *d_lval,
+                     const int *d_lid, int nlists, int lsz, int KP, int k, double *d_dist, int64_t *d_idx,
+                     int64_t out_stride, int64_t id_offset, const float *d_qerr, const float *d_dberr,
+                     const float *d_qn, const float *d_maxn, int *d_cert, cudaStream_t st);
 
 // ---- search.cu : k-NN driver shared by snk_knn and the greedy loop
 // dQ float64 [nq, D] device; results device.

@@ -547,7 +547,8 @@ int snk_tc_query_ld(const snk_db *db, int space) { return ((const tc_state *)db-
 const short *snk_tc_qmap(const snk_db *db, int space) { return ((const tc_state *)db->tc_state)->sp[space].d_qmap; }
 
 int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64_t nq, int k, int KP, float *d_val,
-                     int *d_id, float *d_tau, cudaStream_t st) {
+                     int *d_id, float *d_tau, snk_tc_lists *lists, cudaStream_t st) {
+    if (lists) lists->valid = false;
     tc_state *s = (tc_state *)db->tc_state;
     const tc_space_host &h = s->sp[space];
     SNK_CHECK(h.ok, "tensor-core engine does not support this search space");
@@ -587,6 +588,11 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
                 knn_tc_kernel<false, 8><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
         }
         SNK_CUDA(cudaGetLastError());
+        if (lists && snk_merge_rerank_fits(nlists, lsz)) {   // merge + tau happen inside the re-rank kernel
+            lists->valid = true; lists->val = p.oval; lists->id = p.oid; lists->nlists = nlists; lists->lsz = lsz;
+            db->counters[2] += 1;
+            return 0;
+        }
         chunk_tau_kernel<<<64, 256, 0, st>>>(p.oval, nq, nlists, lsz, d_tau);
         SNK_CUDA(cudaGetLastError());
         db->counters[2] += 2;

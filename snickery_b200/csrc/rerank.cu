@@ -1,70 +1,157 @@
-// Exact float64 re-rank of a shortlist + exactness certificate.
+// Exact float64 re-rank of a shortlist + exactness certificate (+ optional fused list merge).
 //
 // The reference evaluates distances in float64 on rows weight(f32 data, f64 weights)
 // (script/speech_manip.py:209-213) -- both inside the KD-tree (script/synth_simple.py:229,490)
 // and in explicit numpy code (script/synth_halfphone.py:1346-1351).  This kernel recomputes
 // exactly those float64 values for the shortlisted rows from the RAW float32 matrices and the
 // float64 weight vectors, so the final ordering is decided on the reference's own numbers.
+//
+// kMerge = true: the input is the tensor-core kernel's per-(chunk, column-half) lists
+// [nq, nlists, lsz] (ascending keys); the block first selects the KP smallest by rank counting and
+// derives tau = min over lists of the list's largest key, then proceeds as below.  This fuses what
+// used to be three launches (chunk_tau, topk_scan merge, rerank) of the greedy step.
 #include "common.cuh"
 #include <limits.h>
 
 namespace {
+
+constexpr int RR_THREADS = 256;
+constexpr int RR_MAX_MERGE = 1024;   // most list entries a block merges in shared memory
 
 struct rr_space {
     const float *A;    // Jc_raw
     const float *B;    // F_raw
     const double *wA;  // wj
     const double *wB;  // wt
-    int dA, D, a_row_off, a_col, ldA, ldB, periodB;
+    int dA, dB, D, a_row_off, a_col, ldA, ldB, Dt, m;
 };
-
-__device__ __forceinline__ double rr_elem(const rr_space &sp, int64_t u, int d) {
-    if (d < sp.dA) {
-        const int c = sp.a_col + d;
-        return (double)__ldg(sp.A + (u + sp.a_row_off) * (int64_t)sp.ldA + c) * __ldg(sp.wA + c);
-    }
-    const int c = d - sp.dA;
-    return (double)__ldg(sp.B + u * (int64_t)sp.ldB + c) * __ldg(sp.wB + (c % sp.periodB));
-}
 
 __device__ __forceinline__ bool dpair_lt(double v1, int i1, double v2, int i2) {
     return v1 < v2 || (v1 == v2 && i1 < i2);
 }
+__device__ __forceinline__ bool fpair_lt(float v1, int i1, float v2, int i2) {
+    return v1 < v2 || (v1 == v2 && i1 < i2);
+}
 
-__global__ void __launch_bounds__(128)
-rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict__ val,
-              const int *__restrict__ id, int KP, int k, double *__restrict__ odist,
-              int64_t *__restrict__ oidx, int64_t ostride, int64_t id_offset, int64_t nrows,
-              const float *__restrict__ qerr, const float *__restrict__ dberr,
-              const float *__restrict__ qn, const float *__restrict__ maxn,
+// squared float64 distances of rows u0 and u1 (u1 < 0: only u0) to the query held in shared memory
+__device__ __forceinline__ void row_pair_dist(const rr_space &sp, const double *__restrict__ q_s,
+                                              const double *__restrict__ wA_s, const double *__restrict__ wB_s, int u0,
+                                              int u1, int lane, double &out0, double &out1) {
+    double a0 = 0.0, a1 = 0.0;
+    const bool two = u1 >= 0;
+    const int v1 = two ? u1 : u0;
+    if (sp.dA > 0) {
+        const float *r0 = sp.A + ((int64_t)u0 + sp.a_row_off) * sp.ldA + sp.a_col;
+        const float *r1 = sp.A + ((int64_t)v1 + sp.a_row_off) * sp.ldA + sp.a_col;
+        for (int d = lane; d < sp.dA; d += 32) {
+            const double w = wA_s[d], x = q_s[d];
+            const double y0 = (double)__ldg(r0 + d) * w, y1 = (double)__ldg(r1 + d) * w;
+            const double e0 = __dsub_rn(x, y0), e1 = __dsub_rn(x, y1);
+            a0 = __dadd_rn(a0, __dmul_rn(e0, e0));
+            a1 = __dadd_rn(a1, __dmul_rn(e1, e1));
+        }
+    }
+    // the m-frame window of row u is contiguous in F_raw: frames u .. u+m-1
+    const float *f0 = sp.B + (int64_t)u0 * sp.ldB;
+    const float *f1 = sp.B + (int64_t)v1 * sp.ldB;
+    for (int j = 0; j < sp.m; ++j) {
+        const double *qj = q_s + sp.dA + j * sp.Dt;
+        for (int c = lane; c < sp.Dt; c += 32) {
+            const double w = wB_s[c], x = qj[c];
+            const double y0 = (double)__ldg(f0 + j * sp.ldB + c) * w, y1 = (double)__ldg(f1 + j * sp.ldB + c) * w;
+            const double e0 = __dsub_rn(x, y0), e1 = __dsub_rn(x, y1);
+            a0 = __dadd_rn(a0, __dmul_rn(e0, e0));
+            a1 = __dadd_rn(a1, __dmul_rn(e1, e1));
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a0 = __dadd_rn(a0, __shfl_xor_sync(0xffffffffu, a0, off));
+        a1 = __dadd_rn(a1, __shfl_xor_sync(0xffffffffu, a1, off));
+    }
+    out0 = a0;
+    out1 = two ? a1 : INFINITY;
+}
+
+template <bool kMerge>
+__global__ void __launch_bounds__(RR_THREADS)
+rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict__ val, const int *__restrict__ id,
+              int KP, int nlists, int lsz, int k, double *__restrict__ odist, int64_t *__restrict__ oidx,
+              int64_t ostride, int64_t id_offset, int64_t nrows, const float *__restrict__ qerr,
+              const float *__restrict__ dberr, const float *__restrict__ qn, const float *__restrict__ maxn,
               const float *__restrict__ tau_extra, int *__restrict__ cert, int *__restrict__ nfail,
               const int *__restrict__ qsel) {
     extern __shared__ double sm[];
-    double *d2 = sm;
-    int *ids = reinterpret_cast<int *>(sm + KP);
+    double *q_s = sm;                       // [D]
+    double *wA_s = q_s + sp.D;              // [dA]
+    double *wB_s = wA_s + sp.dA;            // [Dt]
+    double *d2 = wB_s + sp.Dt;              // [KP]
+    int *ids = reinterpret_cast<int *>(d2 + KP);          // [KP]
+    float *sval = reinterpret_cast<float *>(ids + KP);    // [KP] approximate keys of the selected rows
+    float *mval = sval + KP;                               // kMerge: [n] all list keys
+    int *mid = reinterpret_cast<int *>(mval + (kMerge ? nlists * lsz : 0));   // kMerge: [n] all list ids
+    __shared__ float s_wtau[RR_THREADS / 32];
+
     const int64_t ql = blockIdx.x;                    // index into the (compact) shortlist arrays
     const int64_t q = qsel ? qsel[ql] : ql;           // index into queries / outputs / per-query bounds
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const double *qrow = Q + q * (int64_t)sp.D;
-    for (int c = warp; c < KP; c += nwarp) {
-        const int u = id[ql * KP + c];
-        double acc = INFINITY;
-        if (u >= 0) {
-            acc = 0.0;
-            for (int d = lane; d < sp.D; d += 32) {
-                const double df = __dsub_rn(qrow[d], rr_elem(sp, u, d));
-                acc = __dadd_rn(acc, __dmul_rn(df, df));
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = RR_THREADS >> 5;
+
+    for (int d = tid; d < sp.D; d += RR_THREADS) q_s[d] = Q[q * (int64_t)sp.D + d];
+    for (int d = tid; d < sp.dA; d += RR_THREADS) wA_s[d] = sp.wA[sp.a_col + d];
+    for (int d = tid; d < sp.Dt; d += RR_THREADS) wB_s[d] = sp.wB[d];
+
+    if (kMerge) {
+        const int n = nlists * lsz;
+        const float *gv = val + ql * (int64_t)n;
+        const int *gi = id + ql * (int64_t)n;
+        for (int t = tid; t < n; t += RR_THREADS) {
+            const int i = gi[t];
+            mval[t] = i >= 0 ? gv[t] : INFINITY;
+            mid[t] = i >= 0 ? i : INT_MAX;
         }
-        if (lane == 0) {
-            d2[c] = acc;
-            ids[c] = u >= 0 ? u : INT_MAX;
+        for (int t = tid; t < KP; t += RR_THREADS) { sval[t] = INFINITY; ids[t] = INT_MAX; }
+        __syncthreads();
+        // a row dropped inside a list has a key >= that list's largest kept key
+        float tl = INFINITY;
+        for (int l = tid; l < nlists; l += RR_THREADS) tl = fminf(tl, mval[l * lsz + lsz - 1]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) tl = fminf(tl, __shfl_xor_sync(0xffffffffu, tl, off));
+        if (lane == 0) s_wtau[warp] = tl;
+        for (int t = tid; t < n; t += RR_THREADS) {
+            const float v = mval[t];
+            const int i = mid[t];
+            int rank = 0;
+            for (int j = 0; j < n; ++j)
+                rank += (fpair_lt(mval[j], mid[j], v, i) || (mval[j] == v && mid[j] == i && j < t)) ? 1 : 0;
+            if (rank < KP) { sval[rank] = v; ids[rank] = i; }
+        }
+    } else {
+        for (int t = tid; t < KP; t += RR_THREADS) {
+            const int i = id[ql * KP + t];
+            sval[t] = i >= 0 ? val[ql * KP + t] : INFINITY;
+            ids[t] = i >= 0 ? i : INT_MAX;
         }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < KP; t += blockDim.x) {
+
+    // exact distances, two shortlisted rows per warp pass
+    for (int c = 2 * warp; c < KP; c += 2 * nwarp) {
+        const int u0 = ids[c], u1 = (c + 1 < KP) ? ids[c + 1] : INT_MAX;
+        double r0 = INFINITY, r1 = INFINITY;
+        if (u0 != INT_MAX) {
+            row_pair_dist(sp, q_s, wA_s, wB_s, u0, u1 != INT_MAX ? u1 : -1, lane, r0, r1);
+        } else if (u1 != INT_MAX) {
+            double dummy;
+            row_pair_dist(sp, q_s, wA_s, wB_s, u1, -1, lane, r1, dummy);
+        }
+        if (lane == 0) {
+            d2[c] = r0;
+            if (c + 1 < KP) d2[c + 1] = r1;
+        }
+    }
+    __syncthreads();
+
+    for (int t = tid; t < KP; t += RR_THREADS) {
         const double v = d2[t];
         const int i = ids[t];
         int rank = 0;
@@ -75,18 +162,17 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
             odist[q * ostride + rank] = ok ? sqrt(v) : INFINITY;
             oidx[q * ostride + rank] = ok ? (int64_t)i + id_offset : nrows;
             if (cert && rank == k - 1) {
-                // every row outside the shortlist has approx distance >= tau; its true distance is
-                // >= tau - (||dx|| + ||dy||) by the triangle inequality (fp16 rounding of both sides)
                 // tau: smallest approximate key any row OUTSIDE the shortlist can have
                 float mx = -INFINITY;
                 bool full = true;
                 for (int j = 0; j < KP; ++j) {
-                    const float a = val[ql * KP + j];
-                    if (id[ql * KP + j] < 0) full = false;
-                    else mx = fmaxf(mx, a);
+                    if (ids[j] == INT_MAX) full = false;
+                    else mx = fmaxf(mx, sval[j]);
                 }
                 if (!full) mx = INFINITY;                       // the final merge dropped nothing
                 if (tau_extra) mx = fminf(mx, tau_extra[q]);    // ... but an earlier stage may have
+                if (kMerge)
+                    for (int w = 0; w < RR_THREADS / 32; ++w) mx = fminf(mx, s_wtau[w]);
                 int good = 1;
                 if (mx < INFINITY) {
                     const float qq = qn ? qn[q] : 0.f;
@@ -104,6 +190,18 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
     }
 }
 
+rr_space make_rr(const snk_db *db, const snk_space &sp) {
+    rr_space rs;
+    rs.A = db->Jc_raw; rs.B = db->F_raw; rs.wA = db->wj; rs.wB = db->wt;
+    rs.dA = sp.dA; rs.dB = sp.dB; rs.D = sp.D; rs.a_row_off = sp.a_row_off; rs.a_col = sp.a_col;
+    rs.ldA = sp.ldA_raw; rs.ldB = sp.ldB_raw; rs.Dt = db->Dt; rs.m = sp.dB / db->Dt;
+    return rs;
+}
+
+size_t rr_smem(const rr_space &rs, int KP, int nmerge) {
+    return (size_t)(rs.D + rs.dA + rs.Dt + KP) * 8 + (size_t)KP * 8 + (size_t)nmerge * 8 + 16;
+}
+
 }  // namespace
 
 int snk_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, const float *d_val,
@@ -113,15 +211,32 @@ int snk_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, co
                cudaStream_t st) {
     if (nq <= 0) return 0;
     SNK_CHECK(k <= KP, "rerank: k (%d) exceeds shortlist (%d)", k, KP);
-    rr_space rs;
-    rs.A = db->Jc_raw; rs.B = db->F_raw; rs.wA = db->wj; rs.wB = db->wt;
-    rs.dA = sp.dA; rs.D = sp.D; rs.a_row_off = sp.a_row_off; rs.a_col = sp.a_col;
-    rs.ldA = sp.ldA_raw; rs.ldB = sp.ldB_raw; rs.periodB = db->Dt;
-    const size_t smem = (size_t)KP * (sizeof(double) + sizeof(int));
-    rerank_kernel<<<(unsigned)nq, 128, smem, st>>>(rs, dQ, d_val, d_id, KP, k, d_dist, d_idx, out_stride,
-                                                    id_offset, sp.rows, d_qerr, d_dberr, d_qn, d_maxn,
-                                                    d_tau_extra, d_cert, d_cert ? d_cert + nq : nullptr,
-                                                    d_qsel);
+    const rr_space rs = make_rr(db, sp);
+    const size_t smem = rr_smem(rs, KP, 0);
+    rerank_kernel<false><<<(unsigned)nq, RR_THREADS, smem, st>>>(rs, dQ, d_val, d_id, KP, 0, 0, k, d_dist, d_idx,
+                                                                   out_stride, id_offset, sp.rows, d_qerr, d_dberr,
+                                                                   d_qn, d_maxn, d_tau_extra, d_cert,
+                                                                   d_cert ? d_cert + nq : nullptr, d_qsel);
+    SNK_CUDA(cudaGetLastError());
+    db->counters[2] += 1;
+    return 0;
+}
+
+bool snk_merge_rerank_fits(int nlists, int lsz) { return nlists * lsz <= RR_MAX_MERGE; }
+
+int snk_merge_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, const float *d_lval,
+                     const int *d_lid, int nlists, int lsz, int KP, int k, double *d_dist, int64_t *d_idx,
+                     int64_t out_stride, int64_t id_offset, const float *d_qerr, const float *d_dberr,
+                     const float *d_qn, const float *d_maxn, int *d_cert, cudaStream_t st) {
+    if (nq <= 0) return 0;
+    SNK_CHECK(k <= KP, "rerank: k (%d) exceeds shortlist (%d)", k, KP);
+    SNK_CHECK(snk_merge_rerank_fits(nlists, lsz), "merge_rerank: %d list entries exceed the in-block merge", nlists * lsz);
+    const rr_space rs = make_rr(db, sp);
+    const size_t smem = rr_smem(rs, KP, nlists * lsz);
+    rerank_kernel<true><<<(unsigned)nq, RR_THREADS, smem, st>>>(rs, dQ, d_lval, d_lid, KP, nlists, lsz, k, d_dist,
+                                                                  d_idx, out_stride, id_offset, sp.rows, d_qerr,
+                                                                  d_dberr, d_qn, d_maxn, nullptr, d_cert,
+                                                                  d_cert ? d_cert + nq : nullptr, nullptr);
     SNK_CUDA(cudaGetLastError());
     db->counters[2] += 1;
     return 0;

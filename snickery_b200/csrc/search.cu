@@ -155,12 +155,19 @@ int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, d
                                                          qerr);
         SNK_CUDA(cudaGetLastError());
         db->counters[2] += 1;
-        SNK_TRY(snk_shortlist_tc(db, space, q16, ld16, qn_, k, KP, val, id, tau, st));
+        snk_tc_lists lists;
+        SNK_TRY(snk_shortlist_tc(db, space, q16, ld16, qn_, k, KP, val, id, tau, &lists, st));
         SNK_CUDA(cudaMemsetAsync(cert + qn_, 0, 4, st));
         const bool joint = space == SNK_SPACE_JOINT;
-        SNK_TRY(snk_rerank(db, sp, Qb, qn_, val, id, KP, k, d_dist + qb * out_stride, d_idx + qb * out_stride,
-                           out_stride, id_offset, qerr, joint ? db->err_j16 : db->err_t16, qn,
-                           joint ? db->maxn_j16 : db->maxn_t16, tau, cert, nullptr, st));
+        if (lists.valid)
+            SNK_TRY(snk_merge_rerank(db, sp, Qb, qn_, lists.val, lists.id, lists.nlists, lists.lsz, KP, k,
+                                     d_dist + qb * out_stride, d_idx + qb * out_stride, out_stride, id_offset, qerr,
+                                     joint ? db->err_j16 : db->err_t16, qn, joint ? db->maxn_j16 : db->maxn_t16, cert,
+                                     st));
+        else
+            SNK_TRY(snk_rerank(db, sp, Qb, qn_, val, id, KP, k, d_dist + qb * out_stride, d_idx + qb * out_stride,
+                               out_stride, id_offset, qerr, joint ? db->err_j16 : db->err_t16, qn,
+                               joint ? db->maxn_j16 : db->maxn_t16, tau, cert, nullptr, st));
         int nfail = 0;
         SNK_CUDA(cudaMemcpyAsync(&nfail, cert + qn_, 4, cudaMemcpyDeviceToHost, st));
         SNK_CUDA(cudaStreamSynchronize(st));
