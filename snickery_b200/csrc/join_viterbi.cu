@@ -173,20 +173,38 @@ struct vit_meta {
     int64_t T;
 };
 
-// One CTA per utterance, thread c < K owns "next" candidate c.
+// cp.async helpers (LDGSTS): tiles are prefetched into a shared-memory ring ahead of the DP front
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+
+// One CTA per utterance, thread c < K owns "next" candidate c.  The K x K join tiles do not depend on
+// the DP state, so they stream through a 3-deep cp.async ring two steps ahead of the relaxation; the
+// chain over t only ever waits on shared memory.
+template <int VIT_STAGES>
 __global__ void viterbi_kernel(const vit_meta *__restrict__ meta, const int64_t *__restrict__ cand,
                                const double *__restrict__ tdist, const float *__restrict__ tiles, int K, int64_t N,
                                unsigned flags, short *__restrict__ bp, int64_t *__restrict__ paths,
                                int64_t *__restrict__ path_len, double *__restrict__ path_cost,
                                double *__restrict__ tcost, double *__restrict__ jcost) {
-    extern __shared__ float vsm[];
-    float *dcur = vsm;          // [K] cost of reaching state a (arcs 0..t-1 consumed)
-    float *dnext = vsm + K;     // [K]
-    float *Dt_s = vsm + 2 * K;  // [K] target cost row t as float32
+    extern __shared__ __align__(16) float vsm[];
+    const int KK = K * K;
+    const int KKp = (KK + 3) & ~3;
+    float *tile_s = vsm;                       // [VIT_STAGES][KKp]
+    float *dcur = vsm + VIT_STAGES * KKp;      // [K] cost of reaching state a (arcs 0..t-1 consumed)
+    float *dnext = dcur + K;                   // [K]
+    float *Dt_s = dnext + K;                   // [K] target cost row t as float32
     __shared__ float s_best;
     __shared__ int s_arg;
     const vit_meta mt = meta[blockIdx.x];
-    const int c = threadIdx.x;
+    const int c = threadIdx.x, nthr = blockDim.x;
     const int64_t f0 = mt.frame_off;
     const int64_t T = mt.T;
     const bool beam1 = flags & 1u;
@@ -198,22 +216,40 @@ __global__ void viterbi_kernel(const vit_meta *__restrict__ meta, const int64_t 
             if (tcost) tcost[blockIdx.x] = INFINITY;
             if (jcost) jcost[blockIdx.x] = INFINITY;
         }
-        for (int64_t t = c; t < T; t += blockDim.x) paths[f0 + t] = -1;
+        for (int64_t t = c; t < T; t += nthr) paths[f0 + t] = -1;
     };
     if (T < 2) { fail(); return; }   // empty J => empty composition (fst_functions_wrapped.py:172-217)
 
+    const bool vec = (KK & 3) == 0;   // tile base addresses are 16-byte aligned iff K*K*4 is a multiple of 16
+    auto prefetch = [&](int64_t t) {
+        if (t < T - 1) {
+            const float *src = tiles + (size_t)(mt.tile_off + t) * KK;
+            float *dst = tile_s + (size_t)(t % VIT_STAGES) * KKp;
+            if (vec) for (int i = c * 4; i < KK; i += nthr * 4) cp_async16(dst + i, src + i);
+            else for (int i = c; i < KK; i += nthr) cp_async4(dst + i, src + i);
+        }
+        cp_async_commit();            // always commit so group counting stays uniform
+    };
+    for (int s = 0; s < VIT_STAGES - 1; ++s) prefetch(s);
+
     if (c < K) dcur[c] = admissible(cand[f0 * K + c], N) ? 0.f : INFINITY;
+    float d_next_row = c < K ? (float)tdist[f0 * K + c] : 0.f;
     for (int64_t t = 0; t < T - 1; ++t) {
-        if (c < K) Dt_s[c] = (float)tdist[(f0 + t) * K + c];
-        __syncthreads();
+        prefetch(t + VIT_STAGES - 1);
         if (c < K) {
-            const float *tile = tiles + (size_t)(mt.tile_off + t) * K * K;
+            Dt_s[c] = d_next_row;
+            d_next_row = (float)tdist[(f0 + t + 1) * K + c];   // next step's target costs, a step early
+        }
+        cp_async_wait<VIT_STAGES - 1>();                        // tile t has landed (for this thread's copies)
+        __syncthreads();                                        // ... and for everyone's; Dt_s / dcur visible
+        if (c < K) {
+            const float *tile = tile_s + (size_t)(t % VIT_STAGES) * KKp;
             float best = INFINITY;
             int arg = -1;
-#pragma unroll 4
+#pragma unroll 5
             for (int a = 0; a < K; ++a) {
-                const float arc = Dt_s[a] + __ldg(tile + a * K + c);   // Times(target arc, join arc)
-                const float v = dcur[a] + arc;                          // Times(distance so far, arc)
+                const float arc = Dt_s[a] + tile[a * K + c];   // Times(target arc, join arc)
+                const float v = dcur[a] + arc;                  // Times(distance so far, arc)
                 if (v < best) { best = v; arg = a; }
             }
             dnext[c] = best;
@@ -241,8 +277,9 @@ __global__ void viterbi_kernel(const vit_meta *__restrict__ meta, const int64_t 
         }
         float *tmp = dcur; dcur = dnext; dnext = tmp;
     }
+    cp_async_wait<0>();
     // final arc: D[T-1, a] + 0 (exit arcs carry no weight, fst_functions_wrapped.py:206-208)
-    if (c < K) Dt_s[c] = (float)tdist[(f0 + T - 1) * K + c];
+    if (c < K) Dt_s[c] = d_next_row;
     __syncthreads();
     if (c < 32) {
         float bv = INFINITY;
@@ -375,9 +412,20 @@ int snk_join_viterbi_batch_dev(snk_db *db, const int64_t *d_cand, const double *
     const int threads = (int)snk_round_up(K, 32);
     {   // per (utt, t): K*K*4 tile read + K*8 target costs + K*2 backpointers
         snk_prof_scope prof(db, SNK_PROF_VITERBI, (double)ntiles * ((double)K * K * 4 + K * 8.0 + K * 2.0), st);
-        viterbi_kernel<<<B, threads, 3 * K * sizeof(float), st>>>(d_meta, d_cand, d_tdist, (const float *)db->ws_tiles.p,
-                                                                  K, db->N, flags, (short *)db->ws_bp.p, d_paths,
-                                                                  d_path_len, d_path_cost, d_tcost, d_jcost);
+        const size_t per_stage = (size_t)((K * K + 3) & ~3) * sizeof(float);
+        const int nst = 3 * per_stage + 3 * K * sizeof(float) <= 200 * 1024 ? 3 : 2;
+        const size_t vsmem = nst * per_stage + 3 * K * sizeof(float);
+        if (nst == 3) {
+            SNK_CUDA(cudaFuncSetAttribute(viterbi_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+            viterbi_kernel<3><<<B, threads, vsmem, st>>>(d_meta, d_cand, d_tdist, (const float *)db->ws_tiles.p, K, db->N,
+                                                         flags, (short *)db->ws_bp.p, d_paths, d_path_len, d_path_cost,
+                                                         d_tcost, d_jcost);
+        } else {
+            SNK_CUDA(cudaFuncSetAttribute(viterbi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+            viterbi_kernel<2><<<B, threads, vsmem, st>>>(d_meta, d_cand, d_tdist, (const float *)db->ws_tiles.p, K, db->N,
+                                                         flags, (short *)db->ws_bp.p, d_paths, d_path_len, d_path_cost,
+                                                         d_tcost, d_jcost);
+        }
     }
     SNK_CUDA(cudaGetLastError());
     db->counters[2] += 1;

@@ -73,6 +73,7 @@ class Synthesiser:
         else:
             self.set_target_weights(self.config["target_stream_weights"])
             self.set_join_weights(self.config["join_stream_weights"])
+        self._push_weights()   # the reference weights its arrays in the constructor (synth_simple.py:128-133)
         if greedy_epoch:
             self.get_tree_for_greedy_search()
         elif self.config.get("preselection_method", "quinphone") == "acoustic":
