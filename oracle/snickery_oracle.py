@@ -98,8 +98,11 @@ class OracleSynthesiser:
 
     # ---- W1 / W2
     def set_join_weights(self, weights):
-        """synth_simple.py:234-255."""
+        """synth_simple.py:234-255; synth_halfphone.py:682-707 doubles the vector for epoch voices written
+        by train_halfphone.py (two-frame join windows, :693-695)."""
         w = per_coeff_weights(weights, self.stream_list_join, self.datadims_join)
+        if self.config.get("halfphone_epoch_join_layout", False):
+            w = np.concatenate([w, w])
         jw = weight(self.join_contexts_unweighted, w)
         self.join_weight_vector = w
         self.unit_end_data = jw[1:, :]
@@ -117,9 +120,16 @@ class OracleSynthesiser:
 
     # ---- G1
     def combined_rep(self):
-        """synth_simple.py:190-224: [prev_join_rep || windowed target features]."""
-        self.prev_join_rep = self.unit_start_data
-        self.current_join_rep = self.unit_end_data
+        """synth_simple.py:190-224: [prev_join_rep || windowed target features].
+        With halfphone_epoch_join_layout the join contexts hold two frames per row and
+        prev / current are the two halves of unit_start_data (synth_halfphone.py:552-553)."""
+        if self.config.get("halfphone_epoch_join_layout", False):
+            n = self.unit_start_data.shape[1]
+            self.prev_join_rep = self.unit_start_data[:, :n // 2]
+            self.current_join_rep = self.unit_start_data[:, n // 2:]
+        else:
+            self.prev_join_rep = self.unit_start_data
+            self.current_join_rep = self.unit_end_data
         feats = self.train_unit_features
         m_ep = self.config.get("multiepoch", 1)
         if m_ep > 1:

@@ -84,6 +84,21 @@ class ShardedKnn:
         self.db.set_weights(np.asarray(weights, dtype=np.float64), np.ones(1))
         self.device = device
 
+    @classmethod
+    def from_epoch_db(cls, F, Jc, multiepoch, wt, wj, rank, world, device, group=None):
+        """Joint-space (greedy) search rows [prev_join || m-frame window] sharded by row block: rank r holds
+        joint rows [lo, hi) and therefore frames [lo, hi+m-1) and join contexts [lo, hi+m]."""
+        self = cls.__new__(cls)
+        self.rank, self.world, self.group, self.device = rank, world, group, device
+        n_joint = F.shape[0] - (multiepoch - 1)
+        self.lo, self.hi = shard_rows(n_joint, rank, world)
+        Fs = np.ascontiguousarray(F[self.lo:self.hi + multiepoch - 1], dtype=np.float32)
+        Js = np.ascontiguousarray(Jc[self.lo:self.hi + multiepoch], dtype=np.float32)
+        self.db = engine.UnitDatabase(Fs, Js, multiepoch=multiepoch, device=device)
+        self.db.set_weights(np.asarray(wt, dtype=np.float64), np.asarray(wj, dtype=np.float64))
+        self.space = engine.SPACE_JOINT
+        return self
+
     def query_local_dev(self, q_dev, k):
         """q_dev: torch float64 CUDA tensor [nq, D]; returns local top-k with GLOBAL row ids."""
         import torch
@@ -92,7 +107,7 @@ class ShardedKnn:
         i = torch.empty((nq, k), dtype=torch.int64, device=q_dev.device)
         lib = engine.load_library()
         stream = torch.cuda.current_stream(q_dev.device)
-        rc = lib.snk_knn_dev(self.db.handle, engine.SPACE_TARGET, C.c_void_p(q_dev.data_ptr()), nq, k,
+        rc = lib.snk_knn_dev(self.db.handle, getattr(self, "space", engine.SPACE_TARGET), C.c_void_p(q_dev.data_ptr()), nq, k,
                              C.c_void_p(d.data_ptr()), C.c_void_p(i.data_ptr()), self.lo, C.c_void_p(stream.cuda_stream))
         if rc:
             raise engine.EngineError(lib.snk_last_error().decode())

@@ -175,6 +175,27 @@ def test_greedy_ragged_batch_and_multiepoch1(golden_epoch, eng):
         assert_greedy_path_ok(o, u, p, d)
 
 
+@pytest.mark.parametrize("eng", ENGINES)
+@pytest.mark.parametrize("m", [1, 3])
+def test_greedy_halfphone_epoch_join_layout(golden_epoch, eng, m):
+    """Epoch voices written by train_halfphone.py store two-frame join windows; greedy search splits them
+    into prev / current halves (synth_halfphone.py:552-553,580-581,693-695)."""
+    F = golden_epoch["F"]
+    Jc1 = golden_epoch["Jc"]
+    Jc = np.ascontiguousarray(np.hstack([Jc1, np.vstack([Jc1[1:], Jc1[-1:]])]))     # [N+1, 302]: frame u-1 | frame u
+    cfg = dict(epoch_config(multiepoch=m), halfphone_epoch_join_layout=True)
+    o = O.OracleSynthesiser(cfg, F, Jc)
+    o.get_tree_for_greedy_search()
+    assert o.prev_join_rep.shape[1] == 151 and o.current_join_rep.shape[0] == F.shape[0] - (m - 1)
+    g = Synthesiser(cfg, F, Jc)
+    g.db.set_engine(eng)
+    utts = [O.weight(x, o.target_weight_vector) for x in syn.make_targets(F, 3, 30, seed=41)]
+    paths, dists = g.greedy_joint_search_batch(utts, return_dists=True)
+    for u, p, d in zip(utts, paths, dists):
+        assert len(p) == 30 // m
+        assert_greedy_path_ok(o, u, p, d)
+
+
 def test_greedy_too_short_utterance_raises(epoch_pair, golden_epoch):
     o, g = epoch_pair
     with pytest.raises(ValueError):
