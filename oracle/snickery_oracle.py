@@ -203,6 +203,84 @@ class OracleSynthesiser:
         distances, candidates = self.tree.query(unit_features, k=self.config["n_candidates"])
         return candidates, distances
 
+    # ---- W3
+    def get_selection_vector(self, stream_list, stream_dims, truncation_values):
+        """synth_simple.py:968-980."""
+        assert len(truncation_values) == len(stream_list)
+        sel, start = [], 0
+        for stream, trunc in zip(stream_list, truncation_values):
+            dim = stream_dims[stream]
+            if trunc == -1:
+                trunc = dim
+            assert trunc <= dim
+            sel.extend(range(start, start + trunc))
+            start += dim
+        return sel
+
+    def truncate_join_streams(self, truncation_values):
+        """synth_simple.py:982-985."""
+        sel = self.get_selection_vector(self.stream_list_join, self.datadims_join, truncation_values)
+        self.unit_end_data = self.unit_end_data[:, sel]
+        self.unit_start_data = self.unit_start_data[:, sel]
+
+    def truncate_target_streams(self, truncation_values):
+        """synth_simple.py:987-992."""
+        sel = self.get_selection_vector(self.stream_list_target, self.datadims_target, truncation_values)
+        self.train_unit_features = self.train_unit_features[:, sel]
+        self.target_truncation_vector = sel
+
+    # ---- K2
+    def build_phonetrees(self, train_unit_names):
+        """synth_halfphone.py:385-402."""
+        monophones = np.array([q.split("/")[2] for q in train_unit_names])
+        self.phonetrees, self.phonetrees_index_converters = {}, {}
+        n = self.train_unit_features.shape[0]
+        for phone in dict.fromkeys(monophones.tolist()):
+            sel = monophones == phone
+            self.phonetrees[phone] = scipy.spatial.cKDTree(self.train_unit_features[sel, :], leafsize=10,
+                                                           compact_nodes=False, balanced_tree=False)
+            self.phonetrees_index_converters[phone] = np.arange(n)[sel]
+
+    def preselect_units_monophone_then_acoustic(self, unit_features, unit_names):
+        """synth_halfphone.py:1369-1396 (phones with fewer than K units keep the -1 / 1e15 padding)."""
+        K = self.config["n_candidates"]
+        m = unit_features.shape[0]
+        candidates = np.ones((m, K), dtype=int) * -1
+        distances = np.ones((m, K)) * VERY_BIG_WEIGHT_VALUE
+        monophones = [q.split("/")[2] for q in unit_names]
+        for i, phone in enumerate(monophones):
+            conv = self.phonetrees_index_converters[phone]
+            kk = min(K, conv.size)
+            d, c = self.phonetrees[phone].query(unit_features[i, :], k=kk)
+            d, c = np.atleast_1d(d), np.atleast_1d(c)
+            candidates[i, :kk] = conv[c]
+            distances[i, :kk] = d
+        return candidates, distances
+
+    # ---- K3 (candidate half)
+    def preselect_units_quinphone(self, unit_features, unit_names, unit_index):
+        """synth_halfphone.py:1305-1354 with label_manip.py:16-32."""
+        K = self.config["n_candidates"]
+        candidates = []
+        for quinphone in unit_names:
+            q = quinphone.split("/")
+            mono, tri = q[2], "/".join(q[1:4])
+            di = "/".join(q[1:3]) if mono.endswith("_L") else "/".join(q[2:4])
+            current = []
+            for form in [quinphone, tri, di, mono]:
+                for unit in unit_index.get(form, []):
+                    current.append(unit)
+                    if len(current) == K:
+                        break
+                if len(current) == K:
+                    break
+            if len(current) == 0:
+                current = [1]
+            current += [-1] * (K - len(current))
+            candidates.append(current)
+        candidates = np.array(candidates)
+        return candidates, self.candidate_distances(candidates, unit_features)
+
     # ---- K3 (distance half)
     def candidate_distances(self, candidates, unit_features):
         """synth_halfphone.py:1346-1351 -- rows for -1 index the LAST unit (numpy

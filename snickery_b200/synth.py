@@ -24,6 +24,23 @@ from . import engine
 from .kdtree import GpuKDTree
 
 APPLY_JCW_ON_TOP = True  # reference script/synth_simple.py:44
+VERY_BIG_WEIGHT_VALUE = 1000000000000000.0  # const.py:3
+LABEL_DELIMITER = "/"  # const.py:5
+
+
+def break_quinphone(quinphone):
+    """label_manip.py:16-32: internal 'a/b/c_L/d/e' label -> (mono, diphone, triphone, quinphone)."""
+    q = quinphone.split(LABEL_DELIMITER)
+    assert len(q) == 5
+    mono = q[2]
+    tri = LABEL_DELIMITER.join(q[1:4])
+    if mono.endswith("_L"):
+        di = LABEL_DELIMITER.join(q[1:3])
+    elif mono.endswith("_R"):
+        di = LABEL_DELIMITER.join(q[2:4])
+    else:
+        raise ValueError("halfphone label %r lacks the _L/_R suffix" % mono)
+    return (mono, di, tri, quinphone)
 TARGET_REP_WIDTHS = {"onepoint": 1, "twopoint": 2, "threepoint": 3, "epoch": 1, "sample": 1}  # const.py:17
 
 
@@ -47,7 +64,8 @@ def segment_axis_cut(a, length):
 
 
 class Synthesiser:
-    def __init__(self, config, train_unit_features_unweighted, join_contexts_unweighted, device=0, verbose=False):
+    def __init__(self, config, train_unit_features_unweighted, join_contexts_unweighted, device=0, verbose=False,
+                 train_unit_names=None):
         self.config = read_config(config)
         self.verbose = verbose
         self.stream_list_target = self.config["stream_list_target"]
@@ -66,6 +84,10 @@ class Synthesiser:
         self.db = engine.UnitDatabase(F, Jc, multiepoch=self._multiepoch, layout=layout, device=device)
         self._wt = self._wj = None
         self._dirty = True
+        self._tmask = self._jmask = None          # truncate_*_streams column masks
+        self._F_raw = F
+        self.train_unit_names = train_unit_names
+        self.phonetrees = None
         jcw = self.config["join_cost_weight"]
         if APPLY_JCW_ON_TOP:   # synth_simple.py:128-133
             self.set_target_weights(np.array(self.config["target_stream_weights"]) * (1.0 - jcw))
@@ -73,7 +95,19 @@ class Synthesiser:
         else:
             self.set_target_weights(self.config["target_stream_weights"])
             self.set_join_weights(self.config["join_stream_weights"])
+        if "truncate_target_streams" in self.config:   # synth_simple.py:136-139
+            self.truncate_target_streams(self.config["truncate_target_streams"])
+        if "truncate_join_streams" in self.config:
+            self.truncate_join_streams(self.config["truncate_join_streams"])
         self._push_weights()   # the reference weights its arrays in the constructor (synth_simple.py:128-133)
+        if train_unit_names is not None and self.target_representation != "epoch":
+            # label index for quinphone preselection (synth_halfphone.py:281-292)
+            self.unit_index = {}
+            for i, quinphone in enumerate(train_unit_names):
+                for form in break_quinphone(quinphone):
+                    self.unit_index.setdefault(form, []).append(i)
+            if self.config.get("preselection_method") == "monophone_then_acoustic":
+                self._build_phonetrees()
         if greedy_epoch:
             self.get_tree_for_greedy_search()
         elif self.config.get("preselection_method", "quinphone") == "acoustic":
@@ -118,9 +152,58 @@ class Synthesiser:
     def _push_weights(self):
         if self._dirty:
             t = self.start_clock("re-weight resident database")
-            self.db.set_weights(self._wt, self._wj)
+            wt = self._wt if self._tmask is None else self._wt * self._tmask
+            wj = self._wj if self._jmask is None else self._wj * self._jmask
+            self.db.set_weights(wt, wj)
+            if self.phonetrees:
+                for tree in self.phonetrees.values():
+                    tree._db.set_weights(wt, np.ones(1))
             self._dirty = False
             self.stop_clock(t)
+
+    # ---- stream truncation (synth_simple.py:968-992).  Dropping columns on both sides of a distance is
+    # the same as giving them zero weight, so the resident matrices keep their shape.
+    def get_selection_vector(self, stream_list, stream_dims, truncation_values):
+        assert len(truncation_values) == len(stream_list), (truncation_values, stream_list)
+        selection_vector = []
+        start = 0
+        for stream, trunc in zip(stream_list, truncation_values):
+            stream_dim = stream_dims[stream]
+            if trunc == -1:
+                trunc = stream_dim
+            assert trunc <= stream_dim, "stream %s has only %s dims, cannot truncate to %s" % (stream, stream_dim, trunc)
+            selection_vector.extend(range(start, start + trunc))
+            start += stream_dim
+        return selection_vector
+
+    def truncate_join_streams(self, truncation_values):
+        sel = self.get_selection_vector(self.stream_list_join, self.datadims_join, truncation_values)
+        mask = np.zeros(len(self._wj))
+        width = sum(self.datadims_join[s] for s in self.stream_list_join)
+        for rep in range(len(self._wj) // width):
+            mask[np.array(sel) + rep * width] = 1.0
+        self._jmask = mask
+        self._dirty = True
+
+    def truncate_target_streams(self, truncation_values):
+        sel = self.get_selection_vector(self.stream_list_target, self.datadims_target, truncation_values)
+        assert TARGET_REP_WIDTHS[self.target_representation] == 1, "truncation is only used with epoch voices"
+        mask = np.zeros(len(self._wt))
+        mask[sel] = 1.0
+        self._tmask = mask
+        self.target_truncation_vector = sel
+        self._dirty = True
+
+    def _full_width(self, unit_features):
+        """synth_utt hands greedy_joint_search the TRUNCATED columns (synth_simple.py:392-397); put them back
+        at their places (the other columns carry zero weight)."""
+        u = np.asarray(unit_features, dtype=np.float64)
+        sel = getattr(self, "target_truncation_vector", None)
+        if sel is not None and u.shape[1] == len(sel) and len(sel) != self.db.Dt:
+            full = np.zeros((u.shape[0], self.db.Dt))
+            full[:, sel] = u
+            return full
+        return u
 
     def get_tree_for_greedy_search(self):
         """synth_simple.py:190-230.  Nothing is built: re-weighting refreshes the device operands."""
@@ -154,7 +237,7 @@ class Synthesiser:
 
     def greedy_joint_search_batch(self, unit_features_list, start_states=None, return_dists=False):
         self._push_weights()
-        feats = [np.asarray(u, dtype=np.float64) for u in unit_features_list]
+        feats = [self._full_width(u) for u in unit_features_list]
         return self.db.greedy_batch(feats, start_states, return_dists=return_dists)
 
     # ---- preselection (synth_halfphone.py:1359-1366, 1346-1351)
@@ -163,6 +246,60 @@ class Synthesiser:
         t = self.start_clock("Acoustic select units ")
         distances, candidates = self.tree.query(unit_features, k=self.config["n_candidates"])
         self.stop_clock(t)
+        return (candidates, distances)
+
+    def _build_phonetrees(self):
+        """One search structure per monophone (synth_halfphone.py:385-402)."""
+        monophones = np.array([q.split(LABEL_DELIMITER)[2] for q in self.train_unit_names])
+        self.phonetrees, self.phonetrees_index_converters = {}, {}
+        wt = self._wt if self._tmask is None else self._wt * self._tmask
+        for phone in dict.fromkeys(monophones.tolist()):
+            sel = monophones == phone
+            self.phonetrees[phone] = GpuKDTree.from_weighted(self._F_raw[sel, :], wt, device=self.db.device)
+            self.phonetrees_index_converters[phone] = np.arange(self.number_of_units)[sel]
+
+    def preselect_units_monophone_then_acoustic(self, unit_features, unit_names):
+        """synth_halfphone.py:1369-1396; -1 / VERY_BIG_WEIGHT_VALUE padding where a phone has too few units.
+        Targets of the same phone are searched in one batched call."""
+        self._push_weights()
+        K = self.config["n_candidates"]
+        unit_features = np.asarray(unit_features, dtype=np.float64)
+        m = unit_features.shape[0]
+        candidates = np.ones((m, K), dtype=int) * -1
+        distances = np.ones((m, K)) * VERY_BIG_WEIGHT_VALUE
+        monophones = np.array([q.split(LABEL_DELIMITER)[2] for q in unit_names])
+        assert len(monophones) == m, (len(monophones), m)
+        for phone in dict.fromkeys(monophones.tolist()):
+            assert phone in self.phonetrees, "unseen monophone %s" % phone
+            rows = np.flatnonzero(monophones == phone)
+            conv = self.phonetrees_index_converters[phone]
+            kk = min(K, conv.size)
+            d, i = self.phonetrees[phone].query(unit_features[rows], k=kk)
+            candidates[rows[:, None], np.arange(kk)[None, :]] = conv[np.asarray(i).reshape(len(rows), kk)]
+            distances[rows[:, None], np.arange(kk)[None, :]] = np.asarray(d).reshape(len(rows), kk)
+        return (candidates, distances)
+
+    def preselect_units_quinphone(self, unit_features, unit_names):
+        """synth_halfphone.py:1305-1354: label-index candidates (quin -> tri -> di -> mono, duplicates kept,
+        -1 padded, empty -> [1]); target distances on the GPU."""
+        K = self.config["n_candidates"]
+        candidates = []
+        for quinphone in unit_names:
+            current = []
+            mono, diphone, triphone, quin = break_quinphone(quinphone)
+            for form in [quin, triphone, diphone, mono]:
+                for unit in self.unit_index.get(form, []):
+                    current.append(unit)
+                    if len(current) == K:
+                        break
+                if len(current) == K:
+                    break
+            if len(current) == 0:
+                current = [1]
+            current += [-1] * (K - len(current))
+            candidates.append(current)
+        candidates = np.array(candidates)
+        distances = self.candidate_target_distances(candidates, unit_features)
         return (candidates, distances)
 
     def candidate_target_distances(self, candidates, unit_features):

@@ -399,3 +399,58 @@ def test_knn_tensor_core_halfphone_medium(k):
                        np.asarray(rd).reshape(210, -1), np.asarray(rc).reshape(210, -1))
     c = g.db.counters()
     assert c["recertified"] <= 0.05 * c["queries"], c
+
+
+# ------------------------------------------------------------------------------------ label-driven preselection, truncation
+def _halfphone_names(phones):
+    """Synthetic internal quinphone labels 'll/l/c_X/r/rr' (const.py:5, label_manip.py:16-32)."""
+    names = []
+    for i, p in enumerate(phones):
+        side = "_L" if i % 2 == 0 else "_R"
+        l, r = phones[max(i - 1, 0)], phones[min(i + 1, len(phones) - 1)]
+        names.append("p%d/p%d/p%d%s/p%d/p%d" % (phones[max(i - 2, 0)], l, p, side, r, phones[min(i + 2, len(phones) - 1)]))
+    return names
+
+
+def test_monophone_then_acoustic_and_quinphone_preselection(golden_halfphone):
+    gh = golden_halfphone
+    names = _halfphone_names(gh["phones"].tolist())
+    names[7] = "px/px/rare_L/px/px"                         # a phone with a single unit: padding path
+    cfg = halfphone_config(n_candidates=6, preselection="monophone_then_acoustic")
+    o = O.OracleSynthesiser(cfg, gh["F"], gh["Jc"])
+    o.build_phonetrees(names)
+    g = Synthesiser(cfg, gh["F"], gh["Jc"], train_unit_names=names)
+    tnames = [names[i] for i in (100, 101, 7, 300, 301, 302)]
+    uf = gh["targets"][:6]
+    rc, rd = o.preselect_units_monophone_then_acoustic(uf, tnames)
+    c, d = g.preselect_units_monophone_then_acoustic(uf, tnames)
+    assert np.array_equal(c, rc)
+    np.testing.assert_allclose(d, rd, rtol=1e-9)
+    assert c[2, 1] == -1 and d[2, 1] == 1e15                  # const.VERY_BIG_WEIGHT_VALUE padding
+    # quinphone label lookup + GPU target distances
+    cq, dq = g.preselect_units_quinphone(uf, tnames)
+    rq, rdq = o.preselect_units_quinphone(uf, tnames, g.unit_index)
+    assert np.array_equal(cq, rq)
+    np.testing.assert_allclose(dq, rdq, rtol=1e-12)
+    # and the lattice goes through Viterbi like any other
+    path = g.viterbi_search(cq, dq)
+    assert path == O.viterbi_search_numpy(o, rq, rdq)
+
+
+def test_truncated_streams(golden_epoch):
+    """truncate_target_streams / truncate_join_streams (synth_simple.py:136-139,968-992)."""
+    cfg = dict(epoch_config(multiepoch=2), truncate_target_streams=[20, -1], truncate_join_streams=[30, 10, 0, 1])
+    o = O.OracleSynthesiser(cfg, golden_epoch["F"], golden_epoch["Jc"])
+    o.truncate_target_streams(cfg["truncate_target_streams"])
+    o.truncate_join_streams(cfg["truncate_join_streams"])
+    o.get_tree_for_greedy_search()
+    assert o.joint_tree.m == 41 + 2 * 21
+    g = Synthesiser(cfg, golden_epoch["F"], golden_epoch["Jc"])
+    x = syn.make_targets(golden_epoch["F"], 1, 40, seed=77)[0]
+    full = O.weight(x, O.per_coeff_weights(np.array(cfg["target_stream_weights"]) * 0.8, cfg["stream_list_target"],
+                                           cfg["datadims_target"]))
+    uf = full[:, o.target_truncation_vector]                   # what synth_utt passes on (synth_simple.py:392-397)
+    ref, rd = o.greedy_joint_search(uf, return_dists=True)
+    paths, dists = g.greedy_joint_search_batch([uf], return_dists=True)
+    assert paths[0] == ref
+    np.testing.assert_allclose(dists[0], rd, rtol=COST_RTOL)
