@@ -29,7 +29,7 @@ namespace {
 constexpr int BM = 128;        // queries per tile (UMMA M)
 constexpr int BN = 128;        // database rows per tile (UMMA N)
 constexpr int BK = 64;         // fp16 elements per K-block = one 128-byte swizzle row
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr int MAXKB = 10;      // resident query K-blocks
 constexpr int MAXLOAD = 10;    // TMA loads per database tile
 constexpr int MAXSUB = 16;     // MMA K-blocks per database tile
@@ -160,8 +160,21 @@ __device__ __forceinline__ float min3(float a, float b, float c) {
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=128
 constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+// ---------------------------------------------------------------- static schedules
+// For the two shapes the reference ships (config/*.cfg: 151-dim join + 61-dim target frames with
+// multiepoch 6; 184-dim half-phone targets) the per-tile load / K-block sequence is a compile-time
+// constant, so the issue thread's descriptors are "uniform base + immediate" and it sustains one
+// UTCHMMA per tensor-pipe slot.  Every other shape runs the table-driven path (SCHED 0).
+//   NS   : K-blocks of the join part (one plain tile load each), KSL: UMMA_K steps of its last block
+//   TB   : 64-column blocks per target frame (one slab load each), KTL: UMMA_K steps of the last one
+//   M    : frames per row (window offsets served by one slab)
+//   R    : ring revolutions held in shared memory (slots = (NS + TB) * R)
+template <int SCHED> struct sched_traits { static constexpr int NS = 0, KSL = 0, TB = 0, KTL = 0, M = 0, R = 0; };
+template <> struct sched_traits<1> { static constexpr int NS = 3, KSL = 2, TB = 1, KTL = 4, M = 6, R = 1; };   // joint 151 | 6 x 61
+template <> struct sched_traits<2> { static constexpr int NS = 0, KSL = 0, TB = 3, KTL = 4, M = 1, R = 2; };   // target 184
+
 // ---------------------------------------------------------------- kernel
-template <bool kStore, int LSZ>
+template <bool kStore, int LSZ, int SCHED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapS,
               const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapGslab,
@@ -218,6 +231,33 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 tma_load_2d(sA + kb * TILE_BYTES, &mapQ, kb * BK, qt * BM, bar_a);
         }
         __syncwarp();
+        if constexpr (SCHED != 0) {
+            using S = sched_traits<SCHED>;
+            constexpr int NL = S::NS + S::TB;
+            for (int t = 0; t < ntiles; ++t) {
+                const int r0 = (int)(row_beg + (int64_t)t * BN);
+                const uint32_t ring = (uint32_t)(t % S::R) * NL;
+                const uint32_t ph = (uint32_t)(t / S::R) & 1u;
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                    const uint32_t st = ring + l;
+                    mbar_wait(bar_empty + 8 * st, ph ^ 1);
+                    if (elect_one()) {
+                        if (l < S::NS) {
+                            mbar_expect_tx(bar_full + 8 * st, TILE_BYTES);
+                            tma_load_2d(sB + st * SLOT_BYTES, &mapS, l * BK, r0, bar_full + 8 * st);
+                        } else if (S::M > 1) {
+                            mbar_expect_tx(bar_full + 8 * st, SLOT_BYTES);
+                            tma_load_2d(sB + st * SLOT_BYTES, &mapGslab, (l - S::NS) * BK, r0, bar_full + 8 * st);
+                        } else {
+                            mbar_expect_tx(bar_full + 8 * st, TILE_BYTES);
+                            tma_load_2d(sB + st * SLOT_BYTES, &mapG, (l - S::NS) * BK, r0, bar_full + 8 * st);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < ntiles; ++t) {
@@ -234,6 +274,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp walks the pipeline, one elected lane issues) ==========
         if (lane < p.nsub) {
@@ -244,6 +285,52 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         mbar_wait(bar_a, 0);
         tc_fence_after();
         constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        if constexpr (SCHED != 0) {
+            using S = sched_traits<SCHED>;
+            constexpr int NL = S::NS + S::TB;
+            if (elect_one()) {
+                const uint32_t a0 = sA >> 4, b0 = sB >> 4;       // start-address fields; every offset below is an immediate
+                for (int t = 0; t < ntiles; ++t) {
+                    const int acc = t & 1;
+                    const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
+                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+                    const uint32_t ring = (uint32_t)(t % S::R) * NL;
+                    const uint32_t ph = (uint32_t)(t / S::R) & 1u;
+#pragma unroll
+                    for (int l = 0; l < S::NS; ++l) {
+                        const uint32_t st = ring + l;
+                        mbar_wait(bar_full + 8 * st, ph);
+                        tc_fence_after();
+                        const uint32_t al = a0 + l * (TILE_BYTES >> 4), bl = b0 + st * (SLOT_BYTES >> 4);
+#pragma unroll
+                        for (int ks = 0; ks < (l == S::NS - 1 ? S::KSL : 4); ++ks)
+                            umma_f16(d_tmem, DESC_HI | (uint64_t)(al + 2 * ks), DESC_HI | (uint64_t)(bl + 2 * ks), IDESC,
+                                     (l | ks) != 0 ? 1u : 0u);
+                        umma_commit(bar_empty + 8 * st);
+                    }
+#pragma unroll
+                    for (int b = 0; b < S::TB; ++b) {
+                        const uint32_t st = ring + S::NS + b;
+                        mbar_wait(bar_full + 8 * st, ph);
+                        tc_fence_after();
+                        const uint32_t bl = b0 + st * (SLOT_BYTES >> 4);
+#pragma unroll
+                        for (int j = 0; j < S::M; ++j) {
+                            const uint32_t al = a0 + (S::NS + j * S::TB + b) * (TILE_BYTES >> 4);
+#pragma unroll
+                            for (int ks = 0; ks < (b == S::TB - 1 ? S::KTL : 4); ++ks)   // window offset j = +j rows = +8 in the field
+                                umma_f16(d_tmem, DESC_HI | (uint64_t)(al + 2 * ks), DESC_HI | (uint64_t)(bl + 8 * j + 2 * ks),
+                                         IDESC, (S::NS + b + j + ks) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(bar_empty + 8 * st);
+                    }
+                    umma_commit(bar_tfull + 8 * acc);
+                }
+            }
+            __syncwarp();
+        } else {
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < ntiles; ++t) {
@@ -276,6 +363,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 sb = sb_end;
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+        }
         }
     } else {
         // ===================== epilogue: one thread per query =====================
@@ -404,7 +492,7 @@ typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, vo
                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct tc_space_host {
-    int nkb = 0, nload = 0, nsub = 0, stages = 0;
+    int nkb = 0, nload = 0, nsub = 0, stages = 0, sched = 0;
     tc_load load[MAXLOAD];
     tc_sub sub[MAXSUB];
     short *d_qmap = nullptr;
@@ -487,11 +575,38 @@ int build_space(snk_db *db, int space, tc_space_host *h) {
     if (!h->ok) return 0;
     h->ldq = h->nkb * BK;
     const size_t fixed = 1024 + (size_t)h->nkb * TILE_BYTES + 16 * MAX_STAGES + 8 + 32 + 16 + 2 * BN * 4 + MAXSUB * 16 + 64;
-    h->stages = (int)std::min<size_t>(MAX_STAGES, (227 * 1024 - fixed) / SLOT_BYTES);
+    h->stages = (int)std::min<size_t>(4, (227 * 1024 - fixed) / SLOT_BYTES);
     if (h->stages < 2) { h->ok = false; return 0; }
+    // statically scheduled variants (sched_traits): shapes of the shipped configs
+    h->sched = 0;
+    if (!getenv("SNK_TC_NOSCHED")) {
+        if (space == SNK_SPACE_JOINT && slab && m == 6 && tblocks == 1 && Dt > 48 && db->Djq > 144 && db->Djq <= 160 &&
+            h->stages >= 4) {
+            h->sched = 1;
+            h->stages = 4;
+        } else if (space == SNK_SPACE_TARGET && tblocks == 3 && Dt > 176) {
+            h->sched = 2;
+            h->stages = 6;
+        }
+    }
     SNK_CUDA(cudaMalloc((void **)&h->d_qmap, qmap.size() * sizeof(short)));
     SNK_CUDA(cudaMemcpy(h->d_qmap, qmap.data(), qmap.size() * sizeof(short), cudaMemcpyHostToDevice));
     return 0;
+}
+
+typedef void (*tc_kernel_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const tc_params);
+
+template <bool kStore, int LSZ>
+tc_kernel_fn pick_sched(int sched) {
+    switch (sched) {
+    case 1: return knn_tc_kernel<kStore, LSZ, 1>;
+    case 2: return knn_tc_kernel<kStore, LSZ, 2>;
+    default: return knn_tc_kernel<kStore, LSZ, 0>;
+    }
+}
+tc_kernel_fn pick_kernel(bool store, int lsz, int sched) {
+    if (store) return pick_sched<true, 4>(sched);
+    return lsz == 4 ? pick_sched<false, 4>(sched) : pick_sched<false, 8>(sched);
 }
 
 }  // namespace
@@ -520,9 +635,10 @@ int snk_tc_prepare(snk_db *db) {
             if (s->smem[sp] > 227 * 1024) s->sp[sp].ok = false;
         }
     }
-    SNK_CUDA(cudaFuncSetAttribute(knn_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SNK_CUDA(cudaFuncSetAttribute(knn_tc_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SNK_CUDA(cudaFuncSetAttribute(knn_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int sched = 0; sched <= 2; ++sched)
+        for (int v = 0; v < 3; ++v)
+            SNK_CUDA(cudaFuncSetAttribute((const void *)pick_kernel(v == 2, v == 1 ? 8 : 4, sched),
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return 0;
 }
 
@@ -582,10 +698,7 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         p.oid = (int *)(p.oval + nlist);
         {
             snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)sp.rows * sp.D, st);
-            if (lsz == 4)
-                knn_tc_kernel<false, 4><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
-            else
-                knn_tc_kernel<false, 8><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
+            pick_kernel(false, lsz, h.sched)<<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
         }
         SNK_CUDA(cudaGetLastError());
         if (lists && snk_merge_rerank_fits(nlists, lsz)) {   // merge + tau happen inside the re-rank kernel
@@ -623,7 +736,7 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         p.chunk_rows = snk_cdiv(tiles, nchunks) * BN;
         {
             snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)rn * sp.D, st);
-            knn_tc_kernel<true, 4><<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
+            pick_kernel(true, 4, h.sched)<<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
         }
         SNK_CUDA(cudaGetLastError());
         db->counters[2] += 1;
