@@ -166,7 +166,11 @@ int snk_db_set_weights(snk_db *db, const double *wt, const double *wj) {
     SNK_CUDA(cudaMemcpyAsync(db->wt, wt, (size_t)db->Dt * 8, cudaMemcpyHostToDevice, db->stream));
     SNK_CUDA(cudaMemcpyAsync(db->wj, wj, (size_t)db->Dj * 8, cudaMemcpyHostToDevice, db->stream));
     SNK_TRY(snk_apply_weights(db, db->stream));
+    float stats[4] = {0, 0, 0, 0};   // err_t, err_j, maxn_t, maxn_j
+    SNK_CUDA(cudaMemcpyAsync(stats, db->err_t16, sizeof(stats), cudaMemcpyDeviceToHost, db->stream));
     SNK_CUDA(cudaStreamSynchronize(db->stream));
+    // fp16 range guard: weighted values (or their squared norms) beyond fp16 disable the tensor-core engine
+    db->tc_ok = stats[2] < 6.0e4f && stats[3] < 6.0e4f && stats[0] == stats[0] && stats[1] == stats[1];
     db->weights_set = true;
     return 0;
 }

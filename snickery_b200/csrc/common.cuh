@@ -67,6 +67,7 @@ struct snk_db {
     int Djq = 0, prev_col = 0, prev_row_off = 0, cur_col = 0, cur_row_off = 0;
     int engine = SNK_ENGINE_AUTO;
     bool weights_set = false;
+    bool tc_ok = false;          // fp16 operands of the current weighting are finite (no overflow)
     // resident arrays
     float *F_raw = nullptr;   // [N, Dt]
     float *Jc_raw = nullptr;  // [N+1, Dj]

@@ -49,6 +49,8 @@ struct tc_sub { int a_blk, b_off, base_off, ksteps; };
 struct tc_params {
     int nkb;                // resident query K-blocks
     int nload, nsub, stages;
+    int embed;              // squared norms ride in the operands: key = -2 * accumulator
+    int b_bytes;            // bytes of the database-tile ring
     tc_load load[MAXLOAD];  // map: 0 join-context tile (S16), 1 frame tile (G16), 2 frame slab (G16, BN+8 rows)
     tc_sub sub[MAXSUB];
     int64_t row_lo, row_hi; // rows scanned by this launch
@@ -168,10 +170,23 @@ constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >
 //   NS   : K-blocks of the join part (one plain tile load each), KSL: UMMA_K steps of its last block
 //   TB   : 64-column blocks per target frame (one slab load each), KTL: UMMA_K steps of the last one
 //   M    : frames per row (window offsets served by one slab)
-//   R    : ring revolutions held in shared memory (slots = (NS + TB) * R)
-template <int SCHED> struct sched_traits { static constexpr int NS = 0, KSL = 0, TB = 0, KTL = 0, M = 0, R = 0; };
-template <> struct sched_traits<1> { static constexpr int NS = 3, KSL = 2, TB = 1, KTL = 4, M = 6, R = 1; };   // joint 151 | 6 x 61
-template <> struct sched_traits<2> { static constexpr int NS = 0, KSL = 0, TB = 3, KTL = 4, M = 1, R = 2; };   // target 184
+//   GR   : slots per target-block load (2 = the next tile's frames land while this tile's are multiplied);
+//          join-part loads keep one slot each: they are short, so their slot is free long before reuse
+// Static schedules rely on the squared norms embedded in the operands (weights.cu), so their epilogue
+// needs no norm staging.
+template <int SCHED> struct sched_traits { static constexpr int NS = 0, KSL = 0, TB = 0, KTL = 0, M = 1, GR = 1; };
+template <> struct sched_traits<1> { static constexpr int NS = 3, KSL = 2, TB = 1, KTL = 4, M = 6, GR = 2; };   // joint 151 | 6 x 61
+template <> struct sched_traits<2> { static constexpr int NS = 0, KSL = 0, TB = 3, KTL = 4, M = 1, GR = 2; };   // target 184
+template <int SCHED> struct sched_layout {
+    using S = sched_traits<SCHED>;
+    static constexpr int GBYTES = S::M > 1 ? SLOT_BYTES : TILE_BYTES;
+    static constexpr int NSLOT = S::NS + S::TB * S::GR;
+    static constexpr int B_BYTES = S::NS * TILE_BYTES + S::TB * S::GR * GBYTES;
+    __host__ __device__ static constexpr int s_slot(int l) { return l; }
+    __host__ __device__ static constexpr uint32_t s_off(int l) { return (uint32_t)l * TILE_BYTES; }
+    __host__ __device__ static constexpr int g_slot(int b, int r) { return S::NS + b * S::GR + r; }
+    __host__ __device__ static constexpr uint32_t g_off(int b, int r) { return (uint32_t)S::NS * TILE_BYTES + (uint32_t)(b * S::GR + r) * GBYTES; }
+};
 
 // ---------------------------------------------------------------- kernel
 template <bool kStore, int LSZ, int SCHED>
@@ -179,21 +194,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapS,
               const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapGslab,
               const tc_params p) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles need 1024 B alignment
-    uint8_t *gbase = smem_raw + (sbase - smem_u32(smem_raw));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t sbase = smem_u32(smem_raw);                        // SWIZZLE_128B tiles need 1024 B alignment
+    if (sbase & 1023u) __trap();
+    uint8_t *gbase = smem_raw;
     const uint32_t sA = sbase;
     const uint32_t sB = sA + (uint32_t)p.nkb * TILE_BYTES;
     const int STAGES = p.stages;
-    const uint32_t sBar = sB + (uint32_t)STAGES * SLOT_BYTES;
+    const uint32_t sBar = sB + (uint32_t)p.b_bytes;
     // barriers: full[MAX_STAGES] empty[MAX_STAGES] a_full tmem_full[2] tmem_empty[2]
     const uint32_t bar_full = sBar, bar_empty = sBar + 8 * MAX_STAGES, bar_a = sBar + 16 * MAX_STAGES;
     const uint32_t bar_tfull = bar_a + 8, bar_tempty = bar_tfull + 16;
     const uint32_t s_tmem_ptr = bar_tempty + 16;
-    uint8_t *g_after = gbase + (size_t)p.nkb * TILE_BYTES + (size_t)STAGES * SLOT_BYTES + 16 * MAX_STAGES + 8 + 32;
+    uint8_t *g_after = gbase + (size_t)p.nkb * TILE_BYTES + (size_t)p.b_bytes + 16 * MAX_STAGES + 8 + 32;
     volatile uint32_t *tmem_ptr_g = reinterpret_cast<volatile uint32_t *>(g_after);
-    float *nrm_s = reinterpret_cast<float *>(g_after + 24);           // [2][BN], 16-byte aligned
+    float *nrm_s = reinterpret_cast<float *>(g_after + 24);           // [2][BN], 16-byte aligned (table-driven path only)
     uint4 *sub_s = reinterpret_cast<uint4 *>(g_after + 24 + 2 * BN * 4);   // [MAXSUB] {a start addr >> 4, b byte offset, ksteps, -}
+    (void)STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x / p.nchunks, chunk = blockIdx.x % p.nchunks;
@@ -233,26 +250,29 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         __syncwarp();
         if constexpr (SCHED != 0) {
             using S = sched_traits<SCHED>;
-            constexpr int NL = S::NS + S::TB;
+            using L = sched_layout<SCHED>;
             for (int t = 0; t < ntiles; ++t) {
                 const int r0 = (int)(row_beg + (int64_t)t * BN);
-                const uint32_t ring = (uint32_t)(t % S::R) * NL;
-                const uint32_t ph = (uint32_t)(t / S::R) & 1u;
+                const uint32_t ph_s = (uint32_t)t & 1u;
+                const int gr = t % S::GR;
+                const uint32_t ph_g = (uint32_t)(t / S::GR) & 1u;
 #pragma unroll
-                for (int l = 0; l < NL; ++l) {
-                    const uint32_t st = ring + l;
-                    mbar_wait(bar_empty + 8 * st, ph ^ 1);
+                for (int l = 0; l < S::NS; ++l) {
+                    const uint32_t bar = 8 * L::s_slot(l);
+                    mbar_wait(bar_empty + bar, ph_s ^ 1);
                     if (elect_one()) {
-                        if (l < S::NS) {
-                            mbar_expect_tx(bar_full + 8 * st, TILE_BYTES);
-                            tma_load_2d(sB + st * SLOT_BYTES, &mapS, l * BK, r0, bar_full + 8 * st);
-                        } else if (S::M > 1) {
-                            mbar_expect_tx(bar_full + 8 * st, SLOT_BYTES);
-                            tma_load_2d(sB + st * SLOT_BYTES, &mapGslab, (l - S::NS) * BK, r0, bar_full + 8 * st);
-                        } else {
-                            mbar_expect_tx(bar_full + 8 * st, TILE_BYTES);
-                            tma_load_2d(sB + st * SLOT_BYTES, &mapG, (l - S::NS) * BK, r0, bar_full + 8 * st);
-                        }
+                        mbar_expect_tx(bar_full + bar, TILE_BYTES);
+                        tma_load_2d(sB + L::s_off(l), &mapS, l * BK, r0, bar_full + bar);
+                    }
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int b = 0; b < S::TB; ++b) {
+                    const uint32_t bar = 8 * (uint32_t)L::g_slot(b, gr);
+                    mbar_wait(bar_empty + bar, ph_g ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_full + bar, L::GBYTES);
+                        tma_load_2d(sB + L::g_off(b, gr), S::M > 1 ? &mapGslab : &mapG, b * BK, r0, bar_full + bar);
                     }
                     __syncwarp();
                 }
@@ -277,17 +297,19 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp walks the pipeline, one elected lane issues) ==========
-        if (lane < p.nsub) {
-            const tc_sub su = p.sub[lane];
-            sub_s[lane] = make_uint4((sA + (uint32_t)su.a_blk * TILE_BYTES) >> 4, (uint32_t)su.b_off, (uint32_t)su.ksteps, 0u);
+        if constexpr (SCHED == 0) {   // descriptor table of the table-driven path (not allocated otherwise)
+            if (lane < p.nsub) {
+                const tc_sub su = p.sub[lane];
+                sub_s[lane] = make_uint4((sA + (uint32_t)su.a_blk * TILE_BYTES) >> 4, (uint32_t)su.b_off, (uint32_t)su.ksteps, 0u);
+            }
+            __syncwarp();
         }
-        __syncwarp();
         mbar_wait(bar_a, 0);
         tc_fence_after();
         constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
         if constexpr (SCHED != 0) {
             using S = sched_traits<SCHED>;
-            constexpr int NL = S::NS + S::TB;
+            using L = sched_layout<SCHED>;
             if (elect_one()) {
                 const uint32_t a0 = sA >> 4, b0 = sB >> 4;       // start-address fields; every offset below is an immediate
                 for (int t = 0; t < ntiles; ++t) {
@@ -296,26 +318,26 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
-                    const uint32_t ring = (uint32_t)(t % S::R) * NL;
-                    const uint32_t ph = (uint32_t)(t / S::R) & 1u;
+                    const uint32_t ph_s = (uint32_t)t & 1u;
+                    const int gr = t % S::GR;
+                    const uint32_t ph_g = (uint32_t)(t / S::GR) & 1u;
 #pragma unroll
                     for (int l = 0; l < S::NS; ++l) {
-                        const uint32_t st = ring + l;
-                        mbar_wait(bar_full + 8 * st, ph);
+                        mbar_wait(bar_full + 8 * L::s_slot(l), ph_s);
                         tc_fence_after();
-                        const uint32_t al = a0 + l * (TILE_BYTES >> 4), bl = b0 + st * (SLOT_BYTES >> 4);
+                        const uint32_t al = a0 + l * (TILE_BYTES >> 4), bl = b0 + (L::s_off(l) >> 4);
 #pragma unroll
                         for (int ks = 0; ks < (l == S::NS - 1 ? S::KSL : 4); ++ks)
                             umma_f16(d_tmem, DESC_HI | (uint64_t)(al + 2 * ks), DESC_HI | (uint64_t)(bl + 2 * ks), IDESC,
                                      (l | ks) != 0 ? 1u : 0u);
-                        umma_commit(bar_empty + 8 * st);
+                        umma_commit(bar_empty + 8 * L::s_slot(l));
                     }
 #pragma unroll
                     for (int b = 0; b < S::TB; ++b) {
-                        const uint32_t st = ring + S::NS + b;
-                        mbar_wait(bar_full + 8 * st, ph);
+                        const uint32_t bar = 8 * (uint32_t)L::g_slot(b, gr);
+                        mbar_wait(bar_full + bar, ph_g);
                         tc_fence_after();
-                        const uint32_t bl = b0 + st * (SLOT_BYTES >> 4);
+                        const uint32_t bl = b0 + (L::g_off(b, gr) >> 4);
 #pragma unroll
                         for (int j = 0; j < S::M; ++j) {
                             const uint32_t al = a0 + (S::NS + j * S::TB + b) * (TILE_BYTES >> 4);
@@ -324,7 +346,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                                 umma_f16(d_tmem, DESC_HI | (uint64_t)(al + 2 * ks), DESC_HI | (uint64_t)(bl + 8 * j + 2 * ks),
                                          IDESC, (S::NS + b + j + ks) != 0 ? 1u : 0u);
                         }
-                        umma_commit(bar_empty + 8 * st);
+                        umma_commit(bar_empty + bar);
                     }
                     umma_commit(bar_tfull + 8 * acc);
                 }
@@ -377,16 +399,20 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         int li[LSZ];
 #pragma unroll
         for (int i = 0; i < LSZ; ++i) { lv[i] = INFINITY; li[i] = -1; }
-        float nrm_next = (et < BN && ntiles > 0 && row_beg + et < row_end) ? __ldg(p.nrm + row_beg + et) : INFINITY;
+        const bool embed = SCHED != 0 || p.embed != 0;
+        float nrm_next = (!embed && et < BN && ntiles > 0 && row_beg + et < row_end) ? __ldg(p.nrm + row_beg + et) : INFINITY;
         for (int t = 0; t < ntiles; ++t) {
             const int acc = t & 1;
             const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
             const int64_t r0 = row_beg + (int64_t)t * BN;
-            if (et < BN) {
-                nrm_s[acc * BN + et] = nrm_next;
-                nrm_next = (t + 1 < ntiles && r0 + BN + et < row_end) ? __ldg(p.nrm + r0 + BN + et) : INFINITY;   // next tile's norm, a tile early
+            if (!embed) {
+                if (et < BN) {
+                    nrm_s[acc * BN + et] = nrm_next;
+                    nrm_next = (t + 1 < ntiles && r0 + BN + et < row_end) ? __ldg(p.nrm + r0 + BN + et) : INFINITY;   // next tile's norm, a tile early
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
+            const bool partial = r0 + BN > row_end;   // rows past the chunk end (zero-filled by TMA) must not compete
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * BN;
@@ -399,27 +425,32 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     tc_fence_before();
                     mbar_arrive(bar_tempty + 8 * acc);
                 }
+                // key = ||y~||^2 - 2 x~.y~ : with embedded norms the accumulator already holds x.y - ||y||^2 / 2
+                float key[32];
+                if (embed) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) key[j] = -2.f * v[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) key[j] = fmaf(-2.f, v[j], nrm_s[acc * BN + c0 + j]);
+                }
+                if (partial) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (r0 + c0 + j >= row_end) key[j] = INFINITY;
+                }
                 if (kStore) {
                     if (q < p.nq) {
                         float *dst = p.odist + q * p.ldo + (r0 - p.row_lo) + c0;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 o;
-                            o.x = fmaf(-2.f, v[j + 0], nrm_s[acc * BN + c0 + j + 0]);
-                            o.y = fmaf(-2.f, v[j + 1], nrm_s[acc * BN + c0 + j + 1]);
-                            o.z = fmaf(-2.f, v[j + 2], nrm_s[acc * BN + c0 + j + 2]);
-                            o.w = fmaf(-2.f, v[j + 3], nrm_s[acc * BN + c0 + j + 3]);
-                            *reinterpret_cast<float4 *>(dst + j) = o;
-                        }
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(dst + j) = make_float4(key[j], key[j + 1], key[j + 2], key[j + 3]);
                     }
                 } else {
                     // keys of this 32-column chunk, then a min tree: almost every chunk holds nothing that
                     // beats any lane's current list, and one vote dismisses it.  Otherwise votes narrow
                     // down to the 8-column group and the columns that matter (all votes of a level are
                     // independent instructions, so they pipeline) before any lane touches its list.
-                    float key[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) key[j] = fmaf(-2.f, v[j], nrm_s[acc * BN + c0 + j]);
                     float g[4];
 #pragma unroll
                     for (int gi = 0; gi < 4; ++gi) {
@@ -492,7 +523,9 @@ typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, vo
                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct tc_space_host {
-    int nkb = 0, nload = 0, nsub = 0, stages = 0, sched = 0;
+    int nkb = 0, nload = 0, nsub = 0, stages = 0, sched = 0, b_bytes = 0;
+    bool embed = false;
+    size_t smem = 0;
     tc_load load[MAXLOAD];
     tc_sub sub[MAXSUB];
     short *d_qmap = nullptr;
@@ -519,34 +552,43 @@ int make_map(encode_fn enc, CUtensorMap *map, const void *base, uint64_t cols, u
     return 0;
 }
 
+size_t aux_bytes(int sched) {   // barriers + tmem pointer (+ norm staging and descriptor table of the table-driven path)
+    return 16 * MAX_STAGES + 8 + 32 + 24 + (sched == 0 ? 2 * BN * 4 + MAXSUB * 16 : 0) + 16;
+}
+
 int build_space(snk_db *db, int space, tc_space_host *h) {
     const int Dt = db->Dt;
     const int tblocks = (Dt + BK - 1) / BK;       // K-blocks per target frame
     const int m = space == SNK_SPACE_JOINT ? db->m : 1;
     const bool slab = m > 1 && m <= SLAB_EXTRA + 1 && !getenv("SNK_TC_NOSLAB");
+    // squared norms embedded in three spare operand columns (weights.cu) when every row has them
+    const bool embedG = Dt + 3 <= db->ldG16, embedS = db->Djq + 3 <= db->ldS16;
+    h->embed = (space == SNK_SPACE_JOINT ? (embedG && embedS) : embedG) && !getenv("SNK_TC_NOEMBED");
     std::vector<short> qmap;
     h->nkb = h->nload = h->nsub = 0;
     bool overflow = false;
-    auto add_ablock = [&](int valid, int dim0) {      // next resident query K-block: operand columns -> query dims
-        for (int c = 0; c < BK; ++c) qmap.push_back(c < valid ? (short)(dim0 + c) : (short)-1);
+    // next resident query K-block: operand columns -> query dims; `valid` data columns, then (embedded
+    // norms) three columns the query fills with -0.5 (marker -2)
+    auto add_ablock = [&](int valid, int dim0, bool norm_cols) {
+        for (int c = 0; c < BK; ++c)
+            qmap.push_back(c < valid ? (short)(dim0 + c) : (norm_cols && c < valid + 3 ? (short)-2 : (short)-1));
         return h->nkb++;
     };
     auto add_load = [&](int map, int rowoff, int col, int bytes) {
         if (h->nload >= MAXLOAD) { overflow = true; return; }
         h->load[h->nload++] = tc_load{map, rowoff, col, bytes, h->nsub, 0};
     };
-    auto add_sub = [&](int a_blk, int b_off, int base_off, int valid) {
+    auto add_sub = [&](int a_blk, int b_off, int base_off, int cols) {
         if (h->nsub >= MAXSUB || h->nload == 0) { overflow = true; return; }
-        h->sub[h->nsub++] = tc_sub{a_blk, b_off, base_off, (valid + 15) / 16};
+        h->sub[h->nsub++] = tc_sub{a_blk, b_off, base_off, (cols + 15) / 16};
         h->load[h->nload - 1].nsub++;
     };
-    int nS = 0;
     if (space == SNK_SPACE_JOINT) {
         for (int c = 0; c < db->Djq; c += BK) {
             const int valid = std::min(BK, db->Djq - c);
+            const bool last = c + BK >= db->Djq;
             add_load(0, 0, c, TILE_BYTES);
-            add_sub(add_ablock(valid, c), 0, 0, valid);
-            ++nS;
+            add_sub(add_ablock(valid, c, h->embed && last), 0, 0, valid + (h->embed && last ? 3 : 0));
         }
     }
     const int dim0 = space == SNK_SPACE_JOINT ? db->Djq : 0;
@@ -554,41 +596,48 @@ int build_space(snk_db *db, int space, tc_space_host *h) {
     std::vector<int> ablk((size_t)m * tblocks);
     for (int j = 0; j < m; ++j)
         for (int b = 0; b < tblocks; ++b)
-            ablk[(size_t)j * tblocks + b] = add_ablock(std::min(BK, Dt - b * BK), dim0 + j * Dt + b * BK);
+            ablk[(size_t)j * tblocks + b] = add_ablock(std::min(BK, Dt - b * BK), dim0 + j * Dt + b * BK,
+                                                       h->embed && b == tblocks - 1);
     for (int b = 0; b < tblocks; ++b) {
-        const int valid = std::min(BK, Dt - b * BK);
+        const int cols = std::min(BK, Dt - b * BK) + (h->embed && b == tblocks - 1 ? 3 : 0);
         if (slab) {
-            add_load(2, 0, b * BK, SLOT_BYTES);
             // K-block j starts j rows (j * 128 B) into the slab.  The swizzle atoms themselves stay
             // 1024-byte aligned (TMA wrote them), so the descriptor's base offset stays 0.
-            const bool use_base = getenv("SNK_TC_SLAB_BASE") != nullptr;
-            for (int j = 0; j < m; ++j) add_sub(ablk[(size_t)j * tblocks + b], j * BK * 2, use_base ? (j & 7) : 0, valid);
+            add_load(2, 0, b * BK, SLOT_BYTES);
+            for (int j = 0; j < m; ++j) add_sub(ablk[(size_t)j * tblocks + b], j * BK * 2, 0, cols);
         } else {
             for (int j = 0; j < m; ++j) {
                 add_load(1, j, b * BK, TILE_BYTES);
-                add_sub(ablk[(size_t)j * tblocks + b], 0, 0, valid);
+                add_sub(ablk[(size_t)j * tblocks + b], 0, 0, cols);
             }
         }
     }
-    (void)nS;
     h->ok = !overflow && h->nkb >= 1 && h->nkb <= MAXKB;
     if (!h->ok) return 0;
     h->ldq = h->nkb * BK;
-    const size_t fixed = 1024 + (size_t)h->nkb * TILE_BYTES + 16 * MAX_STAGES + 8 + 32 + 16 + 2 * BN * 4 + MAXSUB * 16 + 64;
-    h->stages = (int)std::min<size_t>(4, (227 * 1024 - fixed) / SLOT_BYTES);
-    if (h->stages < 2) { h->ok = false; return 0; }
     // statically scheduled variants (sched_traits): shapes of the shipped configs
     h->sched = 0;
-    if (!getenv("SNK_TC_NOSCHED")) {
-        if (space == SNK_SPACE_JOINT && slab && m == 6 && tblocks == 1 && Dt > 48 && db->Djq > 144 && db->Djq <= 160 &&
-            h->stages >= 4) {
+    if (!getenv("SNK_TC_NOSCHED") && h->embed) {
+        if (space == SNK_SPACE_JOINT && slab && m == 6 && tblocks == 1 && Dt + 3 > 48 && db->Djq + 3 > 144 &&
+            db->Djq + 3 <= 160)
             h->sched = 1;
-            h->stages = 4;
-        } else if (space == SNK_SPACE_TARGET && tblocks == 3 && Dt > 176) {
+        else if (space == SNK_SPACE_TARGET && tblocks == 3 && Dt + 3 > 176)
             h->sched = 2;
-            h->stages = 6;
-        }
     }
+    const size_t budget = 227 * 1024;
+    if (h->sched == 1) {
+        h->b_bytes = sched_layout<1>::B_BYTES; h->stages = sched_layout<1>::NSLOT;
+    } else if (h->sched == 2) {
+        h->b_bytes = sched_layout<2>::B_BYTES; h->stages = sched_layout<2>::NSLOT;
+    }
+    if (h->sched != 0 && (size_t)h->nkb * TILE_BYTES + h->b_bytes + aux_bytes(h->sched) > budget) h->sched = 0;
+    if (h->sched == 0) {
+        const size_t fixed = (size_t)h->nkb * TILE_BYTES + aux_bytes(0);
+        if (fixed + 2 * SLOT_BYTES > budget) { h->ok = false; return 0; }
+        h->stages = (int)std::min<size_t>(4, (budget - fixed) / SLOT_BYTES);
+        h->b_bytes = h->stages * SLOT_BYTES;
+    }
+    h->smem = (size_t)h->nkb * TILE_BYTES + h->b_bytes + aux_bytes(h->sched);
     SNK_CUDA(cudaMalloc((void **)&h->d_qmap, qmap.size() * sizeof(short)));
     SNK_CUDA(cudaMemcpy(h->d_qmap, qmap.data(), qmap.size() * sizeof(short), cudaMemcpyHostToDevice));
     return 0;
@@ -629,11 +678,7 @@ int snk_tc_prepare(snk_db *db) {
                      BN + SLAB_EXTRA));
     for (int sp = 0; sp < 2; ++sp) {
         SNK_TRY(build_space(db, sp, &s->sp[sp]));
-        if (s->sp[sp].ok) {
-            s->smem[sp] = 1024 + (size_t)s->sp[sp].nkb * TILE_BYTES + (size_t)s->sp[sp].stages * SLOT_BYTES +
-                          16 * MAX_STAGES + 8 + 32 + 16 + 2 * BN * 4 + MAXSUB * 16 + 64;
-            if (s->smem[sp] > 227 * 1024) s->sp[sp].ok = false;
-        }
+        if (s->sp[sp].ok) s->smem[sp] = s->sp[sp].smem;
     }
     for (int sched = 0; sched <= 2; ++sched)
         for (int v = 0; v < 3; ++v)
@@ -656,7 +701,7 @@ bool snk_tc_supported(const snk_db *db, const snk_space &sp, int KP) {
     if (!s) return false;
     const int space = sp.dA > 0 ? SNK_SPACE_JOINT : SNK_SPACE_TARGET;
     (void)KP;
-    return s->sp[space].ok && sp.rows >= 1;
+    return db->tc_ok && s->sp[space].ok && sp.rows >= 1;
 }
 
 int snk_tc_query_ld(const snk_db *db, int space) { return ((const tc_state *)db->tc_state)->sp[space].ldq; }
@@ -676,6 +721,7 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
     tc_params p;
     memset(&p, 0, sizeof(p));
     p.nkb = h.nkb; p.nload = h.nload; p.nsub = h.nsub; p.stages = h.stages;
+    p.embed = h.embed ? 1 : 0; p.b_bytes = h.b_bytes;
     memcpy(p.load, h.load, sizeof(h.load));
     memcpy(p.sub, h.sub, sizeof(h.sub));
     p.nq = nq;

@@ -58,6 +58,7 @@ __global__ void cvt_q16_kernel(const double *__restrict__ Q, int D, int64_t nq, 
         for (int c = lane; c < ld16; c += 32) {
             __half h = __float2half_rn(0.f);
             const int d = qmap[c];
+            if (q < nq && d == -2) h = __float2half_rn(-0.5f);   // multiplies the norm pieces embedded in the row
             if (q < nq && d >= 0) {
                 const double x = Q[q * D + d];
                 h = __double2half(x);

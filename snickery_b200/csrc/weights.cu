@@ -22,11 +22,15 @@ __global__ void weight_f32_kernel(const float *__restrict__ raw, const double *_
 
 // fp16 operand rows: out16[r, c] = half(f64(raw[r + row_off, col0 + c]) * w[col0 + c]) for c < Dv, else 0.
 // Also per-row squared norm of the rounded values and squared rounding error.
+// If embed: columns Dv, Dv+1, Dv+2 receive the squared norm split into three fp16 pieces (hi + mid + lo
+// = the fp32 value to 33 bits).  A query that carries -0.5 in those columns makes the tensor-core
+// accumulator x.y - 0.5 ||y||^2, so the kernel's key ||y||^2 - 2 x.y is just -2 * accumulator and no
+// norm array has to be staged in the epilogue.
 // One warp per row.
 __global__ void weight_f16_kernel(const float *__restrict__ raw, const double *__restrict__ w, int64_t rows_out,
                                   int64_t rows_raw, int Draw, int row_off, int col0, int Dv,
                                   __half *__restrict__ out, int ld, float *__restrict__ nrm,
-                                  float *__restrict__ err2) {
+                                  float *__restrict__ err2, int embed) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -53,6 +57,18 @@ __global__ void weight_f16_kernel(const float *__restrict__ raw, const double *_
         if (lane == 0) {
             nrm[r] = n2;
             err2[r] = e2;
+        }
+        if (embed) {
+            __syncwarp();
+            if (lane == 0) {
+                const __half hi = __float2half_rn(n2);
+                const float r1 = n2 - __half2float(hi);
+                const __half mid = __float2half_rn(r1);
+                const float r2 = r1 - __half2float(mid);
+                out[r * ld + Dv] = hi;
+                out[r * ld + Dv + 1] = mid;
+                out[r * ld + Dv + 2] = __float2half_rn(r2);
+            }
         }
     }
 }
@@ -97,11 +113,12 @@ int snk_apply_weights(snk_db *db, cudaStream_t st) {
     SNK_TRY(snk_buf_reserve(&db->ws_misc, (size_t)(db->N + 1) * 4 * 4));
     float *nG = (float *)db->ws_misc.p, *eG = nG + (db->N + 1), *nS = eG + (db->N + 1), *eS = nS + (db->N + 1);
     weight_f16_kernel<<<blocks, 256, 0, st>>>(db->F_raw, db->wt, db->N, db->N, db->Dt, 0, 0, db->Dt, db->G16,
-                                              db->ldG16, nG, eG);
+                                              db->ldG16, nG, eG, db->Dt + 3 <= db->ldG16);
     SNK_CUDA(cudaGetLastError());
     // S16 row u holds prev_join_rep[u] (row u + prev_row_off, columns prev_col ..)
     weight_f16_kernel<<<blocks, 256, 0, st>>>(db->Jc_raw, db->wj, db->N + 1, db->N + 1, db->Dj, db->prev_row_off,
-                                              db->prev_col, db->Djq, db->S16, db->ldS16, nS, eS);
+                                              db->prev_col, db->Djq, db->S16, db->ldS16, nS, eS,
+                                              db->Djq + 3 <= db->ldS16);
     SNK_CUDA(cudaGetLastError());
     SNK_CUDA(cudaMemsetAsync(db->maxn_t16, 0, 4, st));
     SNK_CUDA(cudaMemsetAsync(db->maxn_j16, 0, 4, st));
