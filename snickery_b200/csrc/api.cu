@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <vector>
 #include <algorithm>
 
@@ -73,6 +74,7 @@ int snk_db_create(snk_db **out, int device_id, int64_t N, int Dt, int Dj, int mu
               prop.major, prop.minor);
     snk_db *db = new snk_db();
     db->device = device_id;
+    if (const char *e = getenv("SNK_DEBUG_CERT_FAIL")) db->debug_fail_mod = atoi(e);
     db->sm_count = prop.multiProcessorCount;
     db->N = N; db->Dt = Dt; db->Dj = Dj; db->m = multiepoch; db->layout = layout_flags;
     db->Np = N - (multiepoch - 1);
@@ -140,7 +142,7 @@ int snk_db_destroy(snk_db *db) {
     cudaFree(db->Fw32); cudaFree(db->Jw32); cudaFree(db->G16); cudaFree(db->S16);
     cudaFree(db->nrm_t16); cudaFree(db->nrm_j16); cudaFree(db->err_t16);
     snk_buf *bufs[] = {&db->ws_q, &db->ws_dist, &db->ws_list, &db->ws_misc, &db->ws_io, &db->ws_io2, &db->ws_tiles,
-                       &db->ws_bp, &db->ws_tc, &db->ws_h0, &db->ws_h1, &db->ws_h2, &db->ws_h3};
+                       &db->ws_bp, &db->ws_tc, &db->ws_h0, &db->ws_h1, &db->ws_h2, &db->ws_h3, &db->ws_flags};
     for (snk_buf *b : bufs) snk_buf_free(b);
     if (db->ev) cudaEventDestroy(db->ev);
     if (db->stream) cudaStreamDestroy(db->stream);
@@ -227,7 +229,7 @@ int snk_knn_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, doub
     SNK_CHECK(db, "db is NULL");
     SNK_CHECK(space == SNK_SPACE_TARGET || space == SNK_SPACE_JOINT, "unknown search space %d", space);
     SNK_CUDA(cudaSetDevice(db->device));
-    return snk_search_dev(db, space, dQ, nq, k, d_dist, d_idx, k, id_offset, (cudaStream_t)stream);
+    return snk_search_dev(db, space, dQ, nq, k, d_dist, d_idx, k, id_offset, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int snk_knn(snk_db *db, int space, const double *Q, int64_t nq, int k, double *dist, int64_t *idx) {
@@ -247,7 +249,7 @@ int snk_knn(snk_db *db, int space, const double *Q, int64_t nq, int k, double *d
         const int64_t n = std::min(slab, nq - q0);
         SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, Q + q0 * sp.D, (size_t)n * sp.D * 8, cudaMemcpyHostToDevice, db->stream));
         SNK_TRY(snk_search_dev(db, space, (const double *)db->ws_h0.p, n, k, (double *)db->ws_h1.p,
-                               (int64_t *)db->ws_h2.p, k, 0, db->stream));
+                               (int64_t *)db->ws_h2.p, k, 0, nullptr, nullptr, db->stream));
         SNK_CUDA(cudaMemcpyAsync(dist + q0 * k, db->ws_h1.p, (size_t)n * k * 8, cudaMemcpyDeviceToHost, db->stream));
         SNK_CUDA(cudaMemcpyAsync(idx + q0 * k, db->ws_h2.p, (size_t)n * k * 8, cudaMemcpyDeviceToHost, db->stream));
         SNK_CUDA(cudaStreamSynchronize(db->stream));

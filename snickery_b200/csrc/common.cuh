@@ -67,6 +67,7 @@ struct snk_db {
     int Djq = 0, prev_col = 0, prev_row_off = 0, cur_col = 0, cur_row_off = 0;
     int engine = SNK_ENGINE_AUTO;
     bool weights_set = false;
+    int debug_fail_mod = 0;      // SNK_DEBUG_CERT_FAIL=n: pretend every n-th query failed its certificate (tests)
     bool tc_ok = false;          // fp16 operands of the current weighting are finite (no overflow)
     // resident arrays
     float *F_raw = nullptr;   // [N, Dt]
@@ -89,7 +90,7 @@ struct snk_db {
     void *tc_state = nullptr;   // tensor maps etc. (knn_tc.cu)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev = nullptr;
-    snk_buf ws_q, ws_dist, ws_list, ws_misc, ws_io, ws_io2, ws_tiles, ws_bp, ws_tc, ws_h0, ws_h1, ws_h2, ws_h3;
+    snk_buf ws_q, ws_dist, ws_list, ws_misc, ws_io, ws_io2, ws_tiles, ws_bp, ws_tc, ws_h0, ws_h1, ws_h2, ws_h3, ws_flags;
     int64_t counters[4] = {0, 0, 0, 0};
     // optional kernel timing (snk_db_profile_*)
     bool prof_on = false;
@@ -148,16 +149,21 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
 int snk_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, const float *d_val,
                const int *d_id, int KP, int k, double *d_dist, int64_t *d_idx, int64_t out_stride,
                int64_t id_offset, const float *d_qerr, const float *d_dberr, const float *d_qn,
-               const float *d_maxn, const float *d_tau_extra, int *d_cert, const int *d_qsel,
-               cudaStream_t st);
+               const float *d_maxn, const float *d_tau_extra, int *d_cert, int *d_nfail, int sticky,
+               const int *d_qsel, cudaStream_t st);
 
 bool snk_merge_rerank_fits(int nlists, int lsz);
 int snk_merge_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, const float *d_lval,
                      const int *d_lid, int nlists, int lsz, int KP, int k, double *d_dist, int64_t *d_idx,
                      int64_t out_stride, int64_t id_offset, const float *d_qerr, const float *d_dberr,
-                     const float *d_qn, const float *d_maxn, int *d_cert, cudaStream_t st);
+                     const float *d_qn, const float *d_maxn, int *d_cert, int *d_nfail, int sticky,
+                     cudaStream_t st);
 
 // ---- search.cu : k-NN driver shared by snk_knn and the greedy loop
 // dQ float64 [nq, D] device; results device.
+// d_sticky (optional, [nq] preset to 1, followed by one int failure counter): deferred certificate mode --
+// uncertified queries only clear their flag / bump the counter, nothing is synchronised or re-searched;
+// the caller inspects the flags later (greedy batches do, once per batch).
 int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist,
-                   int64_t *d_idx, int64_t out_stride, int64_t id_offset, cudaStream_t st);
+                   int64_t *d_idx, int64_t out_stride, int64_t id_offset, int *d_sticky, int *d_sticky_count,
+                   cudaStream_t st);

@@ -79,8 +79,8 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
               int KP, int nlists, int lsz, int k, double *__restrict__ odist, int64_t *__restrict__ oidx,
               int64_t ostride, int64_t id_offset, int64_t nrows, const float *__restrict__ qerr,
               const float *__restrict__ dberr, const float *__restrict__ qn, const float *__restrict__ maxn,
-              const float *__restrict__ tau_extra, int *__restrict__ cert, int *__restrict__ nfail,
-              const int *__restrict__ qsel) {
+              const float *__restrict__ tau_extra, int *__restrict__ cert, int *__restrict__ nfail, int sticky,
+              const int *__restrict__ qsel, int debug_fail_mod) {
     extern __shared__ double sm[];
     double *q_s = sm;                       // [D]
     double *wA_s = q_s + sp.D;              // [dA]
@@ -183,7 +183,11 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
                     const double dk = ok ? sqrt(v) : INFINITY;
                     good = (dk + delta <= tau) ? 1 : 0;
                 }
-                cert[q] = good;
+                if (debug_fail_mod > 0 && q % debug_fail_mod == 0) good = 0;   // test hook: exercise the re-search paths
+                // sticky: the flag array is preset to 1 by the caller and only ever cleared (a greedy batch
+                // inspects it once, after the last step, instead of synchronising every step)
+                if (!sticky) cert[q] = good;
+                else if (!good) cert[q] = 0;
                 if (!good) atomicAdd(nfail, 1);
             }
         }
@@ -207,16 +211,16 @@ size_t rr_smem(const rr_space &rs, int KP, int nmerge) {
 int snk_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, const float *d_val,
                const int *d_id, int KP, int k, double *d_dist, int64_t *d_idx, int64_t out_stride,
                int64_t id_offset, const float *d_qerr, const float *d_dberr, const float *d_qn,
-               const float *d_maxn, const float *d_tau_extra, int *d_cert, const int *d_qsel,
-               cudaStream_t st) {
+               const float *d_maxn, const float *d_tau_extra, int *d_cert, int *d_nfail, int sticky,
+               const int *d_qsel, cudaStream_t st) {
     if (nq <= 0) return 0;
     SNK_CHECK(k <= KP, "rerank: k (%d) exceeds shortlist (%d)", k, KP);
     const rr_space rs = make_rr(db, sp);
     const size_t smem = rr_smem(rs, KP, 0);
     rerank_kernel<false><<<(unsigned)nq, RR_THREADS, smem, st>>>(rs, dQ, d_val, d_id, KP, 0, 0, k, d_dist, d_idx,
                                                                    out_stride, id_offset, sp.rows, d_qerr, d_dberr,
-                                                                   d_qn, d_maxn, d_tau_extra, d_cert,
-                                                                   d_cert ? d_cert + nq : nullptr, d_qsel);
+                                                                   d_qn, d_maxn, d_tau_extra, d_cert, d_nfail, sticky,
+                                                                   d_qsel, d_cert ? db->debug_fail_mod : 0);
     SNK_CUDA(cudaGetLastError());
     db->counters[2] += 1;
     return 0;
@@ -227,7 +231,8 @@ bool snk_merge_rerank_fits(int nlists, int lsz) { return nlists * lsz <= RR_MAX_
 int snk_merge_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, const float *d_lval,
                      const int *d_lid, int nlists, int lsz, int KP, int k, double *d_dist, int64_t *d_idx,
                      int64_t out_stride, int64_t id_offset, const float *d_qerr, const float *d_dberr,
-                     const float *d_qn, const float *d_maxn, int *d_cert, cudaStream_t st) {
+                     const float *d_qn, const float *d_maxn, int *d_cert, int *d_nfail, int sticky,
+                     cudaStream_t st) {
     if (nq <= 0) return 0;
     SNK_CHECK(k <= KP, "rerank: k (%d) exceeds shortlist (%d)", k, KP);
     SNK_CHECK(snk_merge_rerank_fits(nlists, lsz), "merge_rerank: %d list entries exceed the in-block merge", nlists * lsz);
@@ -235,8 +240,8 @@ int snk_merge_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t 
     const size_t smem = rr_smem(rs, KP, nlists * lsz);
     rerank_kernel<true><<<(unsigned)nq, RR_THREADS, smem, st>>>(rs, dQ, d_lval, d_lid, KP, nlists, lsz, k, d_dist,
                                                                   d_idx, out_stride, id_offset, sp.rows, d_qerr,
-                                                                  d_dberr, d_qn, d_maxn, nullptr, d_cert,
-                                                                  d_cert ? d_cert + nq : nullptr, nullptr);
+                                                                  d_dberr, d_qn, d_maxn, nullptr, d_cert, d_nfail, sticky,
+                                                                  nullptr, d_cert ? db->debug_fail_mod : 0);
     SNK_CUDA(cudaGetLastError());
     db->counters[2] += 1;
     return 0;

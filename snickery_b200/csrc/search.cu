@@ -111,14 +111,15 @@ int search_simt(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, c
     db->counters[2] += 1;
     SNK_TRY(snk_shortlist_simt(db, sp, q32, sp.D, nq, KP, val, id, st));
     SNK_TRY(snk_rerank(db, sp, dQ, nq, val, id, KP, k, d_dist, d_idx, out_stride, id_offset, nullptr, nullptr,
-                       nullptr, nullptr, nullptr, nullptr, d_qsel, st));
+                       nullptr, nullptr, nullptr, nullptr, nullptr, 0, d_qsel, st));
     return 0;
 }
 
 }  // namespace
 
 int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist,
-                   int64_t *d_idx, int64_t out_stride, int64_t id_offset, cudaStream_t st) {
+                   int64_t *d_idx, int64_t out_stride, int64_t id_offset, int *d_sticky, int *d_sticky_count,
+                   cudaStream_t st) {
     SNK_CHECK(db->weights_set, "snk_db_set_weights has not been called");
     SNK_CHECK(k >= 1, "k must be >= 1");
     if (nq <= 0) return 0;
@@ -158,17 +159,21 @@ int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, d
         db->counters[2] += 1;
         snk_tc_lists lists;
         SNK_TRY(snk_shortlist_tc(db, space, q16, ld16, qn_, k, KP, val, id, tau, &lists, st));
-        SNK_CUDA(cudaMemsetAsync(cert + qn_, 0, 4, st));
         const bool joint = space == SNK_SPACE_JOINT;
+        const int sticky = d_sticky != nullptr;
+        int *cert_arr = sticky ? d_sticky + qb : cert;
+        int *cert_cnt = sticky ? d_sticky_count : cert + qn_;
+        if (!sticky) SNK_CUDA(cudaMemsetAsync(cert + qn_, 0, 4, st));
         if (lists.valid)
             SNK_TRY(snk_merge_rerank(db, sp, Qb, qn_, lists.val, lists.id, lists.nlists, lists.lsz, KP, k,
                                      d_dist + qb * out_stride, d_idx + qb * out_stride, out_stride, id_offset, qerr,
-                                     joint ? db->err_j16 : db->err_t16, qn, joint ? db->maxn_j16 : db->maxn_t16, cert,
-                                     st));
+                                     joint ? db->err_j16 : db->err_t16, qn, joint ? db->maxn_j16 : db->maxn_t16,
+                                     cert_arr, cert_cnt, sticky, st));
         else
             SNK_TRY(snk_rerank(db, sp, Qb, qn_, val, id, KP, k, d_dist + qb * out_stride, d_idx + qb * out_stride,
                                out_stride, id_offset, qerr, joint ? db->err_j16 : db->err_t16, qn,
-                               joint ? db->maxn_j16 : db->maxn_t16, tau, cert, nullptr, st));
+                               joint ? db->maxn_j16 : db->maxn_t16, tau, cert_arr, cert_cnt, sticky, nullptr, st));
+        if (sticky) continue;   // deferred: the caller inspects the flags
         int nfail = 0;
         SNK_CUDA(cudaMemcpyAsync(&nfail, cert + qn_, 4, cudaMemcpyDeviceToHost, st));
         SNK_CUDA(cudaStreamSynchronize(st));
@@ -235,6 +240,53 @@ __global__ void greedy_assemble_kernel(const greedy_meta *__restrict__ meta, int
 
 }  // namespace
 
+namespace {
+
+// One pass of the greedy chain over the utterances in `meta` (sorted longest first).  With deferred
+// certificates no step synchronises: flags [n] are preset to 1 and cleared by any step whose
+// tensor-core answer could not be certified.
+int greedy_run(snk_db *db, const std::vector<greedy_meta> &meta, const double *d_targets, int64_t *d_paths,
+               double *d_step_dist, int *d_flags, int *d_count, cudaStream_t st) {
+    const int B = (int)meta.size();
+    const int m = db->m;
+    const snk_space sp = snk_make_space(db, SNK_SPACE_JOINT);
+    int64_t maxsteps = 0;
+    for (const greedy_meta &g : meta) maxsteps = std::max(maxsteps, g.nsteps);
+    // ws_io: meta | Q [B, D] | ix [B] | dist [B]
+    const size_t meta_bytes = snk_round_up(sizeof(greedy_meta) * B, 256);
+    const size_t q_bytes = snk_round_up((size_t)B * sp.D * 8, 256);
+    SNK_TRY(snk_buf_reserve(&db->ws_io, meta_bytes + q_bytes + (size_t)B * 16 + 512));
+    char *base = (char *)db->ws_io.p;
+    greedy_meta *d_meta = (greedy_meta *)base;
+    double *Q = (double *)(base + meta_bytes);
+    int64_t *ix = (int64_t *)(base + meta_bytes + q_bytes);
+    double *dist = (double *)(base + meta_bytes + q_bytes + snk_round_up((size_t)B * 8, 256));
+    SNK_CUDA(cudaMemcpyAsync(d_meta, meta.data(), sizeof(greedy_meta) * B, cudaMemcpyHostToDevice, st));
+    SNK_CUDA(cudaStreamSynchronize(st));   // meta may be a stack-lifetime host vector
+    int nact_prev = 0;
+    for (int64_t t = 0; t <= maxsteps; ++t) {
+        int nact = 0;
+        while (nact < B && meta[nact].nsteps > t) ++nact;
+        const int grid = std::max(nact, nact_prev);
+        if (grid == 0) break;
+        greedy_assemble_kernel<<<grid, 128, 0, st>>>(d_meta, nact_prev, nact, t, d_targets, db->Dt, m, db->Jc_raw,
+                                                     db->wj, db->Dj, db->Djq, db->prev_row_off, db->prev_col,
+                                                     db->cur_row_off, db->cur_col, ix, dist, d_paths, d_step_dist, Q);
+        SNK_CUDA(cudaGetLastError());
+        db->counters[2] += 1;
+        if (nact > 0)
+            SNK_TRY(snk_search_dev(db, SNK_SPACE_JOINT, Q, nact, 1, dist, ix, 1, 0, d_flags, d_count, st));
+        nact_prev = nact;
+    }
+    return 0;
+}
+
+__global__ void fill_int_kernel(int *p, int64_t n, int v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace
+
 int snk_greedy_batch_dev(snk_db *db, const double *d_targets, const int64_t *lens, int B,
                          const int64_t *start_state, int64_t *d_paths, double *d_step_dist, void *stream) {
     SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
@@ -244,7 +296,7 @@ int snk_greedy_batch_dev(snk_db *db, const double *d_targets, const int64_t *len
     const int m = db->m;
     // utterance order: longest first so the active set of every step is a prefix
     std::vector<greedy_meta> meta(B);
-    int64_t toff = 0, poff = 0, maxsteps = 0;
+    int64_t toff = 0, poff = 0;
     for (int b = 0; b < B; ++b) {
         SNK_CHECK(lens[b] >= m, "utterance %d has %lld frames, fewer than multiepoch=%d "
                   "(the reference's segment_axis raises ValueError here)", b, (long long)lens[b], m);
@@ -258,35 +310,33 @@ int snk_greedy_batch_dev(snk_db *db, const double *d_targets, const int64_t *len
         }
         toff += lens[b];
         poff += meta[b].nsteps;
-        maxsteps = std::max(maxsteps, meta[b].nsteps);
     }
     std::stable_sort(meta.begin(), meta.end(),
                      [](const greedy_meta &a, const greedy_meta &b) { return a.nsteps > b.nsteps; });
-    const snk_space sp = snk_make_space(db, SNK_SPACE_JOINT);
-    // ws_io: meta | Q [B, D] | ix [B] | dist [B]
-    const size_t meta_bytes = snk_round_up(sizeof(greedy_meta) * B, 256);
-    const size_t q_bytes = snk_round_up((size_t)B * sp.D * 8, 256);
-    SNK_TRY(snk_buf_reserve(&db->ws_io, meta_bytes + q_bytes + (size_t)B * 16 + 512));
-    char *base = (char *)db->ws_io.p;
-    greedy_meta *d_meta = (greedy_meta *)base;
-    double *Q = (double *)(base + meta_bytes);
-    int64_t *ix = (int64_t *)(base + meta_bytes + q_bytes);
-    double *dist = (double *)(base + meta_bytes + q_bytes + snk_round_up((size_t)B * 8, 256));
-    SNK_CUDA(cudaMemcpyAsync(d_meta, meta.data(), sizeof(greedy_meta) * B, cudaMemcpyHostToDevice, st));
-    SNK_CUDA(cudaStreamSynchronize(st));   // meta is a stack-lifetime host vector
-    int nact_prev = 0;
-    for (int64_t t = 0; t <= maxsteps; ++t) {
-        int nact = 0;
-        while (nact < B && meta[nact].nsteps > t) ++nact;
-        const int grid = std::max(nact, nact_prev);
-        if (grid == 0) break;
-        greedy_assemble_kernel<<<grid, 128, 0, st>>>(d_meta, nact_prev, nact, t, d_targets, db->Dt, m, db->Jc_raw,
-                                                     db->wj, db->Dj, db->Djq, db->prev_row_off, db->prev_col,
-                                                     db->cur_row_off, db->cur_col, ix, dist, d_paths, d_step_dist, Q);
-        SNK_CUDA(cudaGetLastError());
-        db->counters[2] += 1;
-        if (nact > 0) SNK_TRY(snk_search_dev(db, SNK_SPACE_JOINT, Q, nact, 1, dist, ix, 1, 0, st));
-        nact_prev = nact;
+    // deferred certificates: flags [B] preset to 1 + a failure counter, inspected once after the last step
+    SNK_TRY(snk_buf_reserve(&db->ws_flags, (size_t)(B + 1) * 4));
+    int *flags = (int *)db->ws_flags.p, *count = flags + B;
+    fill_int_kernel<<<64, 256, 0, st>>>(flags, B, 1);
+    SNK_CUDA(cudaGetLastError());
+    SNK_CUDA(cudaMemsetAsync(count, 0, 4, st));
+    SNK_TRY(greedy_run(db, meta, d_targets, d_paths, d_step_dist, flags, count, st));
+    int nfail = 0;
+    SNK_CUDA(cudaMemcpyAsync(&nfail, count, 4, cudaMemcpyDeviceToHost, st));
+    SNK_CUDA(cudaStreamSynchronize(st));
+    if (nfail > 0) {
+        // some step of some utterance was not certified: redo those utterances with the exact-arithmetic
+        // engine (their later steps depend on the doubtful choice, so the whole chain is repeated)
+        std::vector<int> hflags(B);
+        SNK_CUDA(cudaMemcpy(hflags.data(), flags, (size_t)B * 4, cudaMemcpyDeviceToHost));
+        std::vector<greedy_meta> redo;
+        for (int b = 0; b < B; ++b)
+            if (!hflags[b]) redo.push_back(meta[b]);
+        db->counters[1] += (int64_t)redo.size();
+        const int saved = db->engine;
+        db->engine = SNK_ENGINE_SIMT;
+        const int rc = greedy_run(db, redo, d_targets, d_paths, d_step_dist, nullptr, nullptr, st);
+        db->engine = saved;
+        SNK_TRY(rc);
     }
     return 0;
 }

@@ -454,3 +454,27 @@ def test_truncated_streams(golden_epoch):
     paths, dists = g.greedy_joint_search_batch([uf], return_dists=True)
     assert paths[0] == ref
     np.testing.assert_allclose(dists[0], rd, rtol=COST_RTOL)
+
+
+def test_certificate_failure_paths_stay_exact(golden_epoch, golden_halfphone, monkeypatch):
+    """Pretend every 3rd query failed its exactness certificate: the SIMT re-search (k-NN) and the
+    end-of-batch repair pass (greedy, deferred certificates) must still return the oracle's answer."""
+    monkeypatch.setenv("SNK_DEBUG_CERT_FAIL", "3")
+    cfg = epoch_config()
+    o = O.OracleSynthesiser(cfg, golden_epoch["F"], golden_epoch["Jc"])
+    o.get_tree_for_greedy_search()
+    g = Synthesiser(cfg, golden_epoch["F"], golden_epoch["Jc"])
+    g.db.set_engine(engine.ENGINE_TC)
+    utts = [golden_epoch["targets_%d" % i] for i in range(3)] + [golden_epoch["targets_0"][:37]]
+    paths, dists = g.greedy_joint_search_batch(utts, return_dists=True)
+    for u, p, d in zip(utts, paths, dists):
+        assert_greedy_path_ok(o, u, p, d)
+    assert g.db.counters()["recertified"] >= 1
+    cfg3 = halfphone_config(n_candidates=12)
+    o3 = O.OracleSynthesiser(cfg3, golden_halfphone["F"], golden_halfphone["Jc"])
+    o3.build_acoustic_tree()
+    g3 = Synthesiser(cfg3, golden_halfphone["F"], golden_halfphone["Jc"])
+    g3.db.set_engine(engine.ENGINE_TC)
+    cand, dist = g3.preselect_units_acoustic(golden_halfphone["targets"])
+    assert_knn_matches(dist, cand, golden_halfphone["knn_dist"], golden_halfphone["knn_idx"])
+    assert g3.db.counters()["recertified"] >= 10
