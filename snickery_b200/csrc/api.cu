@@ -112,6 +112,7 @@ int snk_db_create(snk_db **out, int device_id, int64_t N, int Dt, int Dj, int mu
     db->maxn_j16 = db->err_t16 + 3;
 #undef ALLOC
     if (cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&db->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&db->ev) != cudaSuccess) {
         snk_set_error("stream/event creation failed");
         snk_db_destroy(db);
@@ -145,6 +146,8 @@ int snk_db_destroy(snk_db *db) {
                        &db->ws_bp, &db->ws_tc, &db->ws_h0, &db->ws_h1, &db->ws_h2, &db->ws_h3, &db->ws_flags};
     for (snk_buf *b : bufs) snk_buf_free(b);
     if (db->ev) cudaEventDestroy(db->ev);
+    for (cudaEvent_t e : db->upload_events) cudaEventDestroy(e);
+    if (db->copy_stream) cudaStreamDestroy(db->copy_stream);
     if (db->stream) cudaStreamDestroy(db->stream);
     cudaGetLastError();
     delete db;
@@ -273,10 +276,44 @@ int snk_greedy_batch(snk_db *db, const double *targets, const int64_t *lens, int
     SNK_TRY(snk_buf_reserve(&db->ws_h0, (size_t)std::max<int64_t>(frames, 1) * db->Dt * 8));
     SNK_TRY(snk_buf_reserve(&db->ws_h1, (size_t)std::max<int64_t>(steps, 1) * 8));
     SNK_TRY(snk_buf_reserve(&db->ws_h2, (size_t)std::max<int64_t>(steps, 1) * 8));
-    if (frames)
+    // Upload.  Equal-length utterances (the common batch) go up in time slices on a second stream: step t
+    // only needs frames [t*m, (t+1)*m) of every utterance, so the search starts after the first slice and
+    // the remaining host->device traffic hides behind it.  Ragged batches use one plain copy.
+    bool equal = B > 1;
+    for (int b = 1; b < B && equal; ++b) equal = lens[b] == lens[0];
+    const int64_t T = lens[0], nsteps = T / db->m;
+    const int NSLICE = 8;
+    db->step_waits.clear();
+    if (equal && nsteps >= 4 * NSLICE && frames * db->Dt * 8 >= ((int64_t)8 << 20)) {
+        while ((int)db->upload_events.size() < NSLICE) {
+            cudaEvent_t e;
+            SNK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            db->upload_events.push_back(e);
+        }
+        const size_t pitch = (size_t)T * db->Dt * 8;
+        // slice boundaries in steps: a short first slice, the rest even
+        int64_t s0 = 0;
+        for (int c = 0; c < NSLICE; ++c) {
+            const int64_t s1 = c == NSLICE - 1 ? nsteps : std::max<int64_t>(2, (c + 1) * nsteps / NSLICE - nsteps / (2 * NSLICE));
+            const int64_t f0 = s0 * db->m, f1 = c == NSLICE - 1 ? T : s1 * db->m;   // the last slice carries the cut remainder
+            const size_t off = (size_t)f0 * db->Dt * 8, width = (size_t)(f1 - f0) * db->Dt * 8;
+            SNK_CUDA(cudaMemcpy2DAsync((char *)db->ws_h0.p + off, pitch, (const char *)targets + off, pitch, width,
+                                       (size_t)B, cudaMemcpyHostToDevice, db->copy_stream));
+            SNK_CUDA(cudaEventRecord(db->upload_events[c], db->copy_stream));
+            db->step_waits.push_back(std::make_pair(s0, db->upload_events[c]));
+            s0 = s1;
+        }
+    } else if (frames) {
         SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, targets, (size_t)frames * db->Dt * 8, cudaMemcpyHostToDevice, db->stream));
-    SNK_TRY(snk_greedy_batch_dev(db, (const double *)db->ws_h0.p, lens, B, start_state, (int64_t *)db->ws_h1.p,
-                                 step_dist ? (double *)db->ws_h2.p : nullptr, db->stream));
+    }
+    const int rc_greedy = snk_greedy_batch_dev(db, (const double *)db->ws_h0.p, lens, B, start_state,
+                                               (int64_t *)db->ws_h1.p, step_dist ? (double *)db->ws_h2.p : nullptr,
+                                               db->stream);
+    db->step_waits.clear();
+    if (rc_greedy) {
+        cudaStreamSynchronize(db->copy_stream);
+        return rc_greedy;
+    }
     if (steps) {
         SNK_CUDA(cudaMemcpyAsync(paths, db->ws_h1.p, (size_t)steps * 8, cudaMemcpyDeviceToHost, db->stream));
         if (step_dist)

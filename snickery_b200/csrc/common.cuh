@@ -6,6 +6,7 @@
 #include <stddef.h>
 #include <math.h>
 #include <vector>
+#include <utility>
 #include "snk_b200.h"
 
 void snk_set_error(const char *fmt, ...);
@@ -89,6 +90,10 @@ struct snk_db {
     float *maxn_j16 = nullptr;  // [1]
     void *tc_state = nullptr;   // tensor maps etc. (knn_tc.cu)
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host entry points: uploads that overlap the first search steps
+    // greedy batches may wait on upload events before given steps (step index, event), sorted by step
+    std::vector<std::pair<int64_t, cudaEvent_t>> step_waits;
+    std::vector<cudaEvent_t> upload_events;
     cudaEvent_t ev = nullptr;
     snk_buf ws_q, ws_dist, ws_list, ws_misc, ws_io, ws_io2, ws_tiles, ws_bp, ws_tc, ws_h0, ws_h1, ws_h2, ws_h3, ws_flags;
     int64_t counters[4] = {0, 0, 0, 0};

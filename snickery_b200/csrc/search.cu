@@ -264,11 +264,15 @@ int greedy_run(snk_db *db, const std::vector<greedy_meta> &meta, const double *d
     SNK_CUDA(cudaMemcpyAsync(d_meta, meta.data(), sizeof(greedy_meta) * B, cudaMemcpyHostToDevice, st));
     SNK_CUDA(cudaStreamSynchronize(st));   // meta may be a stack-lifetime host vector
     int nact_prev = 0;
+    size_t next_wait = 0;
     for (int64_t t = 0; t <= maxsteps; ++t) {
         int nact = 0;
         while (nact < B && meta[nact].nsteps > t) ++nact;
         const int grid = std::max(nact, nact_prev);
         if (grid == 0) break;
+        // chunked uploads (host entry point): step t may start once its target frames have landed
+        while (next_wait < db->step_waits.size() && db->step_waits[next_wait].first <= t)
+            SNK_CUDA(cudaStreamWaitEvent(st, db->step_waits[next_wait++].second, 0));
         greedy_assemble_kernel<<<grid, 128, 0, st>>>(d_meta, nact_prev, nact, t, d_targets, db->Dt, m, db->Jc_raw,
                                                      db->wj, db->Dj, db->Djq, db->prev_row_off, db->prev_col,
                                                      db->cur_row_off, db->cur_col, ix, dist, d_paths, d_step_dist, Q);
