@@ -33,37 +33,44 @@ __device__ __forceinline__ bool fpair_lt(float v1, int i1, float v2, int i2) {
     return v1 < v2 || (v1 == v2 && i1 < i2);
 }
 
-// squared float64 distances of rows u0 and u1 (u1 < 0: only u0) to the query held in shared memory
+// sum over a contiguous segment of (q - f32 row * f64 weight)^2 for two rows at once; loads are issued
+// four deep before they are consumed so the gathers overlap
+__device__ __forceinline__ void seg_pair(const float *__restrict__ r0, const float *__restrict__ r1,
+                                         const double *__restrict__ w_s, const double *__restrict__ q_s, int n, int lane,
+                                         double &a0, double &a1) {
+    int d = lane;
+    for (; d + 96 < n; d += 128) {
+        float y0[4], y1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { y0[u] = __ldg(r0 + d + 32 * u); y1[u] = __ldg(r1 + d + 32 * u); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double w = w_s[d + 32 * u], x = q_s[d + 32 * u];
+            const double e0 = __dsub_rn(x, (double)y0[u] * w), e1 = __dsub_rn(x, (double)y1[u] * w);
+            a0 = __dadd_rn(a0, __dmul_rn(e0, e0));
+            a1 = __dadd_rn(a1, __dmul_rn(e1, e1));
+        }
+    }
+    for (; d < n; d += 32) {
+        const double w = w_s[d], x = q_s[d];
+        const double e0 = __dsub_rn(x, (double)__ldg(r0 + d) * w), e1 = __dsub_rn(x, (double)__ldg(r1 + d) * w);
+        a0 = __dadd_rn(a0, __dmul_rn(e0, e0));
+        a1 = __dadd_rn(a1, __dmul_rn(e1, e1));
+    }
+}
+
+// squared float64 distances of rows u0 and u1 (u1 < 0: only u0) to the query held in shared memory.
+// wB_s holds the target weights repeated over the m frames of the window (the window is contiguous in F_raw).
 __device__ __forceinline__ void row_pair_dist(const rr_space &sp, const double *__restrict__ q_s,
                                               const double *__restrict__ wA_s, const double *__restrict__ wB_s, int u0,
                                               int u1, int lane, double &out0, double &out1) {
     double a0 = 0.0, a1 = 0.0;
     const bool two = u1 >= 0;
     const int v1 = two ? u1 : u0;
-    if (sp.dA > 0) {
-        const float *r0 = sp.A + ((int64_t)u0 + sp.a_row_off) * sp.ldA + sp.a_col;
-        const float *r1 = sp.A + ((int64_t)v1 + sp.a_row_off) * sp.ldA + sp.a_col;
-        for (int d = lane; d < sp.dA; d += 32) {
-            const double w = wA_s[d], x = q_s[d];
-            const double y0 = (double)__ldg(r0 + d) * w, y1 = (double)__ldg(r1 + d) * w;
-            const double e0 = __dsub_rn(x, y0), e1 = __dsub_rn(x, y1);
-            a0 = __dadd_rn(a0, __dmul_rn(e0, e0));
-            a1 = __dadd_rn(a1, __dmul_rn(e1, e1));
-        }
-    }
-    // the m-frame window of row u is contiguous in F_raw: frames u .. u+m-1
-    const float *f0 = sp.B + (int64_t)u0 * sp.ldB;
-    const float *f1 = sp.B + (int64_t)v1 * sp.ldB;
-    for (int j = 0; j < sp.m; ++j) {
-        const double *qj = q_s + sp.dA + j * sp.Dt;
-        for (int c = lane; c < sp.Dt; c += 32) {
-            const double w = wB_s[c], x = qj[c];
-            const double y0 = (double)__ldg(f0 + j * sp.ldB + c) * w, y1 = (double)__ldg(f1 + j * sp.ldB + c) * w;
-            const double e0 = __dsub_rn(x, y0), e1 = __dsub_rn(x, y1);
-            a0 = __dadd_rn(a0, __dmul_rn(e0, e0));
-            a1 = __dadd_rn(a1, __dmul_rn(e1, e1));
-        }
-    }
+    if (sp.dA > 0)
+        seg_pair(sp.A + ((int64_t)u0 + sp.a_row_off) * sp.ldA + sp.a_col, sp.A + ((int64_t)v1 + sp.a_row_off) * sp.ldA + sp.a_col,
+                 wA_s, q_s, sp.dA, lane, a0, a1);
+    seg_pair(sp.B + (int64_t)u0 * sp.ldB, sp.B + (int64_t)v1 * sp.ldB, wB_s, q_s + sp.dA, sp.dB, lane, a0, a1);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         a0 = __dadd_rn(a0, __shfl_xor_sync(0xffffffffu, a0, off));
@@ -84,8 +91,8 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
     extern __shared__ double sm[];
     double *q_s = sm;                       // [D]
     double *wA_s = q_s + sp.D;              // [dA]
-    double *wB_s = wA_s + sp.dA;            // [Dt]
-    double *d2 = wB_s + sp.Dt;              // [KP]
+    double *wB_s = wA_s + sp.dA;            // [dB] target weights repeated over the window
+    double *d2 = wB_s + sp.dB;              // [KP]
     int *ids = reinterpret_cast<int *>(d2 + KP);          // [KP]
     float *sval = reinterpret_cast<float *>(ids + KP);    // [KP] approximate keys of the selected rows
     float *mval = sval + KP;                               // kMerge: [n] all list keys
@@ -98,7 +105,7 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
 
     for (int d = tid; d < sp.D; d += RR_THREADS) q_s[d] = Q[q * (int64_t)sp.D + d];
     for (int d = tid; d < sp.dA; d += RR_THREADS) wA_s[d] = sp.wA[sp.a_col + d];
-    for (int d = tid; d < sp.Dt; d += RR_THREADS) wB_s[d] = sp.wB[d];
+    for (int d = tid; d < sp.dB; d += RR_THREADS) wB_s[d] = sp.wB[d % sp.Dt];
 
     if (kMerge) {
         const int n = nlists * lsz;
@@ -203,7 +210,7 @@ rr_space make_rr(const snk_db *db, const snk_space &sp) {
 }
 
 size_t rr_smem(const rr_space &rs, int KP, int nmerge) {
-    return (size_t)(rs.D + rs.dA + rs.Dt + KP) * 8 + (size_t)KP * 8 + (size_t)nmerge * 8 + 16;
+    return (size_t)(rs.D + rs.dA + rs.dB + KP) * 8 + (size_t)KP * 8 + (size_t)nmerge * 8 + 16;
 }
 
 }  // namespace

@@ -164,8 +164,9 @@ int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, d
         int *cert_arr = sticky ? d_sticky + qb : cert;
         int *cert_cnt = sticky ? d_sticky_count : cert + qn_;
         if (!sticky) SNK_CUDA(cudaMemsetAsync(cert + qn_, 0, 4, st));
+        // fused merge + re-rank: 16 exact distances are plenty for k <= 2 (the certificate still guards it)
         if (lists.valid)
-            SNK_TRY(snk_merge_rerank(db, sp, Qb, qn_, lists.val, lists.id, lists.nlists, lists.lsz, KP, k,
+            SNK_TRY(snk_merge_rerank(db, sp, Qb, qn_, lists.val, lists.id, lists.nlists, lists.lsz, k <= 2 ? 16 : KP, k,
                                      d_dist + qb * out_stride, d_idx + qb * out_stride, out_stride, id_offset, qerr,
                                      joint ? db->err_j16 : db->err_t16, qn, joint ? db->maxn_j16 : db->maxn_t16,
                                      cert_arr, cert_cnt, sticky, st));
