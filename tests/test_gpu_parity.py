@@ -478,3 +478,54 @@ def test_certificate_failure_paths_stay_exact(golden_epoch, golden_halfphone, mo
     cand, dist = g3.preselect_units_acoustic(golden_halfphone["targets"])
     assert_knn_matches(dist, cand, golden_halfphone["knn_dist"], golden_halfphone["knn_idx"])
     assert g3.db.counters()["recertified"] >= 10
+
+
+# ------------------------------------------------------------------------------------ BASELINE.json full size (configs[1])
+def test_full_size_database_properties():
+    """700k-unit database (IS2018_nick_simplified shape), size-independent properties:
+    identity known answer, tensor-core engine == exact-arithmetic SIMT engine, spot float64 audit,
+    idempotence under re-weighting with the same weights."""
+    import bench
+    cfg = bench.workload_config()
+    db = bench.make_database(bench.DB_UNITS)
+    g = Synthesiser(cfg, db["F"], db["Jc"])
+    wt = g.target_weight_vector
+    F64 = db["F"].astype(np.float64) * wt
+    # (1) the reference's known answer at full size: consecutive database frames give the identity path
+    starts = [5, 123456, 699000 - 6 * 40]
+    utts = [F64[s:s + 6 * 40] for s in starts]
+    paths, dists = g.greedy_joint_search_batch(utts, starts, return_dists=True)
+    for s, p, d in zip(starts, paths, dists):
+        assert p == list(range(s, s + 6 * 40, 6))
+        assert np.all(d == 0.0)
+    # (2) noisy targets: tensor-core path == SIMT path (independent arithmetic), including distances
+    cat = bench.make_batch(db["F"], wt, 24, 60, seed=4242)
+    lens = np.full(24, 60, dtype=np.int64)
+    g.db.set_engine(engine.ENGINE_TC)
+    p_tc, d_tc = g.db.greedy_batch_cat(cat, lens, return_dists=True)
+    c = g.db.counters()
+    g.db.set_engine(engine.ENGINE_SIMT)
+    p_simt, d_simt = g.db.greedy_batch_cat(cat, lens, return_dists=True)
+    assert c["recertified"] <= 2
+    for a, b, da, dbb in zip(p_tc, p_simt, d_tc, d_simt):
+        if a != b:   # only a tie within 1e-6 may separate the two engines
+            t = next(i for i in range(len(a)) if a[i] != b[i])
+            assert abs(da[t] - dbb[t]) <= TIE_RTOL * dbb[t]
+        else:
+            np.testing.assert_allclose(da, dbb, rtol=1e-12)
+    # (3) float64 audit of the first two steps of one utterance against a numpy scan of all 699,995 rows
+    Jw = db["Jc"].astype(np.float64) * g.join_weight_vector
+    prev = np.zeros(151)
+    for t in range(2):
+        q = np.concatenate([prev, cat[t * 6:(t + 1) * 6].reshape(-1)])
+        d2 = ((Jw[:699995] - q[:151]) ** 2).sum(1)
+        for j in range(6):
+            d2 += ((F64[j:699995 + j] - q[151 + 61 * j:151 + 61 * (j + 1)]) ** 2).sum(1)
+        ix = p_tc[0][t]
+        assert d2[ix] <= d2.min() * (1 + 2 * TIE_RTOL)
+        assert abs(np.sqrt(d2[ix]) - d_tc[0][t]) <= COST_RTOL * d_tc[0][t]
+        prev = Jw[ix + 6]
+    # (4) re-weighting with the same weights changes nothing
+    g.db.set_engine(engine.ENGINE_TC)
+    g.reconfigure_settings({})
+    assert g.db.greedy_batch_cat(cat, lens) == p_tc
