@@ -120,6 +120,46 @@ class ShardedKnn:
         return allgather_merge_topk(d, i, self.group)
 
 
+class ShardedGreedy:
+    """Greedy joint search over a database whose joint rows are sharded by row block (SURVEY.md section 8e,
+    row "greedy chain with sharded DB"): one exchange PER TIME STEP.  Every rank searches its shard with the
+    replicated step queries, the per-shard best (distance, global row) pairs are all-gathered and merged,
+    and the next step's previous-join vector is read from the replicated weighted join contexts
+    (current_join_rep[u] = Jw[u + m], reference script/synth_simple.py:213-214,501), so no second exchange is
+    needed.  Messages are B * 16 bytes per rank and step: latency bound."""
+
+    def __init__(self, F, Jc, multiepoch, wt, wj, rank, world, device, group=None):
+        import torch
+        self.m = int(multiepoch)
+        self.knn = ShardedKnn.from_epoch_db(F, Jc, multiepoch, wt, wj, rank, world, device, group)
+        dev = torch.device("cuda", device)
+        # replicated float64 weighted join contexts, the reference's own values (f32 data * f64 weights)
+        self.Jw = torch.from_numpy(np.ascontiguousarray(Jc, dtype=np.float32)).to(dev).double() * \
+            torch.from_numpy(np.asarray(wj, dtype=np.float64)).to(dev)
+        self.Dj = self.Jw.shape[1]
+        self.Dt = F.shape[1]
+
+    def search(self, targets, start_states=None):
+        """targets: torch float64 CUDA tensor [B, T, Dt] (weighted, equal lengths); returns int64 [B, T // m]."""
+        import torch
+        B, T, Dt = targets.shape
+        steps = T // self.m
+        if steps == 0:
+            raise ValueError("Not enough data points to segment array in 'cut' mode")
+        paths = torch.empty((B, steps), dtype=torch.int64, device=targets.device)
+        prev = torch.zeros((B, self.Dj), dtype=torch.float64, device=targets.device)
+        if start_states is not None:
+            ss = torch.as_tensor(start_states, device=targets.device)
+            prev = torch.where((ss >= 0)[:, None], self.Jw[ss.clamp(min=0)], prev)   # prev_join_rep[u] = Jw[u]
+        for t in range(steps):
+            q = torch.cat([prev, targets[:, t * self.m:(t + 1) * self.m, :].reshape(B, self.m * Dt)], dim=1).contiguous()
+            _, idx = self.knn.query(q, 1)
+            ix = idx[:, 0]
+            paths[:, t] = ix
+            prev = self.Jw[ix + self.m]
+        return paths
+
+
 def gather_paths(paths_local, utt_ids_local, n_utts, group=None):
     """Collect utterance-sharded path lists on every rank in utterance order (object all-gather: the
     payload is a few KB of integers)."""
