@@ -529,3 +529,34 @@ def test_full_size_database_properties():
     g.db.set_engine(engine.ENGINE_TC)
     g.reconfigure_settings({})
     assert g.db.greedy_batch_cat(cat, lens) == p_tc
+
+
+def test_stream_weight_balancing_loop_matches_cpu_loop(golden_epoch):
+    """Row N1: the RPROP balancing loop (balance_stream_weights.py:82-172) driven by the GPU engine follows
+    the same weight trajectory as the same loop driven by the oracle."""
+    from snickery_b200 import balance
+    cfg = epoch_config(multiepoch=1)
+    F, Jc = golden_epoch["F"], golden_epoch["Jc"]
+    tune = [x.astype(np.float64) for x in syn.make_targets(F, 4, 40, seed=88)]
+    g = Synthesiser(cfg, F, Jc)
+    best_g, losses_g, hist_g = balance.balance_stream_weights(g, tune, max_epochs=5)
+
+    o = O.OracleSynthesiser(cfg, F, Jc)
+
+    def evaluate(jw, tw):
+        o.set_join_weights(jw)
+        o.set_target_weights(tw)
+        o.get_tree_for_greedy_search()
+        js, ts = [], []
+        for u in tune:
+            uf = O.weight(u, o.target_weight_vector)
+            p = o.greedy_joint_search(uf)
+            ts.append(o.get_target_scores_per_stream(uf, p))
+            js.append(o.get_join_scores_per_stream(p))
+        return np.vstack(js), np.vstack(ts)
+
+    best_o, losses_o, hist_o = balance.rprop_balance(evaluate, 4, 2, max_epochs=5)
+    assert len(losses_g) == len(losses_o)
+    np.testing.assert_allclose(losses_g, losses_o, rtol=1e-9)
+    np.testing.assert_allclose(np.array(hist_g), np.array(hist_o), rtol=1e-12)
+    np.testing.assert_allclose(best_g, best_o, rtol=1e-12)

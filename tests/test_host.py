@@ -40,3 +40,20 @@ def test_weight_vectors_match_oracle():
     assert np.array_equal(s.target_weight_vector, wt) and np.array_equal(s.join_weight_vector, wj)
     with pytest.raises(AssertionError):
         s.set_join_weights([1.0])   # assert len(weights) == len(streams), synth_simple.py:235
+
+
+def test_rprop_balance_loop_on_a_synthetic_cost_surface():
+    """Host logic of the balancing loop (balance_stream_weights.py:82-172) with an analytic evaluate()."""
+    from snickery_b200 import balance
+
+    def evaluate(jw, tw):   # stream cost grows with the square of its weight
+        js = np.tile((np.array([1.0, 2.0, 3.0, 4.0]) * jw ** 2)[None, :], (5, 1))
+        ts = np.tile((np.array([10.0, 0.5]) * tw ** 2)[None, :], (6, 1))
+        js[0, :] = 0.0      # zeros are ignored by the mean (:99-107)
+        return js, ts
+
+    best, losses, hist = balance.rprop_balance(evaluate, 4, 2, max_epochs=60)
+    assert losses[-1] < losses[0] * 0.2 and len(hist) == len(losses)
+    assert np.all(best >= 0.0)
+    m = balance.mean_scores_without_zeros(*evaluate(best[:4], best[4:]))
+    assert abs(m[:4].sum() - m[4:].sum()) < 0.5 * m.sum()       # join and target contributions pulled together
