@@ -60,9 +60,17 @@ struct tc_params {
     const float *nrm;       // [rows] squared norms of the fp16 rows
     float *oval;            // fused : [nq_pad, nchunks * EPI_SPLIT, LSZ] keys (ascending)
     int *oid;               //         row ids
-    float *odist;           // store : [nq, ldo] keys of rows row_lo ..
+    float *odist;           // store : [nq, ldo] keys of the scanned tiles, compacted (tile_stride > 1 = sample)
     int64_t ldo;
+    int tile_stride;        // scan every tile_stride-th tile of a chunk (1 = all)
+    // emit mode: every row whose key is <= thr[q] is appended to the (query, chunk, half) buffer
+    const float *thr;       // [nq]
+    float *bufv;            // [nq_pad, nchunks * EPI_SPLIT, cap]
+    int *bufi;
+    int cap;
+    float *tau;             // [nq] preset to thr; a buffer overflow writes -inf (certificate must fail)
 };
+constexpr int MODE_LIST = 0, MODE_STORE = 1, MODE_EMIT = 2;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -189,7 +197,7 @@ template <int SCHED> struct sched_layout {
 };
 
 // ---------------------------------------------------------------- kernel
-template <bool kStore, int LSZ, int SCHED>
+template <int MODE, int LSZ, int SCHED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapS,
               const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapGslab,
@@ -216,7 +224,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     const int qt = blockIdx.x / p.nchunks, chunk = blockIdx.x % p.nchunks;
     const int64_t row_beg = p.row_lo + (int64_t)chunk * p.chunk_rows;
     const int64_t row_end = min(p.row_hi, row_beg + p.chunk_rows);
-    const int ntiles = row_end > row_beg ? (int)((row_end - row_beg + BN - 1) / BN) : 0;
+    const int64_t tstep = (int64_t)BN * p.tile_stride;
+    const int ntiles = row_end > row_beg ? (int)((row_end - row_beg + tstep - 1) / tstep) : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) {
@@ -252,7 +261,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             using S = sched_traits<SCHED>;
             using L = sched_layout<SCHED>;
             for (int t = 0; t < ntiles; ++t) {
-                const int r0 = (int)(row_beg + (int64_t)t * BN);
+                const int r0 = (int)(row_beg + (int64_t)t * tstep);
                 const uint32_t ph_s = (uint32_t)t & 1u;
                 const int gr = t % S::GR;
                 const uint32_t ph_g = (uint32_t)(t / S::GR) & 1u;
@@ -281,7 +290,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < ntiles; ++t) {
-            const int64_t r0 = row_beg + (int64_t)t * BN;
+            const int64_t r0 = row_beg + (int64_t)t * tstep;
             for (int l = 0; l < p.nload; ++l) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 if (elect_one()) {
@@ -401,14 +410,19 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         for (int i = 0; i < LSZ; ++i) { lv[i] = INFINITY; li[i] = -1; }
         const bool embed = SCHED != 0 || p.embed != 0;
         float nrm_next = (!embed && et < BN && ntiles > 0 && row_beg + et < row_end) ? __ldg(p.nrm + row_beg + et) : INFINITY;
+        // emit mode state
+        const float thr = (MODE == MODE_EMIT && q < p.nq) ? p.thr[q] : -INFINITY;
+        int ecnt = 0;
+        float *ebv = MODE == MODE_EMIT ? p.bufv + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * p.cap : nullptr;
+        int *ebi = MODE == MODE_EMIT ? p.bufi + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * p.cap : nullptr;
         for (int t = 0; t < ntiles; ++t) {
             const int acc = t & 1;
             const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
-            const int64_t r0 = row_beg + (int64_t)t * BN;
+            const int64_t r0 = row_beg + (int64_t)t * tstep;
             if (!embed) {
                 if (et < BN) {
                     nrm_s[acc * BN + et] = nrm_next;
-                    nrm_next = (t + 1 < ntiles && r0 + BN + et < row_end) ? __ldg(p.nrm + r0 + BN + et) : INFINITY;   // next tile's norm, a tile early
+                    nrm_next = (t + 1 < ntiles && r0 + tstep + et < row_end) ? __ldg(p.nrm + r0 + tstep + et) : INFINITY;   // next tile's norm, a tile early
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
             }
@@ -439,9 +453,17 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     for (int j = 0; j < 32; ++j)
                         if (r0 + c0 + j >= row_end) key[j] = INFINITY;
                 }
-                if (kStore) {
+                if (MODE == MODE_EMIT) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (key[j] <= thr) {
+                            if (ecnt < p.cap) { ebv[ecnt] = key[j]; ebi[ecnt] = (int)(r0 + c0 + j); }
+                            ++ecnt;
+                        }
+                    }
+                } else if (MODE == MODE_STORE) {
                     if (q < p.nq) {
-                        float *dst = p.odist + q * p.ldo + (r0 - p.row_lo) + c0;
+                        float *dst = p.odist + q * p.ldo + (r0 - p.row_lo) / p.tile_stride + c0;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
                             *reinterpret_cast<float4 *>(dst + j) = make_float4(key[j], key[j + 1], key[j + 2], key[j + 3]);
@@ -492,7 +514,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 }
             }
         }
-        if (!kStore) {
+        if (MODE == MODE_EMIT && ecnt > p.cap && q < p.nq) p.tau[q] = -INFINITY;   // rows were lost: never certify
+        if (MODE == MODE_LIST) {
             float *ov = p.oval + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * LSZ;
             int *oi = p.oid + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * LSZ;
 #pragma unroll
@@ -512,6 +535,26 @@ __global__ void chunk_tau_kernel(const float *__restrict__ oval, int64_t nq, int
         for (int c = 0; c < nlists; ++c) t = fminf(t, oval[((size_t)q * nlists + c) * lsz + lsz - 1]);
         tau[q] = t;
     }
+}
+// thr[q] = k-th smallest of the KP sampled keys (+inf if the sample held fewer than k rows); tau starts equal
+__global__ void kth_select_kernel(const float *__restrict__ val, const int *__restrict__ id, int64_t nq, int KP, int k,
+                                  float *__restrict__ thr, float *__restrict__ tau) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    float kth = INFINITY;
+    for (int t = lane; t < KP; t += 32) {
+        const float v = id[q * KP + t] >= 0 ? val[q * KP + t] : INFINITY;
+        int rank = 0;
+        for (int j = 0; j < KP; ++j) {
+            const float w = id[q * KP + j] >= 0 ? val[q * KP + j] : INFINITY;
+            rank += (w < v || (w == v && j < t)) ? 1 : 0;
+        }
+        if (rank == k - 1) kth = v;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) kth = fminf(kth, __shfl_xor_sync(0xffffffffu, kth, off));
+    if (lane == 0) { thr[q] = kth; tau[q] = kth; }
 }
 __global__ void fill_kernel(float *p, int64_t n, float v) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
@@ -645,17 +688,18 @@ int build_space(snk_db *db, int space, tc_space_host *h) {
 
 typedef void (*tc_kernel_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const tc_params);
 
-template <bool kStore, int LSZ>
+template <int MODE, int LSZ>
 tc_kernel_fn pick_sched(int sched) {
     switch (sched) {
-    case 1: return knn_tc_kernel<kStore, LSZ, 1>;
-    case 2: return knn_tc_kernel<kStore, LSZ, 2>;
-    default: return knn_tc_kernel<kStore, LSZ, 0>;
+    case 1: return knn_tc_kernel<MODE, LSZ, 1>;
+    case 2: return knn_tc_kernel<MODE, LSZ, 2>;
+    default: return knn_tc_kernel<MODE, LSZ, 0>;
     }
 }
-tc_kernel_fn pick_kernel(bool store, int lsz, int sched) {
-    if (store) return pick_sched<true, 4>(sched);
-    return lsz == 4 ? pick_sched<false, 4>(sched) : pick_sched<false, 8>(sched);
+tc_kernel_fn pick_kernel(int mode, int lsz, int sched) {
+    if (mode == MODE_STORE) return pick_sched<MODE_STORE, 4>(sched);
+    if (mode == MODE_EMIT) return pick_sched<MODE_EMIT, 4>(sched);
+    return lsz == 4 ? pick_sched<MODE_LIST, 4>(sched) : pick_sched<MODE_LIST, 8>(sched);
 }
 
 }  // namespace
@@ -681,8 +725,9 @@ int snk_tc_prepare(snk_db *db) {
         if (s->sp[sp].ok) s->smem[sp] = s->sp[sp].smem;
     }
     for (int sched = 0; sched <= 2; ++sched)
-        for (int v = 0; v < 3; ++v)
-            SNK_CUDA(cudaFuncSetAttribute((const void *)pick_kernel(v == 2, v == 1 ? 8 : 4, sched),
+        for (int v = 0; v < 4; ++v)
+            SNK_CUDA(cudaFuncSetAttribute((const void *)pick_kernel(v == 2 ? MODE_STORE : (v == 3 ? MODE_EMIT : MODE_LIST),
+                                                                    v == 1 ? 8 : 4, sched),
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return 0;
 }
@@ -725,6 +770,7 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
     memcpy(p.load, h.load, sizeof(h.load));
     memcpy(p.sub, h.sub, sizeof(h.sub));
     p.nq = nq;
+    p.tile_stride = 1;
     p.nrm = space == SNK_SPACE_JOINT ? db->nrm_j16 : db->nrm_t16;
     const size_t smem = s->smem[space];
     const int64_t row_tiles = snk_cdiv(sp.rows, BN);
@@ -744,7 +790,7 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         p.oid = (int *)(p.oval + nlist);
         {
             snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)sp.rows * sp.D, st);
-            pick_kernel(false, lsz, h.sched)<<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
+            pick_kernel(MODE_LIST, lsz, h.sched)<<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
         }
         SNK_CUDA(cudaGetLastError());
         if (lists && snk_merge_rerank_fits(nlists, lsz)) {   // merge + tau happen inside the re-rank kernel
@@ -763,35 +809,84 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         }
         return 0;
     }
-    // store mode: keys of a row span go to HBM, the warp scan selects the KP smallest per query
-    const size_t WS = (size_t)512 << 20;
-    int64_t span = (int64_t)(WS / 4 / (size_t)nq_pad) / BN * BN;
-    span = std::max<int64_t>(BN, std::min<int64_t>(span, row_tiles * BN));
-    SNK_TRY(snk_buf_reserve(&db->ws_dist, (size_t)nq_pad * span * 4));
-    p.odist = (float *)db->ws_dist.p;
-    p.ldo = span;
-    fill_kernel<<<64, 256, 0, st>>>(d_tau, nq, INFINITY);
-    SNK_CUDA(cudaGetLastError());
-    bool first = true;
-    for (int64_t rb = 0; rb < sp.rows; rb += span) {
-        const int64_t rn = std::min<int64_t>(span, sp.rows - rb);
-        const int64_t tiles = snk_cdiv(rn, BN);
-        int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(db->sm_count / std::max(nqt, 1), tiles));
+    // ---- larger k.  store_scan: keys of a row span (every `stride`-th tile of it) go to HBM, the warp scan
+    // keeps the KPs smallest per query.
+    auto store_scan = [&](int stride, int KPs, float *o_val, int *o_id) -> int {
+        const size_t WS = (size_t)512 << 20;
+        int64_t span_cols = (int64_t)(WS / 4 / (size_t)nq_pad) / BN * BN;
+        span_cols = std::max<int64_t>(BN, std::min<int64_t>(span_cols, snk_cdiv(row_tiles, stride) * BN));
+        const int64_t span_rows = span_cols * stride;
+        SNK_TRY(snk_buf_reserve(&db->ws_dist, (size_t)nq_pad * span_cols * 4));
+        p.odist = (float *)db->ws_dist.p;
+        p.ldo = span_cols;
+        p.tile_stride = stride;
+        bool first = true;
+        for (int64_t rb = 0; rb < sp.rows; rb += span_rows) {
+            const int64_t rn = std::min<int64_t>(span_rows, sp.rows - rb);
+            const int64_t tiles = snk_cdiv(rn, (int64_t)BN * stride);      // sampled tiles of this span
+            int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(db->sm_count / std::max(nqt, 1), tiles));
+            if (nqt > db->sm_count) nchunks = 1;
+            p.row_lo = rb; p.row_hi = rb + rn; p.nchunks = nchunks;
+            p.chunk_rows = snk_cdiv(tiles, nchunks) * BN * stride;
+            {
+                snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)tiles * BN * sp.D, st);
+                pick_kernel(MODE_STORE, 4, h.sched)<<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
+            }
+            SNK_CUDA(cudaGetLastError());
+            db->counters[2] += 1;
+            for (int64_t q0 = 0; q0 < nq; q0 += 32768) {
+                const int64_t n = std::min<int64_t>(32768, nq - q0);
+                SNK_TRY(snk_topk_scan(db, p.odist + q0 * span_cols, nullptr, n, tiles * BN, span_cols, (int)rb, KPs, first,
+                                      o_val + q0 * KPs, o_id + q0 * KPs, st));
+            }
+            first = false;
+        }
+        p.tile_stride = 1;
+        return 0;
+    };
+
+    // Sampled threshold + emit: the k-th smallest key of every 8th tile bounds the k-th smallest key overall
+    // from above; a second pass over the whole database appends every row at or below that bound to
+    // per-(query, chunk, half) buffers (about 8k rows per query), and only those are scanned and re-ranked.
+    // Rows above the bound cannot be among the k nearest, so the bound itself is the certificate's tau.
+    constexpr int SAMPLE = 8;
+    if (!getenv("SNK_TC_NOEMIT") && sp.rows / SAMPLE >= (int64_t)16 * k && row_tiles >= 4 * SAMPLE) {
+        SNK_TRY(store_scan(SAMPLE, KP, d_val, d_id));
+        SNK_TRY(snk_buf_reserve(&db->ws_misc, (size_t)nq_pad * 4));
+        float *thr = (float *)db->ws_misc.p;
+        kth_select_kernel<<<(unsigned)snk_cdiv(nq * 32, 256), 256, 0, st>>>(d_val, d_id, nq, KP, k, thr, d_tau);
+        SNK_CUDA(cudaGetLastError());
+        int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(db->sm_count / std::max(nqt, 1), row_tiles));
         if (nqt > db->sm_count) nchunks = 1;
-        p.row_lo = rb; p.row_hi = rb + rn; p.nchunks = nchunks;
-        p.chunk_rows = snk_cdiv(tiles, nchunks) * BN;
+        const int nlists = nchunks * EPI_SPLIT;
+        // neighbours cluster on a few consecutive rows (trajectories), so one list may take most of the ~8k
+        // expected rows: size every list for that
+        const int cap = (int)snk_round_up(std::min<int64_t>(1024, std::max<int64_t>(128, (int64_t)10 * k)), 32);
+        const size_t nent = (size_t)nq_pad * nlists * cap;
+        SNK_TRY(snk_buf_reserve(&db->ws_tc, nent * 8));
+        p.bufv = (float *)db->ws_tc.p;
+        p.bufi = (int *)(p.bufv + nent);
+        p.cap = cap; p.thr = thr; p.tau = d_tau;
+        p.row_lo = 0; p.row_hi = sp.rows; p.nchunks = nchunks;
+        p.chunk_rows = snk_cdiv(row_tiles, nchunks) * BN;
+        SNK_CUDA(cudaMemsetAsync(p.bufi, 0xFF, nent * 4, st));     // unused slots read as id -1
         {
-            snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)rn * sp.D, st);
-            pick_kernel(true, 4, h.sched)<<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
+            snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)sp.rows * sp.D, st);
+            pick_kernel(MODE_EMIT, 4, h.sched)<<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
         }
         SNK_CUDA(cudaGetLastError());
-        db->counters[2] += 1;
+        db->counters[2] += 3;
         for (int64_t q0 = 0; q0 < nq; q0 += 32768) {
             const int64_t n = std::min<int64_t>(32768, nq - q0);
-            SNK_TRY(snk_topk_scan(db, p.odist + q0 * span, nullptr, n, snk_cdiv(rn, BN) * BN, span, (int)rb, KP, first,
-                                  d_val + q0 * KP, d_id + q0 * KP, st));
+            SNK_TRY(snk_topk_scan(db, p.bufv + (size_t)q0 * nlists * cap, p.bufi + (size_t)q0 * nlists * cap, n,
+                                  (int64_t)nlists * cap, (int64_t)nlists * cap, 0, KP, true, d_val + q0 * KP, d_id + q0 * KP,
+                                  st));
         }
-        first = false;
+        return 0;
     }
+    // small databases: plain store + scan of every key
+    fill_kernel<<<64, 256, 0, st>>>(d_tau, nq, INFINITY);
+    SNK_CUDA(cudaGetLastError());
+    SNK_TRY(store_scan(1, KP, d_val, d_id));
     return 0;
 }
