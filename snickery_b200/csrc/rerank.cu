@@ -16,7 +16,7 @@
 namespace {
 
 constexpr int RR_THREADS = 256;
-constexpr int RR_MAX_MERGE = 1024;   // most list entries a block merges in shared memory
+constexpr int RR_MAX_MERGE = 2048;   // most list entries a block merges in shared memory
 
 struct rr_space {
     const float *A;    // Jc_raw
@@ -95,8 +95,9 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
     double *d2 = wB_s + sp.dB;              // [KP]
     int *ids = reinterpret_cast<int *>(d2 + KP);          // [KP]
     float *sval = reinterpret_cast<float *>(ids + KP);    // [KP] approximate keys of the selected rows
-    float *mval = sval + KP;                               // kMerge: [n] all list keys
-    int *mid = reinterpret_cast<int *>(mval + (kMerge ? nlists * lsz : 0));   // kMerge: [n] all list ids
+    const int nm = kMerge ? nlists * lsz : 0, nwin = kMerge ? (RR_THREADS / 32) * KP : 0;
+    float *mval = sval + KP;                               // kMerge: [n] all list keys, then [nwarp*KP] phase-1 winners
+    int *mid = reinterpret_cast<int *>(mval + nm + nwin);  // kMerge: [n] all list ids, then the winners' ids
     __shared__ float s_wtau[RR_THREADS / 32];
 
     const int64_t ql = blockIdx.x;                    // index into the (compact) shortlist arrays
@@ -124,13 +125,42 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) tl = fminf(tl, __shfl_xor_sync(0xffffffffu, tl, off));
         if (lane == 0) s_wtau[warp] = tl;
-        for (int t = tid; t < n; t += RR_THREADS) {
-            const float v = mval[t];
-            const int i = mid[t];
-            int rank = 0;
-            for (int j = 0; j < n; ++j)
-                rank += (fpair_lt(mval[j], mid[j], v, i) || (mval[j] == v && mid[j] == i && j < t)) ? 1 : 0;
-            if (rank < KP) { sval[rank] = v; ids[rank] = i; }
+        if (n <= 256) {
+            for (int t = tid; t < n; t += RR_THREADS) {
+                const float v = mval[t];
+                const int i = mid[t];
+                int rank = 0;
+                for (int j = 0; j < n; ++j)
+                    rank += (fpair_lt(mval[j], mid[j], v, i) || (mval[j] == v && mid[j] == i && j < t)) ? 1 : 0;
+                if (rank < KP) { sval[rank] = v; ids[rank] = i; }
+            }
+        } else {
+            // two phases: every warp ranks its own slice and keeps the slice's KP smallest, then the
+            // nwarp * KP winners are ranked.  An entry dropped in phase 1 is >= its slice's KP-th smallest,
+            // hence >= the final KP-th smallest, so the final list's maximum still bounds every drop.
+            float *wv = mval + n;                       // [nwarp * KP] winners
+            int *wi = mid + n;
+            for (int t = tid; t < nwarp * KP; t += RR_THREADS) { wv[t] = INFINITY; wi[t] = INT_MAX; }
+            __syncthreads();
+            const int ns = (n + nwarp - 1) / nwarp, s0 = warp * ns, s1 = min(n, s0 + ns);
+            for (int t = s0 + lane; t < s1; t += 32) {
+                const float v = mval[t];
+                const int i = mid[t];
+                int rank = 0;
+                for (int j = s0; j < s1; ++j)
+                    rank += (fpair_lt(mval[j], mid[j], v, i) || (mval[j] == v && mid[j] == i && j < t)) ? 1 : 0;
+                if (rank < KP) { wv[warp * KP + rank] = v; wi[warp * KP + rank] = i; }
+            }
+            __syncthreads();
+            const int nw = nwarp * KP;
+            for (int t = tid; t < nw; t += RR_THREADS) {
+                const float v = wv[t];
+                const int i = wi[t];
+                int rank = 0;
+                for (int j = 0; j < nw; ++j)
+                    rank += (fpair_lt(wv[j], wi[j], v, i) || (wv[j] == v && wi[j] == i && j < t)) ? 1 : 0;
+                if (rank < KP) { sval[rank] = v; ids[rank] = i; }
+            }
         }
     } else {
         for (int t = tid; t < KP; t += RR_THREADS) {
@@ -210,7 +240,8 @@ rr_space make_rr(const snk_db *db, const snk_space &sp) {
 }
 
 size_t rr_smem(const rr_space &rs, int KP, int nmerge) {
-    return (size_t)(rs.D + rs.dA + rs.dB + KP) * 8 + (size_t)KP * 8 + (size_t)nmerge * 8 + 16;
+    return (size_t)(rs.D + rs.dA + rs.dB + KP) * 8 + (size_t)KP * 8 + (size_t)nmerge * 8 +
+           (nmerge ? (size_t)(RR_THREADS / 32) * KP * 8 : 0) + 16;
 }
 
 }  // namespace
