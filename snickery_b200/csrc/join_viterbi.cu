@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include <vector>
 #include <algorithm>
+#include <stdlib.h>
 
 namespace {
 
@@ -193,7 +194,7 @@ __global__ void viterbi_kernel(const vit_meta *__restrict__ meta, const int64_t 
                                const double *__restrict__ tdist, const float *__restrict__ tiles, int K, int64_t N,
                                unsigned flags, short *__restrict__ bp, int64_t *__restrict__ paths,
                                int64_t *__restrict__ path_len, double *__restrict__ path_cost,
-                               double *__restrict__ tcost, double *__restrict__ jcost) {
+                               double *__restrict__ tcost, double *__restrict__ jcost, int bp_smem_frames) {
     extern __shared__ __align__(16) float vsm[];
     const int KK = K * K;
     const int KKp = (KK + 3) & ~3;
@@ -201,6 +202,11 @@ __global__ void viterbi_kernel(const vit_meta *__restrict__ meta, const int64_t 
     float *dcur = vsm + VIT_STAGES * KKp;      // [K] cost of reaching state a (arcs 0..t-1 consumed)
     float *dnext = dcur + K;                   // [K]
     float *Dt_s = dnext + K;                   // [K] target cost row t as float32
+    // shared-memory mirror of the backpointers (the HBM copy is still written): the back-trace is a chain of
+    // T dependent reads, far cheaper from shared memory.  Used when the utterance fits (bp_smem_frames).
+    unsigned char *bp_s = reinterpret_cast<unsigned char *>(Dt_s + K);          // [bp_smem_frames][K]
+    int *col_s = reinterpret_cast<int *>(bp_s + (((size_t)bp_smem_frames * K + 3) & ~(size_t)3));   // [bp_smem_frames]
+    __shared__ double s_red[2][32];
     __shared__ float s_best;
     __shared__ int s_arg;
     const vit_meta mt = meta[blockIdx.x];
@@ -208,6 +214,7 @@ __global__ void viterbi_kernel(const vit_meta *__restrict__ meta, const int64_t 
     const int64_t f0 = mt.frame_off;
     const int64_t T = mt.T;
     const bool beam1 = flags & 1u;
+    const bool bp_local = T <= bp_smem_frames;
 
     auto fail = [&]() {
         if (c == 0) {
@@ -254,6 +261,7 @@ __global__ void viterbi_kernel(const vit_meta *__restrict__ meta, const int64_t 
             }
             dnext[c] = best;
             bp[(f0 + t + 1) * K + c] = (short)arg;
+            if (bp_local) bp_s[(t + 1) * K + c] = (unsigned char)(arg < 0 ? 255 : arg);
         }
         __syncthreads();
         if (beam1) {
@@ -298,6 +306,40 @@ __global__ void viterbi_kernel(const vit_meta *__restrict__ meta, const int64_t 
     }
     __syncthreads();
     if (s_arg < 0) { fail(); return; }
+    if (bp_local) {
+        // walk the chain in shared memory, then gather units and costs with all threads
+        if (c == 0) {
+            int col = s_arg;
+            for (int64_t t = T - 1; t >= 0; --t) {
+                col_s[t] = col;
+                if (t > 0) col = bp_s[t * K + col];
+            }
+        }
+        __syncthreads();
+        double tc = 0.0, jc = 0.0;
+        for (int64_t t = c; t < T; t += nthr) {
+            const int col = col_s[t];
+            paths[f0 + t] = cand[(f0 + t) * K + col];
+            tc += tdist[(f0 + t) * K + col];
+            if (t > 0) jc += (double)tiles[(size_t)(mt.tile_off + t - 1) * K * K + col_s[t - 1] * K + col];
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            tc += __shfl_xor_sync(0xffffffffu, tc, off);
+            jc += __shfl_xor_sync(0xffffffffu, jc, off);
+        }
+        if ((c & 31) == 0) { s_red[0][c >> 5] = tc; s_red[1][c >> 5] = jc; }
+        __syncthreads();
+        if (c == 0) {
+            double tcs = 0.0, jcs = 0.0;
+            for (int w = 0; w < (nthr + 31) / 32; ++w) { tcs += s_red[0][w]; jcs += s_red[1][w]; }
+            path_len[blockIdx.x] = T;
+            path_cost[blockIdx.x] = (double)s_best;
+            if (tcost) tcost[blockIdx.x] = tcs;
+            if (jcost) jcost[blockIdx.x] = jcs;
+        }
+        return;
+    }
     if (c == 0) {
         int col = s_arg;
         double tc = 0.0, jc = 0.0;
@@ -413,19 +455,38 @@ int snk_join_viterbi_batch_dev(snk_db *db, const int64_t *d_cand, const double *
     {   // per (utt, t): K*K*4 tile read + K*8 target costs + K*2 backpointers
         snk_prof_scope prof(db, SNK_PROF_VITERBI, (double)ntiles * ((double)K * K * 4 + K * 8.0 + K * 2.0), st);
         const size_t per_stage = (size_t)((K * K + 3) & ~3) * sizeof(float);
-        const int nst = 3 * per_stage + 3 * K * sizeof(float) <= 200 * 1024 ? 3 : 2;
-        const size_t vsmem = nst * per_stage + 3 * K * sizeof(float);
-        if (nst == 3) {
-            SNK_CUDA(cudaFuncSetAttribute(viterbi_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
-            viterbi_kernel<3><<<B, threads, vsmem, st>>>(d_meta, d_cand, d_tdist, (const float *)db->ws_tiles.p, K, db->N,
-                                                         flags, (short *)db->ws_bp.p, d_paths, d_path_len, d_path_cost,
-                                                         d_tcost, d_jcost);
-        } else {
-            SNK_CUDA(cudaFuncSetAttribute(viterbi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
-            viterbi_kernel<2><<<B, threads, vsmem, st>>>(d_meta, d_cand, d_tdist, (const float *)db->ws_tiles.p, K, db->N,
-                                                         flags, (short *)db->ws_bp.p, d_paths, d_path_len, d_path_cost,
-                                                         d_tcost, d_jcost);
+        int nst = 3;                                      // tiles in flight ahead of the DP front
+        if (const char *e = getenv("SNK_VIT_STAGES")) nst = atoi(e);
+        while (nst > 2 && nst * per_stage + 3 * K * sizeof(float) > 200 * 1024) --nst;
+        nst = std::max(2, std::min(nst, 5));
+        // shared-memory backpointer mirror for utterances up to bp_frames frames (K <= 254: one byte each)
+        int64_t maxT = 0;
+        for (int b = 0; b < B; ++b) maxT = std::max(maxT, lens[b]);
+        int bp_frames = 0;
+        if (K <= 254 && maxT * K + maxT * 4 <= 24 * 1024 && !getenv("SNK_VIT_NOBPSMEM")) bp_frames = (int)maxT;
+        const size_t bp_bytes = bp_frames ? (((size_t)bp_frames * K + 3) & ~(size_t)3) + (size_t)bp_frames * 4 : 0;
+        // a third tile stage only if all B utterances stay resident in a single wave with it (measured:
+        // a second wave costs far more than the deeper prefetch gains)
+        if (!getenv("SNK_VIT_STAGES") && nst == 3) {
+            const size_t s3 = 3 * per_stage + 3 * K * sizeof(float) + bp_bytes + 1024;
+            const int64_t resident = (int64_t)std::min<size_t>(32, (227 * 1024) / s3) * db->sm_count;
+            if (resident < B) nst = 2;
         }
+        const size_t vsmem = nst * per_stage + 3 * K * sizeof(float) + bp_bytes;
+#define SNK_LAUNCH_VIT(NST_)                                                                                              \
+    do {                                                                                                                \
+        SNK_CUDA(cudaFuncSetAttribute(viterbi_kernel<NST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));     \
+        viterbi_kernel<NST_><<<B, threads, vsmem, st>>>(d_meta, d_cand, d_tdist, (const float *)db->ws_tiles.p, K, db->N,  \
+                                                     flags, (short *)db->ws_bp.p, d_paths, d_path_len, d_path_cost,     \
+                                                     d_tcost, d_jcost, bp_frames);                                      \
+    } while (0)
+        switch (nst) {
+        case 2: SNK_LAUNCH_VIT(2); break;
+        case 3: SNK_LAUNCH_VIT(3); break;
+        case 4: SNK_LAUNCH_VIT(4); break;
+        default: SNK_LAUNCH_VIT(5); break;
+        }
+#undef SNK_LAUNCH_VIT
     }
     SNK_CUDA(cudaGetLastError());
     db->counters[2] += 1;
