@@ -560,3 +560,52 @@ def test_stream_weight_balancing_loop_matches_cpu_loop(golden_epoch):
     np.testing.assert_allclose(losses_g, losses_o, rtol=1e-9)
     np.testing.assert_allclose(np.array(hist_g), np.array(hist_o), rtol=1e-12)
     np.testing.assert_allclose(best_g, best_o, rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------ degenerate shapes and error paths
+def test_degenerate_shapes_and_errors():
+    import snickery_b200
+    rng = np.random.default_rng(0)
+    F = rng.standard_normal((7, 5)).astype(np.float32)
+    Jc = rng.standard_normal((8, 3)).astype(np.float32)
+    db = snickery_b200.UnitDatabase(F, Jc, multiepoch=2)
+    with pytest.raises(snickery_b200.EngineError, match="set_weights"):
+        db.knn(np.zeros((1, 5)), 1)
+    db.set_weights(np.ones(5), np.ones(3))
+    # empty query sets / batches
+    d, i = db.knn(np.zeros((0, 5)), 3)
+    assert d.shape == (0, 3) and i.shape == (0, 3)
+    assert db.greedy_batch([]) == []
+    paths, pc, tc, jc = db.join_viterbi_batch([], [])
+    assert paths == []
+    # k larger than the database, tiny database, joint space of 6 rows
+    d, i = db.knn(F[:2].astype(np.float64), 9)
+    assert np.all(i[:, 7:] == 7) and np.all(np.isinf(d[:, 7:])) and i[0, 0] == 0 and i[1, 0] == 1
+    q = np.concatenate([Jc[3].astype(np.float64), F[3].astype(np.float64), F[4].astype(np.float64)])[None, :]
+    d, i = db.knn(q, 2, engine.SPACE_JOINT)
+    assert i[0, 0] == 3 and d[0, 0] == 0.0
+    # greedy: the m-frame remainder is cut, one frame short of m raises like segment_axis
+    p = db.greedy_batch([F[:5].astype(np.float64), F[:2].astype(np.float64)])
+    assert [len(x) for x in p] == [2, 1]
+    with pytest.raises(ValueError):
+        db.greedy_batch([F[:1].astype(np.float64)])
+    # Viterbi: zero-length and single-frame utterances inside a batch give empty paths
+    cand = [np.array([[1, 2], [2, 3], [3, 4]]), np.zeros((0, 2), dtype=np.int64), np.array([[1, 2]]), np.array([[1, 1], [2, 2]])]
+    dist = [np.ones((3, 2)), np.zeros((0, 2)), np.ones((1, 2)), np.ones((2, 2))]
+    paths, pc, tc, jc = db.join_viterbi_batch(cand, dist)
+    assert paths[0] == [1, 2, 3] and paths[1] == [] and paths[2] == [] and paths[3] == [1, 2]
+    assert pc[0] == 3.0 and jc[0] == 0.0 and np.isinf(pc[1]) and np.isinf(pc[2])
+    # bad arguments are errors, not crashes
+    with pytest.raises(ValueError):
+        db.knn(np.zeros((2, 4)), 1)
+    with pytest.raises(snickery_b200.EngineError):
+        db.join_viterbi_batch([np.ones((2, 200), dtype=np.int64)], [np.ones((2, 200))])    # K beyond the kernel's limit
+    with pytest.raises(snickery_b200.EngineError):
+        snickery_b200.UnitDatabase(F, Jc, multiepoch=0)
+    # a database shorter than the multiepoch window has no joint rows
+    short = snickery_b200.UnitDatabase(F[:2], Jc[:3], multiepoch=4)
+    short.set_weights(np.ones(5), np.ones(3))
+    with pytest.raises(snickery_b200.EngineError, match="empty"):
+        short.knn(np.zeros((1, 3 + 4 * 5)), 1, engine.SPACE_JOINT)
+    db.close()
+    db.close()   # idempotent
