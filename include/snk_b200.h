@@ -153,6 +153,28 @@ int snk_greedy_path_scores(snk_db *db, const double *targets, int64_t T, const i
                            int64_t P, const int *twidths, int n_tstreams, const int *jwidths,
                            int n_jstreams, double *tscores, double *jscores);
 
+/* ---- row N2: MagPhase epoch concatenation -------------------------------------------------------
+ * Replaces the array part of concatenateMagPhaseEpoch_sep_files + retrieve_magphase_frag
+ * (synth_simple.py:677-747,538-652; matrix_operations.py:1-30).  The frame store holds the
+ * per-sentence full-band MagPhase files concatenated: mag / real / imag float32 [nframes, width]
+ * (width = FFTHALFLEN = 1025, const.py:20), the interpolated f0 and the voicing flag, float64 [nframes]
+ * (speech_manip.lin_interp_f0, synth_simple.py:562).  Per unit: the global index of its first
+ * frame (unit_index_within_sentence + sentence offset) and the frame bounds [lo, hi) of its
+ * sentence (fragments are zero padded outside them).                                           */
+typedef struct snk_frames snk_frames;
+int snk_frames_create(snk_frames **out, int device_id, int64_t nframes, int width, const float *mag,
+                      const float *real, const float *imag, const double *f0_interp, const double *vuv,
+                      int64_t nunits, const int64_t *unit_frame, const int64_t *sent_lo, const int64_t *sent_hi);
+int snk_frames_destroy(snk_frames *fr);
+/* path: P selected units; outputs float64 [P * multiepoch, width] (mag, real, imag) and
+ * [P * multiepoch] (fz, vuv) -- the arrays the reference hands to magphase.synthesis_from_lossless.
+ * taper_in: the in-taper np.hanning(((overlap + 1) * 2) + 1)[1:overlap + 1] (float64, [overlap]);
+ * has_fzero != 0 means the caller imposes the target f0 afterwards (no unvoiced zeroing).
+ * kernel_ms (optional): device time of the gather kernel.                                      */
+int snk_concat_magphase_epoch(snk_frames *fr, const int64_t *path, int64_t P, int multiepoch, int overlap,
+                              const double *taper_in, int has_fzero, double *mag, double *real, double *imag,
+                              double *fz, double *vuv, double *kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -532,3 +532,104 @@ def viterbi_search_numpy(synth, candidates, distances, return_cost=False):
     cols.reverse()
     path = [int(cand[t, j]) for t, j in enumerate(cols)]
     return (path, float(fin[arg])) if return_cost else path
+
+
+# --------------------------------------------------------------------------- row N2: MagPhase epoch concatenation
+def zero_pad_matrix(a, start_pad, end_pad):
+    """matrix_operations.py:3-13."""
+    if start_pad > 0:
+        a = np.vstack([np.zeros((start_pad, a.shape[1])), a])
+    if end_pad > 0:
+        a = np.vstack([a, np.zeros((end_pad, a.shape[1]))])
+    return a
+
+
+def taper_matrix(a, taper_length):
+    """matrix_operations.py:16-30 -- multiplies IN PLACE (a float32 slice stays float32)."""
+    m, n = a.shape
+    assert taper_length * 2 <= m, "taper_length (%s) too long for (padded) unit length (%s)" % (taper_length, m)
+    in_taper = np.hanning(((taper_length + 1) * 2) + 1)[1:taper_length + 1].reshape(-1, 1)
+    out_taper = np.flipud(in_taper).reshape(-1, 1)
+    a[:taper_length, :] *= in_taper
+    a[-taper_length:, :] *= out_taper
+    return a
+
+
+def lin_interp_f0(fz):
+    """speech_manip.py:222-244."""
+    import scipy.interpolate
+    y = fz.flatten()
+    voiced_ix = np.where(y > 0.0)[0]
+    voicing_flag = np.zeros(y.shape)
+    voicing_flag[voiced_ix] = 1.0
+    if voiced_ix.shape[0] == 0:
+        v_interpolated = fz
+    else:
+        interpolator = scipy.interpolate.interp1d(voiced_ix, y[voiced_ix], kind="linear", axis=0,
+                                                  bounds_error=False, fill_value="extrapolate")
+        v_interpolated = interpolator(np.arange(y.shape[0]))
+    return (v_interpolated.reshape((-1, 1)), voicing_flag.reshape((-1, 1)))
+
+
+class OracleMagPhaseStore:
+    """The per-sentence full-band files as retrieve_magphase_frag reads them (synth_simple.py:538-563):
+    sentences[name] = (mag, real, imag, f0) float32 arrays; unit u lives in train_filenames[u] at
+    unit_index_within_sentence[u].  Files are re-read (copied) on every retrieval like get_speech does."""
+
+    def __init__(self, sentences, train_filenames, unit_index_within_sentence, multiepoch=1):
+        self.sentences = sentences
+        self.train_filenames = train_filenames
+        self.unit_index_within_sentence = unit_index_within_sentence
+        self.multiepoch = multiepoch
+
+    def retrieve_magphase_frag(self, index, extra_frames=0):
+        """synth_simple.py:538-652."""
+        mag_full, real_full, imag_full, f0_full = (a.copy() for a in self.sentences[self.train_filenames[index]])
+        f0_interp, vuv = lin_interp_f0(f0_full)
+        start_index = self.unit_index_within_sentence[index]
+        end_index = start_index + self.multiepoch
+        start_pad = end_pad = 0
+        if extra_frames > 0:
+            new_start_index = start_index - extra_frames
+            new_end_index = end_index + extra_frames
+            nframes, _ = mag_full.shape
+            if new_start_index < 0:
+                start_pad = new_start_index * -1
+            if new_end_index > nframes:
+                end_pad = new_end_index - nframes
+            start_index = 0 if start_pad > 0 else new_start_index
+            end_index = nframes if end_pad > 0 else new_end_index
+        frags = [a[start_index:end_index, :] for a in (mag_full, real_full, imag_full, f0_interp, vuv)]
+        frags = [zero_pad_matrix(a, start_pad, end_pad) for a in frags]
+        assert frags[0].shape[0] == self.multiepoch + extra_frames * 2
+        if extra_frames > 0:
+            frags = [taper_matrix(a, extra_frames * 2) for a in frags]
+        return tuple(frags)
+
+    def concatenate(self, path, overlap=0, fzero=np.zeros(0)):
+        """synth_simple.py:677-729 up to (not including) magphase.synthesis_from_lossless."""
+        assert overlap % 2 == 0, "frame overlap should be even number"
+        m = self.multiepoch
+        width = next(iter(self.sentences.values()))[0].shape[1]
+        nframes = len(path) * m + overlap
+        mag, real, imag = np.zeros((nframes, width)), np.zeros((nframes, width)), np.zeros((nframes, width))
+        fz, vuv = np.zeros((nframes, 1)), np.zeros((nframes, 1))
+        write_start = 0
+        for ix in path:
+            write_end = write_start + m + overlap
+            mag_frag, real_frag, imag_frag, fz_frag, vuv_frag = self.retrieve_magphase_frag(ix, extra_frames=overlap // 2)
+            mag[write_start:write_end, :] += mag_frag
+            real[write_start:write_end, :] += real_frag
+            imag[write_start:write_end, :] += imag_frag
+            fz[write_start:write_end, :] += fz_frag
+            vuv[write_start:write_end, :] += vuv_frag
+            write_start += m
+        if overlap > 0:
+            taper = overlap // 2
+            mag, real, imag, fz, vuv = (a[taper:-taper, :] for a in (mag, real, imag, fz, vuv))
+        if fzero.size > 0:
+            fz = fzero
+        else:
+            unvoiced = np.where(vuv < 0.5)[0]
+            fz[unvoiced, :] = 0.0
+        return mag, real, imag, fz

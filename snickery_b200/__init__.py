@@ -4,7 +4,7 @@ The CUDA engine lives in csrc/ behind the C ABI of include/snk_b200.h; `engine` 
 ctypes, `kdtree` and `synth` mirror the reference's call sites.  No CPU fallback exists.
 """
 from . import engine  # noqa: F401
-from .engine import EngineError, UnitDatabase  # noqa: F401
+from .engine import EngineError, FrameStore, UnitDatabase  # noqa: F401
 from .kdtree import GpuKDTree, GpuStashableKDTree  # noqa: F401
 from .synth import Synthesiser  # noqa: F401
 

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libsnk_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["api.cu", "weights.cu", "knn_simt.cu", "knn_tc.cu", "rerank.cu", "search.cu", "join_viterbi.cu", "scores.cu"]
+SOURCES = ["api.cu", "weights.cu", "knn_simt.cu", "knn_tc.cu", "rerank.cu", "search.cu", "join_viterbi.cu", "scores.cu", "concat.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

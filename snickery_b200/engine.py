@@ -67,6 +67,9 @@ def load_library(path=None):
         "snk_join_viterbi_batch": [vp, P(i64), P(dbl), P(i64), i32, i32, C.c_uint, P(i64), P(i64), P(dbl), P(dbl), P(dbl)],
         "snk_join_viterbi_batch_dev": [vp, vp, vp, P(i64), i32, i32, C.c_uint, vp, vp, vp, vp, vp, vp],
         "snk_greedy_path_scores": [vp, P(dbl), i64, P(i64), i64, P(i32), i32, P(i32), i32, P(dbl), P(dbl)],
+        "snk_frames_create": [P(vp), i32, i64, i32, P(flt), P(flt), P(flt), P(dbl), P(dbl), i64, P(i64), P(i64), P(i64)],
+        "snk_frames_destroy": [vp],
+        "snk_concat_magphase_epoch": [vp, P(i64), i64, i32, i32, P(dbl), i32, P(dbl), P(dbl), P(dbl), P(dbl), P(dbl), P(dbl)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -81,7 +84,8 @@ EXPORTED_SYMBOLS = ["snk_last_error", "snk_version", "snk_device_count", "snk_db
                     "snk_db_profile_read", "snk_knn",
                     "snk_knn_dev", "snk_topk_merge_dev", "snk_greedy_batch", "snk_greedy_batch_dev",
                     "snk_candidate_distances", "snk_join_tiles", "snk_join_viterbi_batch",
-                    "snk_join_viterbi_batch_dev", "snk_greedy_path_scores"]
+                    "snk_join_viterbi_batch_dev", "snk_greedy_path_scores", "snk_frames_create", "snk_frames_destroy",
+                    "snk_concat_magphase_epoch"]
 
 
 def _check(rc):
@@ -260,3 +264,57 @@ class UnitDatabase:
                                                      _ptr(jw, C.c_int32), jw.size, _ptr(ts, C.c_double),
                                                      _ptr(js, C.c_double)))
         return ts, js
+
+
+class FrameStore:
+    """Full-band MagPhase frames of the voice resident in HBM (row N2): gather + cross-fade + overlap-add of
+    the selected units, as concatenateMagPhaseEpoch_sep_files does before waveform synthesis
+    (reference script/synth_simple.py:677-747)."""
+
+    def __init__(self, mag, real, imag, f0_interp, vuv, unit_frame, sent_lo, sent_hi, device=0):
+        lib = load_library()
+        mag, real, imag = (np.ascontiguousarray(a, dtype=np.float32) for a in (mag, real, imag))
+        f0 = np.ascontiguousarray(f0_interp, dtype=np.float64).ravel()
+        vv = np.ascontiguousarray(vuv, dtype=np.float64).ravel()
+        uf, lo, hi = (np.ascontiguousarray(a, dtype=np.int64).ravel() for a in (unit_frame, sent_lo, sent_hi))
+        if not (mag.shape == real.shape == imag.shape) or mag.ndim != 2 or f0.size != mag.shape[0] or vv.size != mag.shape[0]:
+            raise ValueError("mag/real/imag must be [nframes, width] with f0 / vuv of nframes entries")
+        if not (uf.size == lo.size == hi.size):
+            raise ValueError("unit_frame, sent_lo, sent_hi must have one entry per unit")
+        self.nframes, self.width = mag.shape
+        self._h = C.c_void_p()
+        _check(lib.snk_frames_create(C.byref(self._h), int(device), self.nframes, self.width, _ptr(mag, C.c_float),
+                                     _ptr(real, C.c_float), _ptr(imag, C.c_float), _ptr(f0, C.c_double), _ptr(vv, C.c_double),
+                                     uf.size, _ptr(uf, C.c_int64), _ptr(lo, C.c_int64), _ptr(hi, C.c_int64)))
+        self.last_kernel_ms = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            load_library().snk_frames_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def concatenate(self, path, multiepoch=1, overlap=0, fzero=None):
+        """Returns (mag, real, imag, fz) float64 arrays ready for magphase.synthesis_from_lossless."""
+        path = np.ascontiguousarray(path, dtype=np.int64)
+        P = path.size
+        if overlap % 2:
+            raise AssertionError("frame overlap should be even number")
+        taper = np.hanning(((overlap + 1) * 2) + 1)[1:overlap + 1].astype(np.float64) if overlap else None  # matrix_operations.py:19
+        rows = P * int(multiepoch)
+        mag, real, imag = (np.empty((rows, self.width)) for _ in range(3))
+        fz, vuv = np.empty((rows, 1)), np.empty((rows, 1))
+        ms = C.c_double()
+        _check(load_library().snk_concat_magphase_epoch(self._h, _ptr(path, C.c_int64), P, int(multiepoch), int(overlap),
+                                                        _ptr(taper, C.c_double), int(fzero is not None), _ptr(mag, C.c_double),
+                                                        _ptr(real, C.c_double), _ptr(imag, C.c_double), _ptr(fz, C.c_double),
+                                                        _ptr(vuv, C.c_double), C.byref(ms)))
+        self.last_kernel_ms = ms.value
+        if fzero is not None and np.size(fzero) > 0:
+            fz = np.asarray(fzero)               # synth_simple.py:725-726
+        return mag, real, imag, fz

@@ -609,3 +609,46 @@ def test_degenerate_shapes_and_errors():
         short.knn(np.zeros((1, 3 + 4 * 5)), 1, engine.SPACE_JOINT)
     db.close()
     db.close()   # idempotent
+
+
+# ------------------------------------------------------------------------------------ row N2: MagPhase concatenation
+def _magphase_voice(n_sent=5, width=1025, seed=3):
+    rng = np.random.default_rng(seed)
+    sentences, names, within, lens = {}, [], [], []
+    for i in range(n_sent):
+        n = int(rng.integers(12, 30))
+        f0 = np.where(rng.random((n, 1)) < 0.6, 100.0 + 50.0 * rng.random((n, 1)), 0.0).astype(np.float32)
+        sentences["utt%d" % i] = tuple(rng.standard_normal((n, width)).astype(np.float32) for _ in range(3)) + (f0,)
+        names += ["utt%d" % i] * n
+        within += list(range(n))
+        lens.append(n)
+    return sentences, names, np.array(within), lens
+
+
+@pytest.mark.parametrize("m,overlap", [(1, 0), (6, 2), (6, 6), (3, 0), (2, 2)])
+def test_magphase_epoch_concatenation(m, overlap):
+    from snickery_b200 import FrameStore
+    sentences, names, within, lens = _magphase_voice()
+    o = O.OracleMagPhaseStore(sentences, names, within, multiepoch=m)
+    order = list(sentences)
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    cat = [np.vstack([sentences[k][j] for k in order]) for j in range(3)]
+    f0i, vuv = zip(*[O.lin_interp_f0(sentences[k][3]) for k in order])
+    sent_of = np.repeat(np.arange(len(order)), lens)
+    fs = FrameStore(cat[0], cat[1], cat[2], np.vstack(f0i), np.vstack(vuv), unit_frame=offs[sent_of] + within,
+                    sent_lo=offs[sent_of], sent_hi=offs[sent_of + 1])
+    rng = np.random.default_rng(m * 10 + overlap)
+    n_units = len(names)
+    # units whose m-frame body stays inside their sentence (the reference slices past the end otherwise),
+    # including first / last units so the zero-padded edge fragments are exercised
+    ok = np.flatnonzero(within + m <= np.array(lens)[sent_of])
+    path = [int(ok[0])] + rng.choice(ok, 25).tolist() + [int(ok[-1])]
+    want = o.concatenate(path, overlap=overlap)
+    got = fs.concatenate(path, multiepoch=m, overlap=overlap)
+    for w, g in zip(want, got):
+        assert g.shape == w.shape and g.dtype == np.float64
+        assert np.array_equal(g, w)          # float64 sums of the same float32 x float64 products: bit exact
+    fzero = rng.random((len(path) * m, 1))
+    assert fs.concatenate(path, multiepoch=m, overlap=overlap, fzero=fzero)[3] is not None
+    with pytest.raises(AssertionError):
+        fs.concatenate(path, multiepoch=m, overlap=1)

@@ -164,3 +164,29 @@ def test_synthetic_generator_shapes_and_ties():
     assert 0.05 < uv.mean() < 0.7                                  # exact-tie unvoiced runs exist
     hp = syn.make_halfphone_db(n_units=500, seed=4)
     assert hp["F"].shape == (500, 184) and hp["Jc"].shape == (501, 151)
+
+
+def test_magphase_concatenation_oracle_known_answers():
+    """Row N2 restatement (synth_simple.py:538-747): a natural run of units cross-fades back to the original
+    frames (in-taper + out-taper = 1), edges are zero padded, unvoiced f0 is zeroed."""
+    rng = np.random.default_rng(1)
+    n, w, m = 40, 17, 3
+    f0 = np.where(np.arange(n)[:, None] % 10 < 6, 120.0, 0.0).astype(np.float32)
+    sent = {"a": tuple(rng.standard_normal((n, w)).astype(np.float32) for _ in range(3)) + (f0,)}
+    o = O.OracleMagPhaseStore(sent, ["a"] * n, np.arange(n), multiepoch=m)
+    path = list(range(6, 30, m))                                # natural continuation
+    for overlap in (0, 2):
+        mag, real, imag, fz = o.concatenate(path, overlap=overlap)
+        assert mag.shape == (len(path) * m, w) and fz.shape == (len(path) * m, 1)
+        np.testing.assert_allclose(mag, sent["a"][0][6:30], rtol=2e-7, atol=1e-7)
+        np.testing.assert_allclose(imag, sent["a"][2][6:30], rtol=2e-7, atol=1e-7)
+        voiced = f0[6:30, 0] > 0
+        assert np.all(fz[~voiced] == 0.0) and np.allclose(fz[voiced], 120.0)
+    t = np.hanning(((2 + 1) * 2) + 1)[1:3]
+    assert np.allclose(t + t[::-1], 1.0)                         # matrix_operations.py:25 "check sum to 1"
+    # first unit of a sentence with overlap: the leading extra frame is zero padding (then trimmed)
+    mag, _, _, _ = o.concatenate([0, 20], overlap=2)
+    frag = o.retrieve_magphase_frag(0, extra_frames=1)[0]
+    assert frag.shape == (m + 2, w) and np.all(frag[0] == 0.0) and frag.dtype == np.float64
+    with pytest.raises(AssertionError):
+        o.concatenate(path, overlap=1)
