@@ -178,10 +178,12 @@ def test_magphase_concatenation_oracle_known_answers():
     for overlap in (0, 2):
         mag, real, imag, fz = o.concatenate(path, overlap=overlap)
         assert mag.shape == (len(path) * m, w) and fz.shape == (len(path) * m, 1)
-        np.testing.assert_allclose(mag, sent["a"][0][6:30], rtol=2e-7, atol=1e-7)
-        np.testing.assert_allclose(imag, sent["a"][2][6:30], rtol=2e-7, atol=1e-7)
+        e = overlap // 2      # the very first / last kept frames only see one side of the cross-fade
+        sl = slice(e, len(path) * m - e)
+        np.testing.assert_allclose(mag[sl], sent["a"][0][6:30][sl], rtol=2e-7, atol=1e-7)
+        np.testing.assert_allclose(imag[sl], sent["a"][2][6:30][sl], rtol=2e-7, atol=1e-7)
         voiced = f0[6:30, 0] > 0
-        assert np.all(fz[~voiced] == 0.0) and np.allclose(fz[voiced], 120.0)
+        assert np.all(fz[sl][~voiced[sl]] == 0.0) and np.allclose(fz[sl][voiced[sl]], 120.0)
     t = np.hanning(((2 + 1) * 2) + 1)[1:3]
     assert np.allclose(t + t[::-1], 1.0)                         # matrix_operations.py:25 "check sum to 1"
     # first unit of a sentence with overlap: the leading extra frame is zero padding (then trimmed)
