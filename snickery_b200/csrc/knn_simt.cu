@@ -239,16 +239,11 @@ int snk_topk_scan(snk_db *db, const float *d_vals, const int *d_ids, int64_t nq,
         db->counters[2] += 1;
         return scan_dispatch(KP, d_vals, d_ids, nq, n, ld, id_base, 1, init, d_val, d_id, st);
     }
-    // two-level: partial lists, then merge them (together with the carried-in list)
-    SNK_TRY(snk_buf_reserve(&db->ws_misc, (size_t)nq * (nsplit + 1) * KP * 8));
+    // two-level: nsplit partial lists per query, then one more scan over them that also merges the
+    // carried-in list (init == false)
+    SNK_TRY(snk_buf_reserve(&db->ws_misc, (size_t)nq * nsplit * KP * 8));
     float *pv = (float *)db->ws_misc.p;
-    int *pi = (int *)(pv + (size_t)nq * (nsplit + 1) * KP);
-    // partials occupy columns [0, nsplit*KP) of rows of length (nsplit+1)*KP; the carried list is
-    // copied behind them so one merge pass sees everything.
-    const int64_t pld = (int64_t)(nsplit + 1) * KP;
-    // level 1 writes [nq, nsplit, KP] contiguous; use a temp view with stride nsplit*KP then merge
-    // with the carried list via a second scan that is not "init".
-    (void)pld;
+    int *pi = (int *)(pv + (size_t)nq * nsplit * KP);
     db->counters[2] += 2;
     SNK_TRY(scan_dispatch(KP, d_vals, d_ids, nq, n, ld, id_base, nsplit, true, pv, pi, st));
     SNK_TRY(scan_dispatch(KP, pv, pi, nq, (int64_t)nsplit * KP, (int64_t)nsplit * KP, 0, 1, init, d_val, d_id, st));
