@@ -93,50 +93,50 @@ dist_f32_kernel(space_dev sp, const float *__restrict__ Q, int ldq, int64_t nq, 
 
 // ---------------------------------------------------------------------------------
 // Warp top-KP scan: one warp keeps the KP = 32*E smallest (value, id) pairs of a row
-// segment in registers; order inside the list is arbitrary.  Ties: lower id wins.
+// segment in registers.  Ties: lower id wins.
 __device__ __forceinline__ bool pair_lt(float v1, int i1, float v2, int i2) {
     return v1 < v2 || (v1 == v2 && i1 < i2);
 }
 
+// The list is kept SORTED ascending across the warp (position p = e * 32 + lane): inserting a pair is a
+// lane-parallel shift -- every entry larger than the new pair takes its left neighbour (or the new pair at
+// the insertion point) -- a handful of shuffles instead of a reduction per insertion.
 template <int E>
 struct warp_list {
     float lv[E];
     int li[E];
-    float tv;   // current worst (largest) pair in the list, warp-uniform
+    float tv;   // current worst (largest) pair in the list = entry KP-1, warp-uniform
     int ti;
-    int tpos;   // e * 32 + lane of the worst pair
 
-    __device__ __forceinline__ void recompute() {
-        float bv = lv[0];
-        int bi = li[0], bp = threadIdx.x & 31;
-#pragma unroll
-        for (int e = 1; e < E; ++e)
-            if (pair_lt(bv, bi, lv[e], li[e])) { bv = lv[e]; bi = li[e]; bp = e * 32 + (threadIdx.x & 31); }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            const int op = __shfl_xor_sync(0xffffffffu, bp, off);
-            // ties (e.g. several still-empty slots) must resolve identically in every lane
-            if (pair_lt(bv, bi, ov, oi) || (bv == ov && bi == oi && op < bp)) { bv = ov; bi = oi; bp = op; }
-        }
-        tv = bv; ti = bi; tpos = bp;
+    __device__ __forceinline__ void refresh() {
+        tv = __shfl_sync(0xffffffffu, lv[E - 1], 31);
+        ti = __shfl_sync(0xffffffffu, li[E - 1], 31);
     }
     __device__ __forceinline__ void init() {
 #pragma unroll
         for (int e = 0; e < E; ++e) { lv[e] = INFINITY; li[e] = INT_MAX; }
-        tv = INFINITY; ti = INT_MAX; tpos = 0;
+        tv = INFINITY; ti = INT_MAX;
     }
     // cv, ci warp-uniform
     __device__ __forceinline__ void offer(float cv, int ci) {
-        if (pair_lt(cv, ci, tv, ti)) {
-            if ((threadIdx.x & 31) == (tpos & 31)) {
+        if (!pair_lt(cv, ci, tv, ti)) return;
+        const int lane = threadIdx.x & 31;
+        float carry_v = -INFINITY;   // entry to the left of this row's lane 0 (last entry of the previous row)
+        int carry_i = INT_MIN;
 #pragma unroll
-                for (int e = 0; e < E; ++e)
-                    if (e == (tpos >> 5)) { lv[e] = cv; li[e] = ci; }
+        for (int e = 0; e < E; ++e) {
+            float left_v = __shfl_up_sync(0xffffffffu, lv[e], 1);
+            int left_i = __shfl_up_sync(0xffffffffu, li[e], 1);
+            if (lane == 0) { left_v = carry_v; left_i = carry_i; }
+            carry_v = __shfl_sync(0xffffffffu, lv[e], 31);      // before this row changes
+            carry_i = __shfl_sync(0xffffffffu, li[e], 31);
+            if (pair_lt(cv, ci, lv[e], li[e])) {                 // this entry moves right
+                const bool left_moves = pair_lt(cv, ci, left_v, left_i);
+                lv[e] = left_moves ? left_v : cv;
+                li[e] = left_moves ? left_i : ci;
             }
-            recompute();
         }
+        refresh();
     }
     // per-lane candidate; all lanes must call
     __device__ __forceinline__ void offer_lanes(float v, int id) {
@@ -174,7 +174,7 @@ topk_scan_kernel(const float *__restrict__ vals, const int *__restrict__ ids, in
             const int id = oi[e * 32 + lane];
             L.li[e] = id < 0 ? INT_MAX : id;
         }
-        L.recompute();
+        L.refresh();   // lists written by this kernel are sorted ascending
     }
     const float *row = vals + q * ld;
     const int *irow = ids ? ids + q * ld : nullptr;
