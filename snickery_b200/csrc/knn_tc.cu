@@ -860,8 +860,10 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         if (nqt > db->sm_count) nchunks = 1;
         const int nlists = nchunks * EPI_SPLIT;
         // neighbours cluster on a few consecutive rows (trajectories), so one list may take most of the ~8k
-        // expected rows: size every list for that
-        const int cap = (int)snk_round_up(std::min<int64_t>(1024, std::max<int64_t>(128, (int64_t)10 * k)), 32);
+        // expected rows and an unsampled tile may hide a whole cluster: size every list for 20k rows (measured:
+        // 10k overflowed for 0.17 % of the queries, 20k for 0.001 %)
+        const int cap = getenv("SNK_TC_EMIT_CAP") ? atoi(getenv("SNK_TC_EMIT_CAP")) :
+                        (int)snk_round_up(std::min<int64_t>(2048, std::max<int64_t>(256, (int64_t)20 * k)), 32);
         const size_t nent = (size_t)nq_pad * nlists * cap;
         SNK_TRY(snk_buf_reserve(&db->ws_tc, nent * 8));
         p.bufv = (float *)db->ws_tc.p;
