@@ -171,8 +171,8 @@ __device__ __forceinline__ float min3(float a, float b, float c) {
 constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 // ---------------------------------------------------------------- static schedules
-// For the two shapes the reference ships (config/*.cfg: 151-dim join + 61-dim target frames with
-// multiepoch 6; 184-dim half-phone targets) the per-tile load / K-block sequence is a compile-time
+// For the shapes the reference ships (config/*.cfg: 151-dim join + 61-dim target frames with
+// multiepoch 6, 4, 3 or 1; 184-dim half-phone targets) the per-tile load / K-block sequence is a compile-time
 // constant, so the issue thread's descriptors are "uniform base + immediate" and it sustains one
 // UTCHMMA per tensor-pipe slot.  Every other shape runs the table-driven path (SCHED 0).
 //   NS   : K-blocks of the join part (one plain tile load each), KSL: UMMA_K steps of its last block
@@ -183,8 +183,13 @@ constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >
 // Static schedules rely on the squared norms embedded in the operands (weights.cu), so their epilogue
 // needs no norm staging.
 template <int SCHED> struct sched_traits { static constexpr int NS = 0, KSL = 0, TB = 0, KTL = 0, M = 1, GR = 1; };
-template <> struct sched_traits<1> { static constexpr int NS = 3, KSL = 2, TB = 1, KTL = 4, M = 6, GR = 2; };   // joint 151 | 6 x 61
-template <> struct sched_traits<2> { static constexpr int NS = 0, KSL = 0, TB = 3, KTL = 4, M = 1, GR = 2; };   // target 184
+template <int M_> struct joint_traits { static constexpr int NS = 3, KSL = 2, TB = 1, KTL = 4, M = M_, GR = 2; };   // joint 151 | M x 61
+template <> struct sched_traits<2> { static constexpr int NS = 0, KSL = 0, TB = 3, KTL = 4, M = 1, GR = 2; };      // target 184
+// SCHED 10 + m: the joint space at the multiepoch values the reference's configs use (config/*.cfg: 6, 1, 4, 3)
+template <> struct sched_traits<11> : joint_traits<1> {};
+template <> struct sched_traits<13> : joint_traits<3> {};
+template <> struct sched_traits<14> : joint_traits<4> {};
+template <> struct sched_traits<16> : joint_traits<6> {};
 template <int SCHED> struct sched_layout {
     using S = sched_traits<SCHED>;
     static constexpr int GBYTES = S::M > 1 ? SLOT_BYTES : TILE_BYTES;
@@ -661,17 +666,20 @@ int build_space(snk_db *db, int space, tc_space_host *h) {
     // statically scheduled variants (sched_traits): shapes of the shipped configs
     h->sched = 0;
     if (!getenv("SNK_TC_NOSCHED") && h->embed) {
-        if (space == SNK_SPACE_JOINT && slab && m == 6 && tblocks == 1 && Dt + 3 > 48 && db->Djq + 3 > 144 &&
-            db->Djq + 3 <= 160)
-            h->sched = 1;
+        if (space == SNK_SPACE_JOINT && (slab || m == 1) && (m == 1 || m == 3 || m == 4 || m == 6) && tblocks == 1 &&
+            Dt + 3 > 48 && db->Djq + 3 > 144 && db->Djq + 3 <= 160)
+            h->sched = 10 + m;
         else if (space == SNK_SPACE_TARGET && tblocks == 3 && Dt + 3 > 176)
             h->sched = 2;
     }
     const size_t budget = 227 * 1024;
-    if (h->sched == 1) {
-        h->b_bytes = sched_layout<1>::B_BYTES; h->stages = sched_layout<1>::NSLOT;
-    } else if (h->sched == 2) {
-        h->b_bytes = sched_layout<2>::B_BYTES; h->stages = sched_layout<2>::NSLOT;
+    switch (h->sched) {
+    case 2: h->b_bytes = sched_layout<2>::B_BYTES; h->stages = sched_layout<2>::NSLOT; break;
+    case 11: h->b_bytes = sched_layout<11>::B_BYTES; h->stages = sched_layout<11>::NSLOT; break;
+    case 13: h->b_bytes = sched_layout<13>::B_BYTES; h->stages = sched_layout<13>::NSLOT; break;
+    case 14: h->b_bytes = sched_layout<14>::B_BYTES; h->stages = sched_layout<14>::NSLOT; break;
+    case 16: h->b_bytes = sched_layout<16>::B_BYTES; h->stages = sched_layout<16>::NSLOT; break;
+    default: break;
     }
     if (h->sched != 0 && (size_t)h->nkb * TILE_BYTES + h->b_bytes + aux_bytes(h->sched) > budget) h->sched = 0;
     if (h->sched == 0) {
@@ -691,8 +699,11 @@ typedef void (*tc_kernel_fn)(const CUtensorMap, const CUtensorMap, const CUtenso
 template <int MODE, int LSZ>
 tc_kernel_fn pick_sched(int sched) {
     switch (sched) {
-    case 1: return knn_tc_kernel<MODE, LSZ, 1>;
     case 2: return knn_tc_kernel<MODE, LSZ, 2>;
+    case 11: return knn_tc_kernel<MODE, LSZ, 11>;
+    case 13: return knn_tc_kernel<MODE, LSZ, 13>;
+    case 14: return knn_tc_kernel<MODE, LSZ, 14>;
+    case 16: return knn_tc_kernel<MODE, LSZ, 16>;
     default: return knn_tc_kernel<MODE, LSZ, 0>;
     }
 }
@@ -724,7 +735,7 @@ int snk_tc_prepare(snk_db *db) {
         SNK_TRY(build_space(db, sp, &s->sp[sp]));
         if (s->sp[sp].ok) s->smem[sp] = s->sp[sp].smem;
     }
-    for (int sched = 0; sched <= 2; ++sched)
+    for (int sched : {0, 2, 11, 13, 14, 16})
         for (int v = 0; v < 4; ++v)
             SNK_CUDA(cudaFuncSetAttribute((const void *)pick_kernel(v == 2 ? MODE_STORE : (v == 3 ? MODE_EMIT : MODE_LIST),
                                                                     v == 1 ? 8 : 4, sched),

@@ -176,7 +176,7 @@ def test_greedy_ragged_batch_and_multiepoch1(golden_epoch, eng):
 
 
 @pytest.mark.parametrize("eng", ENGINES)
-@pytest.mark.parametrize("m", [1, 3])
+@pytest.mark.parametrize("m", [1, 3, 4])
 def test_greedy_halfphone_epoch_join_layout(golden_epoch, eng, m):
     """Epoch voices written by train_halfphone.py store two-frame join windows; greedy search splits them
     into prev / current halves (synth_halfphone.py:552-553,580-581,693-695)."""
