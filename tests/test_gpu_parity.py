@@ -652,3 +652,56 @@ def test_magphase_epoch_concatenation(m, overlap):
     assert fs.concatenate(path, multiepoch=m, overlap=overlap, fzero=fzero)[3] is not None
     with pytest.raises(AssertionError):
         fs.concatenate(path, multiepoch=m, overlap=1)
+
+
+# ------------------------------------------------------------------------------------ shape fuzz: every kernel path
+SHAPES = [
+    # (Dt, Dj, m, N, k)   -- chosen to hit: embedded norms on/off, frame slab with 1-2 column blocks, plain multi-load
+    (61, 151, 6, 3000, 1),     # static schedule 16
+    (61, 151, 2, 2000, 3),     # table-driven, slab, embedded norms
+    (64, 151, 3, 2500, 1),     # Dt = 64: no spare columns -> norm staging path
+    (61, 64, 4, 2200, 2),      # Djq = 64: join part without spare columns -> norm staging path
+    (70, 30, 2, 1800, 1),      # two column blocks per frame, slab serves both
+    (130, 20, 3, 1500, 4),     # three column blocks per frame: 2 + 9 K-blocks > 10 -> SIMT engine takes over
+    (20, 10, 9, 4000, 1),      # m = 9: largest window a slab serves
+    (20, 10, 10, 4000, 1),     # m = 10: per-frame loads, table-driven
+    (184, 8, 1, 5000, 7),      # static schedule 2 (target space queried below as well), store mode (tiny database)
+    (33, 200, 1, 2600, 1),     # wide join part: four K-blocks
+    (5, 3, 1, 300, 1),         # tiny everything: single partial tile
+    (61, 151, 6, 129, 1),      # database of one tile + one row
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_shape_fuzz_tensor_core_vs_float64(shape):
+    """Random databases of awkward shapes: the tensor-core engine (whatever path it picks) and the SIMT engine
+    must both return the float64 brute-force answer in the joint and in the target space."""
+    import snickery_b200
+    Dt, Dj, m, N, k = shape
+    rng = np.random.default_rng(abs(hash(shape)) % (2 ** 31))
+    walk = np.cumsum(rng.standard_normal((N + 1, Dt + Dj)) * 0.3, axis=0)     # trajectories: neighbours cluster
+    walk -= walk.mean(0)
+    F = walk[:N, :Dt].astype(np.float32)
+    Jc = walk[:, Dt:].astype(np.float32)
+    wt = rng.uniform(0.2, 1.0, Dt)
+    wj = rng.uniform(0.2, 1.0, Dj)
+    db = snickery_b200.UnitDatabase(F, Jc, multiepoch=m)
+    db.set_weights(wt, wj)
+    Fw = F.astype(np.float64) * wt
+    Jw = Jc.astype(np.float64) * wj
+    Np = N - m + 1
+    joint = np.hstack([Jw[:Np]] + [Fw[j:Np + j] for j in range(m)])
+    nq = 70
+    rows = rng.integers(0, Np, nq)
+    qj = joint[rows] + 0.05 * rng.standard_normal((nq, joint.shape[1]))
+    qj[:5] = joint[rows[:5]]                                                # exact hits: distance 0
+    qt = Fw[rows] + 0.05 * rng.standard_normal((nq, Dt))
+    for space, data, q in ((engine.SPACE_JOINT, joint, qj), (engine.SPACE_TARGET, Fw, qt)):
+        kk = min(k, data.shape[0])
+        rd, ri = O.brute_force_knn(data, q, kk)
+        for eng in (engine.ENGINE_AUTO, engine.ENGINE_SIMT):
+            db.set_engine(eng)
+            d, i = db.knn(q, kk, space)
+            assert_knn_matches(d, i, rd, ri)
+    assert np.all(db.knn(qj[:5], 1, engine.SPACE_JOINT)[0] == 0.0)
+    db.close()
