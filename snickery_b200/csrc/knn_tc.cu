@@ -34,11 +34,14 @@ constexpr int MAXKB = 10;      // resident query K-blocks
 constexpr int MAXLOAD = 10;    // TMA loads per database tile
 constexpr int MAXSUB = 16;     // MMA K-blocks per database tile
 constexpr int SLAB_EXTRA = 8;  // extra rows of a frame slab: serves window offsets 0..8
-constexpr int EPI_SPLIT = 2;   // epilogue warps per TMEM lane quarter: each takes BN / EPI_SPLIT columns of a tile
+// epilogue warps per TMEM lane quarter (each takes BN / split columns of a tile): 2 by default, 4 for the
+// half-phone target shape (K = 192: a tile is only 768 tensor-pipe cycles, the epilogue is the longer stage and
+// more warps hide its latency; measured 22.7 -> 20.1 ms on the k = 50 pipeline).  The one-frame joint shape
+// (multiepoch 1) does not gain: it is bound by the 64 KB per tile it pulls from L2.
+__host__ __device__ constexpr int epi_split_of(int sched) { return sched == 2 ? 4 : 2; }
 constexpr int TILE_BYTES = BM * BK * 2;                    // 16 KiB query K-block
 constexpr int SLOT_BYTES = (BN + SLAB_EXTRA) * BK * 2;     // 17 KiB ring slot (plain tile or frame slab)
-constexpr int NUM_EPI_THREADS = 128 * EPI_SPLIT;
-constexpr int NUM_THREADS = 64 + NUM_EPI_THREADS;
+__host__ __device__ constexpr int num_threads_of(int sched) { return 64 + 128 * epi_split_of(sched); }
 constexpr uint32_t TMEM_COLS = 256;       // two 128-column fp32 accumulators
 
 // One TMA load per ring slot; it feeds nsub MMA K-blocks.  A frame slab (BN + 8 rows of G16) feeds the
@@ -58,14 +61,14 @@ struct tc_params {
     int nchunks;
     int64_t nq;
     const float *nrm;       // [rows] squared norms of the fp16 rows
-    float *oval;            // fused : [nq_pad, nchunks * EPI_SPLIT, LSZ] keys (ascending)
+    float *oval;            // fused : [nq_pad, nchunks * split, LSZ] keys (ascending)
     int *oid;               //         row ids
     float *odist;           // store : [nq, ldo] keys of the scanned tiles, compacted (tile_stride > 1 = sample)
     int64_t ldo;
     int tile_stride;        // scan every tile_stride-th tile of a chunk (1 = all)
     // emit mode: every row whose key is <= thr[q] is appended to the (query, chunk, half) buffer
     const float *thr;       // [nq]
-    float *bufv;            // [nq_pad, nchunks * EPI_SPLIT, cap]
+    float *bufv;            // [nq_pad, nchunks * split, cap]
     int *bufi;
     int cap;
     float *tau;             // [nq] preset to thr; a buffer overflow writes -inf (certificate must fail)
@@ -203,7 +206,7 @@ template <int SCHED> struct sched_layout {
 
 // ---------------------------------------------------------------- kernel
 template <int MODE, int LSZ, int SCHED>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads_of(SCHED), 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapS,
               const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapGslab,
               const tc_params p) {
@@ -225,6 +228,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     uint4 *sub_s = reinterpret_cast<uint4 *>(g_after + 24 + 2 * BN * 4);   // [MAXSUB] {a start addr >> 4, b byte offset, ksteps, -}
     (void)STAGES;
 
+    constexpr int EPI_SPLIT = epi_split_of(SCHED);
+    constexpr int NUM_EPI_THREADS = 128 * EPI_SPLIT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x / p.nchunks, chunk = blockIdx.x % p.nchunks;
     const int64_t row_beg = p.row_lo + (int64_t)chunk * p.chunk_rows;
@@ -794,14 +799,14 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         if (nqt > db->sm_count) nchunks = 1;
         p.row_lo = 0; p.row_hi = sp.rows; p.nchunks = nchunks;
         p.chunk_rows = snk_cdiv(row_tiles, nchunks) * BN;
-        const int nlists = nchunks * EPI_SPLIT;
+        const int nlists = nchunks * epi_split_of(h.sched);
         const size_t nlist = (size_t)nq_pad * nlists * lsz;
         SNK_TRY(snk_buf_reserve(&db->ws_tc, nlist * 8));
         p.oval = (float *)db->ws_tc.p;
         p.oid = (int *)(p.oval + nlist);
         {
             snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)sp.rows * sp.D, st);
-            pick_kernel(MODE_LIST, lsz, h.sched)<<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
+            pick_kernel(MODE_LIST, lsz, h.sched)<<<nqt * nchunks, num_threads_of(h.sched), smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
         }
         SNK_CUDA(cudaGetLastError());
         if (lists && snk_merge_rerank_fits(nlists, lsz)) {   // merge + tau happen inside the re-rank kernel
@@ -841,7 +846,7 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
             p.chunk_rows = snk_cdiv(tiles, nchunks) * BN * stride;
             {
                 snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)tiles * BN * sp.D, st);
-                pick_kernel(MODE_STORE, 4, h.sched)<<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
+                pick_kernel(MODE_STORE, 4, h.sched)<<<nqt * nchunks, num_threads_of(h.sched), smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
             }
             SNK_CUDA(cudaGetLastError());
             db->counters[2] += 1;
@@ -869,7 +874,7 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         SNK_CUDA(cudaGetLastError());
         int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(db->sm_count / std::max(nqt, 1), row_tiles));
         if (nqt > db->sm_count) nchunks = 1;
-        const int nlists = nchunks * EPI_SPLIT;
+        const int nlists = nchunks * epi_split_of(h.sched);
         // neighbours cluster on a few consecutive rows (trajectories), so one list may take most of the ~8k
         // expected rows and an unsampled tile may hide a whole cluster: size every list for 20k rows (measured:
         // 10k overflowed for 0.17 % of the queries, 20k for 0.001 %)
@@ -885,7 +890,7 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         SNK_CUDA(cudaMemsetAsync(p.bufi, 0xFF, nent * 4, st));     // unused slots read as id -1
         {
             snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)sp.rows * sp.D, st);
-            pick_kernel(MODE_EMIT, 4, h.sched)<<<nqt * nchunks, NUM_THREADS, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
+            pick_kernel(MODE_EMIT, 4, h.sched)<<<nqt * nchunks, num_threads_of(h.sched), smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
         }
         SNK_CUDA(cudaGetLastError());
         db->counters[2] += 3;
