@@ -29,7 +29,7 @@ namespace {
 constexpr int BM = 128;        // queries per tile (UMMA M)
 constexpr int BN = 128;        // database rows per tile (UMMA N)
 constexpr int BK = 64;         // fp16 elements per K-block = one 128-byte swizzle row
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 8;
 constexpr int MAXKB = 10;      // resident query K-blocks
 constexpr int MAXLOAD = 10;    // TMA loads per database tile
 constexpr int MAXSUB = 16;     // MMA K-blocks per database tile
@@ -53,6 +53,7 @@ struct tc_params {
     int nkb;                // resident query K-blocks
     int nload, nsub, stages;
     int embed;              // squared norms ride in the operands: key = -2 * accumulator
+    int cluster;            // CTAs per cluster sharing every database tile by TMA multicast (1 or 2)
     int b_bytes;            // bytes of the database-tile ring
     tc_load load[MAXLOAD];  // map: 0 join-context tile (S16), 1 frame tile (G16), 2 frame slab (G16, BN+8 rows)
     tc_sub sub[MAXSUB];
@@ -74,6 +75,9 @@ struct tc_params {
     float *tau;             // [nq] preset to thr; a buffer overflow writes -inf (certificate must fail)
 };
 constexpr int MODE_LIST = 0, MODE_STORE = 1, MODE_EMIT = 2;
+// half-box tensor maps of the multicast path: each CTA of a pair fetches half of every database tile
+struct tc_maps_mc { CUtensorMap S_h, G_h, Gslab72; };
+constexpr int MC_ROWS0 = 72;   // rows of a frame slab fetched by rank 0 (9 swizzle atoms); rank 1 takes the other 64
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,6 +114,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
 }
+// the same box lands at the same shared-memory offset (and signals the same barrier offset) in every CTA of mask
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -134,6 +154,11 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// ... and on the same barrier offset of every CTA of mask (a slot fed by multicast is free only when all are done)
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -185,9 +210,14 @@ constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >
 //          join-part loads keep one slot each: they are short, so their slot is free long before reuse
 // Static schedules rely on the squared norms embedded in the operands (weights.cu), so their epilogue
 // needs no norm staging.
-template <int SCHED> struct sched_traits { static constexpr int NS = 0, KSL = 0, TB = 0, KTL = 0, M = 1, GR = 1; };
-template <int M_> struct joint_traits { static constexpr int NS = 3, KSL = 2, TB = 1, KTL = 4, M = M_, GR = 2; };   // joint 151 | M x 61
-template <> struct sched_traits<2> { static constexpr int NS = 0, KSL = 0, TB = 3, KTL = 4, M = 1, GR = 2; };      // target 184
+//   SR   : slots per join-part load.  One is enough when a tile keeps the tensor pipe busy for longer than a load
+//          takes to arrive (multiepoch 4, 6); shorter tiles (multiepoch 1, 3) need the second slot, and have the
+//          shared memory for it because their query tile is smaller
+template <int SCHED> struct sched_traits { static constexpr int NS = 0, KSL = 0, TB = 0, KTL = 0, M = 1, GR = 1, SR = 1; };
+template <int M_> struct joint_traits {   // joint 151 | M x 61
+    static constexpr int NS = 3, KSL = 2, TB = 1, KTL = 4, M = M_, GR = 2, SR = M_ <= 3 ? 2 : 1;
+};
+template <> struct sched_traits<2> { static constexpr int NS = 0, KSL = 0, TB = 3, KTL = 4, M = 1, GR = 2, SR = 1; };   // target 184
 // SCHED 10 + m: the joint space at the multiepoch values the reference's configs use (config/*.cfg: 6, 1, 4, 3)
 template <> struct sched_traits<11> : joint_traits<1> {};
 template <> struct sched_traits<13> : joint_traits<3> {};
@@ -196,12 +226,14 @@ template <> struct sched_traits<16> : joint_traits<6> {};
 template <int SCHED> struct sched_layout {
     using S = sched_traits<SCHED>;
     static constexpr int GBYTES = S::M > 1 ? SLOT_BYTES : TILE_BYTES;
-    static constexpr int NSLOT = S::NS + S::TB * S::GR;
-    static constexpr int B_BYTES = S::NS * TILE_BYTES + S::TB * S::GR * GBYTES;
-    __host__ __device__ static constexpr int s_slot(int l) { return l; }
-    __host__ __device__ static constexpr uint32_t s_off(int l) { return (uint32_t)l * TILE_BYTES; }
-    __host__ __device__ static constexpr int g_slot(int b, int r) { return S::NS + b * S::GR + r; }
-    __host__ __device__ static constexpr uint32_t g_off(int b, int r) { return (uint32_t)S::NS * TILE_BYTES + (uint32_t)(b * S::GR + r) * GBYTES; }
+    static constexpr int NSLOT = S::NS * S::SR + S::TB * S::GR;
+    static constexpr int B_BYTES = S::NS * S::SR * TILE_BYTES + S::TB * S::GR * GBYTES;
+    __host__ __device__ static constexpr int s_slot(int l, int r) { return l * S::SR + r; }
+    __host__ __device__ static constexpr uint32_t s_off(int l, int r) { return (uint32_t)(l * S::SR + r) * TILE_BYTES; }
+    __host__ __device__ static constexpr int g_slot(int b, int r) { return S::NS * S::SR + b * S::GR + r; }
+    __host__ __device__ static constexpr uint32_t g_off(int b, int r) {
+        return (uint32_t)(S::NS * S::SR) * TILE_BYTES + (uint32_t)(b * S::GR + r) * GBYTES;
+    }
 };
 
 // ---------------------------------------------------------------- kernel
@@ -209,7 +241,7 @@ template <int MODE, int LSZ, int SCHED>
 __global__ void __launch_bounds__(num_threads_of(SCHED), 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapS,
               const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapGslab,
-              const tc_params p) {
+              const __grid_constant__ tc_maps_mc mc, const tc_params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t sbase = smem_u32(smem_raw);                        // SWIZZLE_128B tiles need 1024 B alignment
     if (sbase & 1023u) __trap();
@@ -231,7 +263,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     constexpr int EPI_SPLIT = epi_split_of(SCHED);
     constexpr int NUM_EPI_THREADS = 128 * EPI_SPLIT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x / p.nchunks, chunk = blockIdx.x % p.nchunks;
+    // a cluster (pair) scans one chunk with two query tiles: every database tile is read from L2 once for both
+    const int crank = p.cluster > 1 ? (int)cluster_ctarank() : 0;
+    const int cid = blockIdx.x / p.cluster;
+    const int qt = (cid / p.nchunks) * p.cluster + crank, chunk = cid % p.nchunks;
+    const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
     const int64_t row_beg = p.row_lo + (int64_t)chunk * p.chunk_rows;
     const int64_t row_end = min(p.row_hi, row_beg + p.chunk_rows);
     const int64_t tstep = (int64_t)BN * p.tile_stride;
@@ -240,7 +276,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, (uint32_t)p.cluster);   // one commit per CTA sharing the slot
         }
         mbar_init(bar_a, 1);
         for (int a = 0; a < 2; ++a) {
@@ -252,6 +288,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     if (warp == 1) tmem_alloc(s_tmem_ptr, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();     // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_g;
 
@@ -272,16 +309,21 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             using L = sched_layout<SCHED>;
             for (int t = 0; t < ntiles; ++t) {
                 const int r0 = (int)(row_beg + (int64_t)t * tstep);
-                const uint32_t ph_s = (uint32_t)t & 1u;
+                const int sr = t % S::SR;
+                const uint32_t ph_s = (uint32_t)(t / S::SR) & 1u;
                 const int gr = t % S::GR;
                 const uint32_t ph_g = (uint32_t)(t / S::GR) & 1u;
 #pragma unroll
                 for (int l = 0; l < S::NS; ++l) {
-                    const uint32_t bar = 8 * L::s_slot(l);
+                    const uint32_t bar = 8 * (uint32_t)L::s_slot(l, sr);
                     mbar_wait(bar_empty + bar, ph_s ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(bar_full + bar, TILE_BYTES);
-                        tma_load_2d(sB + L::s_off(l), &mapS, l * BK, r0, bar_full + bar);
+                        if (p.cluster > 1)   // this CTA's half of the rows, delivered to both CTAs
+                            tma_load_2d_mc(sB + L::s_off(l, sr) + crank * (TILE_BYTES / 2), &mc.S_h, l * BK, r0 + crank * (BN / 2),
+                                           bar_full + bar, cmask);
+                        else
+                            tma_load_2d(sB + L::s_off(l, sr), &mapS, l * BK, r0, bar_full + bar);
                     }
                     __syncwarp();
                 }
@@ -291,7 +333,20 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     mbar_wait(bar_empty + bar, ph_g ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(bar_full + bar, L::GBYTES);
-                        tma_load_2d(sB + L::g_off(b, gr), S::M > 1 ? &mapGslab : &mapG, b * BK, r0, bar_full + bar);
+                        if (p.cluster > 1) {
+                            if (S::M > 1) {   // slab of BN + 8 rows: 72 rows (9 swizzle atoms) from rank 0, 64 from rank 1
+                                if (crank == 0)
+                                    tma_load_2d_mc(sB + L::g_off(b, gr), &mc.Gslab72, b * BK, r0, bar_full + bar, cmask);
+                                else
+                                    tma_load_2d_mc(sB + L::g_off(b, gr) + MC_ROWS0 * BK * 2, &mc.G_h, b * BK, r0 + MC_ROWS0,
+                                                   bar_full + bar, cmask);
+                            } else {
+                                tma_load_2d_mc(sB + L::g_off(b, gr) + crank * (TILE_BYTES / 2), &mc.G_h, b * BK,
+                                               r0 + crank * (BN / 2), bar_full + bar, cmask);
+                            }
+                        } else {
+                            tma_load_2d(sB + L::g_off(b, gr), S::M > 1 ? &mapGslab : &mapG, b * BK, r0, bar_full + bar);
+                        }
                     }
                     __syncwarp();
                 }
@@ -337,19 +392,21 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
-                    const uint32_t ph_s = (uint32_t)t & 1u;
+                    const int sr = t % S::SR;
+                    const uint32_t ph_s = (uint32_t)(t / S::SR) & 1u;
                     const int gr = t % S::GR;
                     const uint32_t ph_g = (uint32_t)(t / S::GR) & 1u;
 #pragma unroll
                     for (int l = 0; l < S::NS; ++l) {
-                        mbar_wait(bar_full + 8 * L::s_slot(l), ph_s);
+                        mbar_wait(bar_full + 8 * (uint32_t)L::s_slot(l, sr), ph_s);
                         tc_fence_after();
-                        const uint32_t al = a0 + l * (TILE_BYTES >> 4), bl = b0 + (L::s_off(l) >> 4);
+                        const uint32_t al = a0 + l * (TILE_BYTES >> 4), bl = b0 + (L::s_off(l, sr) >> 4);
 #pragma unroll
                         for (int ks = 0; ks < (l == S::NS - 1 ? S::KSL : 4); ++ks)
                             umma_f16(d_tmem, DESC_HI | (uint64_t)(al + 2 * ks), DESC_HI | (uint64_t)(bl + 2 * ks), IDESC,
                                      (l | ks) != 0 ? 1u : 0u);
-                        umma_commit(bar_empty + 8 * L::s_slot(l));
+                        if (p.cluster > 1) umma_commit_mc(bar_empty + 8 * (uint32_t)L::s_slot(l, sr), cmask);
+                        else umma_commit(bar_empty + 8 * (uint32_t)L::s_slot(l, sr));
                     }
 #pragma unroll
                     for (int b = 0; b < S::TB; ++b) {
@@ -365,7 +422,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                                 umma_f16(d_tmem, DESC_HI | (uint64_t)(al + 2 * ks), DESC_HI | (uint64_t)(bl + 8 * j + 2 * ks),
                                          IDESC, (S::NS + b + j + ks) != 0 ? 1u : 0u);
                         }
-                        umma_commit(bar_empty + bar);
+                        if (p.cluster > 1) umma_commit_mc(bar_empty + bar, cmask);
+                        else umma_commit(bar_empty + bar);
                     }
                     umma_commit(bar_tfull + 8 * acc);
                 }
@@ -534,6 +592,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();     // the peer may still multicast into this CTA's ring / arrive on its barriers
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -588,6 +647,7 @@ struct tc_space_host {
 struct tc_state {
     encode_fn encode = nullptr;
     CUtensorMap mapS, mapG, mapGslab;
+    tc_maps_mc mc;
     tc_space_host sp[2];
     size_t smem[2] = {0, 0};
 };
@@ -699,7 +759,8 @@ int build_space(snk_db *db, int space, tc_space_host *h) {
     return 0;
 }
 
-typedef void (*tc_kernel_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const tc_params);
+typedef void (*tc_kernel_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const tc_maps_mc,
+                             const tc_params);
 
 template <int MODE, int LSZ>
 tc_kernel_fn pick_sched(int sched) {
@@ -716,6 +777,44 @@ tc_kernel_fn pick_kernel(int mode, int lsz, int sched) {
     if (mode == MODE_STORE) return pick_sched<MODE_STORE, 4>(sched);
     if (mode == MODE_EMIT) return pick_sched<MODE_EMIT, 4>(sched);
     return lsz == 4 ? pick_sched<MODE_LIST, 4>(sched) : pick_sched<MODE_LIST, 8>(sched);
+}
+
+// launches with a thread-block cluster of p.cluster CTAs (consecutive blockIdx.x) when the multicast path is on
+int launch_tc(tc_kernel_fn fn, int grid, int threads, size_t smem, cudaStream_t st, const CUtensorMap &mapQ,
+              const tc_state *s, const tc_params &p) {
+    if (p.cluster <= 1) {
+        fn<<<grid, threads, smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, s->mc, p);
+        return 0;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)p.cluster;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    void *args[] = {(void *)&mapQ, (void *)&s->mapS, (void *)&s->mapG, (void *)&s->mapGslab, (void *)&s->mc, (void *)&p};
+    SNK_CUDA(cudaLaunchKernelExC(&cfg, (const void *)fn, args));
+    return 0;
+}
+
+// work split of one launch: query tiles (padded to the cluster size) x database chunks
+struct tc_split { int cluster, nqt_pad, nchunks; };
+tc_split make_split(const snk_db *db, const tc_space_host &h, int nqt, int64_t tiles) {
+    tc_split sp;
+    // Pairs of CTAs sharing every database tile by TMA multicast halve the L2 reads.  Measured neutral on B200
+    // (m = 6: 1418 vs 1394 TFLOP/s, m = 4: 1278 vs 1329): these kernels are not L2-bound, so it is opt-in.
+    sp.cluster = (h.sched != 0 && nqt >= 2 && getenv("SNK_TC_CLUSTER")) ? 2 : 1;
+    sp.nqt_pad = (int)snk_round_up(nqt, sp.cluster);
+    sp.nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(db->sm_count / std::max(sp.nqt_pad, 1), tiles));
+    if (sp.nqt_pad > db->sm_count) sp.nchunks = 1;
+    return sp;
 }
 
 }  // namespace
@@ -736,6 +835,10 @@ int snk_tc_prepare(snk_db *db) {
     SNK_TRY(make_map(s->encode, &s->mapG, db->G16, (uint64_t)db->ldG16, (uint64_t)db->N, (uint64_t)db->ldG16, BN));
     SNK_TRY(make_map(s->encode, &s->mapGslab, db->G16, (uint64_t)db->ldG16, (uint64_t)db->N, (uint64_t)db->ldG16,
                      BN + SLAB_EXTRA));
+    // half boxes of the multicast (cluster of two) path
+    SNK_TRY(make_map(s->encode, &s->mc.S_h, db->S16, (uint64_t)db->ldS16, (uint64_t)db->N + 1, (uint64_t)db->ldS16, BN / 2));
+    SNK_TRY(make_map(s->encode, &s->mc.G_h, db->G16, (uint64_t)db->ldG16, (uint64_t)db->N, (uint64_t)db->ldG16, BN / 2));
+    SNK_TRY(make_map(s->encode, &s->mc.Gslab72, db->G16, (uint64_t)db->ldG16, (uint64_t)db->N, (uint64_t)db->ldG16, MC_ROWS0));
     for (int sp = 0; sp < 2; ++sp) {
         SNK_TRY(build_space(db, sp, &s->sp[sp]));
         if (s->sp[sp].ok) s->smem[sp] = s->sp[sp].smem;
@@ -775,14 +878,14 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
     const tc_space_host &h = s->sp[space];
     SNK_CHECK(h.ok, "tensor-core engine does not support this search space");
     const snk_space sp = snk_make_space(db, space);
-    const int64_t nq_pad = snk_round_up(nq, BM);
-    const int nqt = (int)(nq_pad / BM);
+    const int64_t nq_pad = snk_round_up(nq, 2 * BM);      // room for the padded second query tile of a cluster
+    const int nqt = (int)snk_cdiv(nq, BM);
     CUtensorMap mapQ;
     SNK_TRY(make_map(s->encode, &mapQ, dQ16, (uint64_t)ldq16, (uint64_t)nq_pad, (uint64_t)ldq16, BM));
     tc_params p;
     memset(&p, 0, sizeof(p));
     p.nkb = h.nkb; p.nload = h.nload; p.nsub = h.nsub; p.stages = h.stages;
-    p.embed = h.embed ? 1 : 0; p.b_bytes = h.b_bytes;
+    p.embed = h.embed ? 1 : 0; p.b_bytes = h.b_bytes; p.cluster = 1;
     memcpy(p.load, h.load, sizeof(h.load));
     memcpy(p.sub, h.sub, sizeof(h.sub));
     p.nq = nq;
@@ -795,8 +898,9 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
     const bool fused = k <= 4;
     if (fused) {
         const int lsz = k <= 2 ? 4 : 8;
-        int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(db->sm_count / std::max(nqt, 1), row_tiles));
-        if (nqt > db->sm_count) nchunks = 1;
+        const tc_split ws = make_split(db, h, nqt, row_tiles);
+        const int nchunks = ws.nchunks;
+        p.cluster = ws.cluster;
         p.row_lo = 0; p.row_hi = sp.rows; p.nchunks = nchunks;
         p.chunk_rows = snk_cdiv(row_tiles, nchunks) * BN;
         const int nlists = nchunks * epi_split_of(h.sched);
@@ -806,7 +910,8 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         p.oid = (int *)(p.oval + nlist);
         {
             snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)sp.rows * sp.D, st);
-            pick_kernel(MODE_LIST, lsz, h.sched)<<<nqt * nchunks, num_threads_of(h.sched), smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
+            SNK_TRY(launch_tc(pick_kernel(MODE_LIST, lsz, h.sched), ws.nqt_pad * nchunks, num_threads_of(h.sched), smem, st,
+                              mapQ, s, p));
         }
         SNK_CUDA(cudaGetLastError());
         if (lists && snk_merge_rerank_fits(nlists, lsz)) {   // merge + tau happen inside the re-rank kernel
@@ -840,13 +945,15 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         for (int64_t rb = 0; rb < sp.rows; rb += span_rows) {
             const int64_t rn = std::min<int64_t>(span_rows, sp.rows - rb);
             const int64_t tiles = snk_cdiv(rn, (int64_t)BN * stride);      // sampled tiles of this span
-            int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(db->sm_count / std::max(nqt, 1), tiles));
-            if (nqt > db->sm_count) nchunks = 1;
+            const tc_split ws = make_split(db, h, nqt, tiles);
+            const int nchunks = ws.nchunks;
+            p.cluster = ws.cluster;
             p.row_lo = rb; p.row_hi = rb + rn; p.nchunks = nchunks;
             p.chunk_rows = snk_cdiv(tiles, nchunks) * BN * stride;
             {
                 snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)tiles * BN * sp.D, st);
-                pick_kernel(MODE_STORE, 4, h.sched)<<<nqt * nchunks, num_threads_of(h.sched), smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
+                SNK_TRY(launch_tc(pick_kernel(MODE_STORE, 4, h.sched), ws.nqt_pad * nchunks, num_threads_of(h.sched), smem, st,
+                                  mapQ, s, p));
             }
             SNK_CUDA(cudaGetLastError());
             db->counters[2] += 1;
@@ -872,8 +979,9 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         float *thr = (float *)db->ws_misc.p;
         kth_select_kernel<<<(unsigned)snk_cdiv(nq * 32, 256), 256, 0, st>>>(d_val, d_id, nq, KP, k, thr, d_tau);
         SNK_CUDA(cudaGetLastError());
-        int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(db->sm_count / std::max(nqt, 1), row_tiles));
-        if (nqt > db->sm_count) nchunks = 1;
+        const tc_split ws = make_split(db, h, nqt, row_tiles);
+        const int nchunks = ws.nchunks;
+        p.cluster = ws.cluster;
         const int nlists = nchunks * epi_split_of(h.sched);
         // neighbours cluster on a few consecutive rows (trajectories), so one list may take most of the ~8k
         // expected rows and an unsampled tile may hide a whole cluster: size every list for 20k rows (measured:
@@ -890,7 +998,8 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         SNK_CUDA(cudaMemsetAsync(p.bufi, 0xFF, nent * 4, st));     // unused slots read as id -1
         {
             snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)sp.rows * sp.D, st);
-            pick_kernel(MODE_EMIT, 4, h.sched)<<<nqt * nchunks, num_threads_of(h.sched), smem, st>>>(mapQ, s->mapS, s->mapG, s->mapGslab, p);
+            SNK_TRY(launch_tc(pick_kernel(MODE_EMIT, 4, h.sched), ws.nqt_pad * nchunks, num_threads_of(h.sched), smem, st, mapQ,
+                              s, p));
         }
         SNK_CUDA(cudaGetLastError());
         db->counters[2] += 3;

@@ -137,7 +137,7 @@ int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, d
     const int64_t QB = 16384;
     for (int64_t qb = 0; qb < nq; qb += QB) {
         const int64_t qn_ = std::min(QB, nq - qb);
-        const int64_t qpad = snk_round_up(qn_, 128);
+        const int64_t qpad = snk_round_up(qn_, 256);   // two query tiles: the tensor-core kernel may pair CTAs
         // ws_q layout: Q16 [qpad, ld16] | qn [qpad] | qerr [qpad] | tau [qpad] | cert [qpad+1] | qsel [qpad] | cnt
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };

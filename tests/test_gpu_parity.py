@@ -705,3 +705,23 @@ def test_shape_fuzz_tensor_core_vs_float64(shape):
             assert_knn_matches(d, i, rd, ri)
     assert np.all(db.knn(qj[:5], 1, engine.SPACE_JOINT)[0] == 0.0)
     db.close()
+
+
+def test_cluster_multicast_path(golden_epoch, monkeypatch):
+    """Opt-in thread-block-cluster path (pairs of CTAs share every database tile by TMA multicast): same answers."""
+    monkeypatch.setenv("SNK_TC_CLUSTER", "1")
+    db = syn.make_epoch_db(n_units=20000, seed=55)
+    cfg = epoch_config(tsw=(0.5, 0.5))
+    o = O.OracleSynthesiser(cfg, db["F"], db["Jc"])
+    o.get_tree_for_greedy_search()
+    g = Synthesiser(cfg, db["F"], db["Jc"])
+    g.db.set_engine(engine.ENGINE_TC)
+    utts = [O.weight(x, o.target_weight_vector) for x in syn.make_targets(db["F"], 300, 24, seed=6)]   # 3 query tiles: odd, padded pair
+    paths, dists = g.greedy_joint_search_batch(utts, return_dists=True)
+    for b in (0, 127, 128, 255, 256, 299):
+        assert_greedy_path_ok(o, utts[b], paths[b], dists[b])
+    assert g.db.counters()["recertified"] == 0
+    q = o.combined_rep()[::97][:200] + 0.01
+    rd, ri = o.joint_tree.query(q, k=12)                     # store / emit paths under the cluster launch
+    d, i = g.joint_tree.query(q, k=12)
+    assert_knn_matches(d, i, rd, ri)
