@@ -9,14 +9,23 @@
 //    from the ROUNDED values, so key + ||x~||^2 is the squared distance between the rounded
 //    vectors and |sqrt(key + ||x~||^2) - true distance| <= ||x - x~|| + ||y - y~|| (triangle
 //    inequality).  rerank.cu uses that bound to certify the float64 re-ranked answer exact.
-//  * the multiepoch joint row [start_join(u) || F(u) .. F(u+m-1)] is never materialised: K-block j
-//    of the target part is the TMA box of rows u0+j .. u0+j+127 of the frame matrix G16.
-//  * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread) + TMEM allocator,
-//    warps 2..5 = epilogue (one thread per query / TMEM lane).  The 128-query operand tile stays
-//    resident in shared memory; database tiles stream through a 4-stage mbarrier ring; two TMEM
-//    accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+//  * the multiepoch joint row [start_join(u) || F(u) .. F(u+m-1)] is never materialised: one TMA
+//    box of 136 rows of the frame matrix G16 (a "slab") serves all m window offsets -- K-block j
+//    reads the slab from row j on (descriptor start address + j * 128 B).
+//  * the squared norms ride in three spare columns of every operand row (hi/mid/lo fp16 pieces,
+//    the query holds -0.5 there), so the accumulator already is x.y - ||y||^2 / 2.
+//  * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM allocator,
+//    warps 2.. = epilogue (one thread per query / TMEM lane, two or four warps per lane quarter).
+//    The 128-query operand tile stays resident in shared memory; database tiles stream through an
+//    mbarrier ring; two TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+//  * for the shapes the reference ships the ring and the K-block sequence are compile-time
+//    schedules (sched_traits); other shapes run a table-driven variant of the same kernel.
+//  * three epilogues: MODE_LIST (register lists of the 4 / 8 best per query, k <= 4), MODE_STORE
+//    (keys to HBM, small databases and the sampling pass of larger k), MODE_EMIT (append every row
+//    at or below a per-query bound; larger k).
 //  * each CTA scans one (query tile, database chunk) pair; per-chunk results are merged by
-//    snk_topk_scan.
+//    rerank.cu (in-block) or snk_topk_scan.  Optionally two CTAs form a cluster and share every
+//    database tile by TMA multicast (SNK_TC_CLUSTER=1).
 #include "common.cuh"
 #include <cuda.h>
 #include <algorithm>
