@@ -725,3 +725,31 @@ def test_cluster_multicast_path(golden_epoch, monkeypatch):
     rd, ri = o.joint_tree.query(q, k=12)                     # store / emit paths under the cluster launch
     d, i = g.joint_tree.query(q, k=12)
     assert_knn_matches(d, i, rd, ri)
+
+
+# ------------------------------------------------------------------------------------ BASELINE.json configs[0]
+def test_config1_slt_simplified_mini():
+    """configs[0] (config/slt_simplified_mini.cfg:30-38,68-72,82,94): ~70k-epoch database, target weights
+    [0.1, 1.0], join weights [.25]*4, join_cost_weight 0.2, multiepoch 6, three test utterances of ~650 frames,
+    greedy search with search_epsilon forced to 0 -- the reference's own engine (cKDTree) on the CPU vs the GPU."""
+    db = syn.make_epoch_db(n_units=70000, seed=1234 + 1)
+    cfg = epoch_config(multiepoch=6, jcw=0.2, tsw=(0.1, 1.0), jsw=(0.25, 0.25, 0.25, 0.25))
+    o = O.OracleSynthesiser(cfg, db["F"], db["Jc"])
+    o.get_tree_for_greedy_search()
+    g = Synthesiser(cfg, db["F"], db["Jc"])
+    utts = [O.weight(x, o.target_weight_vector) for x in syn.make_targets(db["F"], 3, 650, seed=101)]
+    paths, dists = g.greedy_joint_search_batch(utts, return_dists=True)
+    exact = 0
+    for u, p, d in zip(utts, paths, dists):
+        assert len(p) == 650 // 6
+        ref, rd = o.greedy_joint_search(u, return_dists=True)
+        if p == ref:
+            exact += 1
+            np.testing.assert_allclose(d, rd, rtol=COST_RTOL)
+        else:
+            assert_greedy_path_ok(o, u, p, d)
+    assert exact >= 2          # identical unit sequences unless a 1e-6 tie intervenes
+    assert g.db.counters()["recertified"] == 0
+    # the per-stream cost report the balancing loop reads (C1)
+    ts, js = g.get_scores_per_stream(utts[0], paths[0])
+    assert ts.shape == (108, 2) and js.shape == (107, 4) and np.all(ts >= 0) and np.all(js >= 0)
