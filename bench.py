@@ -288,6 +288,27 @@ def run_ours(args):
     h2d = int(B * T * 61 * 8)
     d2h = int(B * steps_per_utt * 8)
 
+    # ---- same call from un-normalised float32 speech (row N4: standardise + weight fused on the device)
+    unnorm_info = None
+    if world == 1 and not args.no_secondary:
+        rng = np.random.default_rng(5)
+        Dt = db["F"].shape[1]
+        mean, std = rng.normal(size=Dt), rng.uniform(0.5, 2.0, size=Dt)
+        x = host_batches[0].numpy() / np.where(wt != 0, wt, 1.0)
+        raw = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+        raw.numpy()[...] = x * std + mean
+        del x
+        syn.set_standardisation(mean, std)
+        syn.db.greedy_batch_cat(raw.numpy(), lens_list, unnorm=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            syn.db.greedy_batch_cat(raw.numpy(), lens_list, unnorm=True)
+        torch.cuda.synchronize()
+        unnorm_info = {"value": B * T * 2 / (time.perf_counter() - t0), "unit": UNIT, "steps": 2,
+                       "h2d_bytes_per_step": int(B * T * Dt * 4),
+                       "note": "snk_greedy_batch_unnorm: compose_speech-style float32 in, host lists out"}
+
     # ---- kernel time of the dominant kernel (profiled pass, outside the timed region)
     syn.db.profile_enable(True)
     step_dev(0)
@@ -328,6 +349,7 @@ def run_ours(args):
     # ---- secondary: join tiles + Viterbi (config 3 shape) kernel rooflines, N = 1 only
     if rank == 0 and world == 1 and not args.no_secondary:
         out["secondary"] = secondary_viterbi(local)
+        out["secondary"]["greedy_e2e_from_unnormalised_f32"] = unnorm_info
     # ---- CPU baseline (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu:
         run, frames, info = cpu_reference_rate(db, cfg, wt, 1, budget_s=12.0, seed=99)

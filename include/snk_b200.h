@@ -110,6 +110,28 @@ int snk_greedy_batch_dev(snk_db *db, const double *d_targets, const int64_t *len
                          const int64_t *start_state, int64_t *d_paths, double *d_step_dist,
                          void *stream);
 
+/* ---- target preparation -----------------------------------------------------
+ * Replaces the per-utterance host numpy between compose_speech and the search
+ * (synth_simple.py:371-391): standardise (data_manipulation.py:162-186) then weight
+ * (speech_manip.py:209-213), in the reference's float64 arithmetic on its float32 input:
+ *   y[r,c] = (x[r,c] == special_uv_value ? std[c] * -1.0 * uv_scaling_factor
+ *                                        : (x[r,c] - mean[c]) / std[c]) * target_weight[c]
+ * snk_db_set_standardisation stores mean_vec_target / std_vec_target (float64 [Dt]) and the
+ * two constants of const.py:12-14 (-1000.0, 20.0).  The weights are those of
+ * snk_db_set_weights, so a re-weighting needs no second call here.                        */
+int snk_db_set_standardisation(snk_db *db, const double *mean, const double *std,
+                               double special_uv_value, double uv_scaling_factor);
+/* unnorm float32 [rows, Dt] (compose_speech output) -> out float64 [rows, Dt], host buffers */
+int snk_prepare_targets(snk_db *db, const float *unnorm, int64_t rows, double *out);
+/* snk_greedy_batch on un-normalised float32 speech: the standardise+weight step is fused
+ * into the query assembly, half the host->device bytes of the float64 form.  Results are
+ * identical to snk_greedy_batch(snk_prepare_targets(unnorm)).                              */
+int snk_greedy_batch_unnorm(snk_db *db, const float *unnorm, const int64_t *lens, int B,
+                            const int64_t *start_state, int64_t *paths, double *step_dist);
+int snk_greedy_batch_unnorm_dev(snk_db *db, const float *d_unnorm, const int64_t *lens, int B,
+                                const int64_t *start_state, int64_t *d_paths,
+                                double *d_step_dist, void *stream);
+
 /* ---- candidate target distances --------------------------------------------------------
  * Replaces the distance half of preselect_units_quinphone (synth_halfphone.py:1346-1351):
  * dist[t,j] = || Fw[cand[t,j]] - targets[t] ||_2 ; cand == -1 indexes the last unit as

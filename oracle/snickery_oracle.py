@@ -42,6 +42,24 @@ def weight(speech, weight_vec):
     return speech * weight_vec
 
 
+SPECIAL_UV_VALUE = -1000.0   # const.py:12
+UV_SCALING_FACTOR = 20.0     # const.py:14
+
+
+def standardise(speech, mean_vec, std_vec):
+    """data_manipulation.py:162-186 -- (speech - mean) / std in float64; entries that held the unvoiced marker
+    before standardisation become std * -1.0 * uv_scaling_factor.  Weighting is left to weight()."""
+    speech = np.asarray(speech)
+    uv_positions = (speech == SPECIAL_UV_VALUE)
+    mean_vec = np.asarray(mean_vec, dtype=np.float64).reshape((1, -1))
+    std_vec = np.asarray(std_vec, dtype=np.float64).reshape((1, -1))
+    speech = (speech - mean_vec) / std_vec
+    uv_values = std_vec * -1.0 * UV_SCALING_FACTOR
+    for column in range(speech.shape[1]):
+        speech[:, column][uv_positions[:, column]] = uv_values[0, column]
+    return speech
+
+
 def segment_axis0(a, length, overlap):
     """segmentaxis.py:40-111 restricted to axis=0, end='cut'.
 

@@ -140,6 +140,7 @@ int snk_db_destroy(snk_db *db) {
     snk_tc_destroy(db);
     for (auto &r : db->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     cudaFree(db->F_raw); cudaFree(db->Jc_raw); cudaFree(db->wt); cudaFree(db->wj);
+    cudaFree(db->std_mean); cudaFree(db->std_sd);
     cudaFree(db->Fw32); cudaFree(db->Jw32); cudaFree(db->G16); cudaFree(db->S16);
     cudaFree(db->nrm_t16); cudaFree(db->nrm_j16); cudaFree(db->err_t16);
     snk_buf *bufs[] = {&db->ws_q, &db->ws_dist, &db->ws_list, &db->ws_misc, &db->ws_io, &db->ws_io2, &db->ws_tiles,
@@ -260,8 +261,43 @@ int snk_knn(snk_db *db, int space, const double *Q, int64_t nq, int k, double *d
     return 0;
 }
 
-int snk_greedy_batch(snk_db *db, const double *targets, const int64_t *lens, int B, const int64_t *start_state,
-                     int64_t *paths, double *step_dist) {
+int snk_db_set_standardisation(snk_db *db, const double *mean, const double *std, double special_uv_value,
+                               double uv_scaling_factor) {
+    SNK_CHECK(db && mean && std, "NULL argument");
+    SNK_CUDA(cudaSetDevice(db->device));
+    for (int c = 0; c < db->Dt; ++c) SNK_CHECK(std[c] != 0.0 && std[c] == std[c], "std[%d] is zero or NaN", c);
+    if (!db->std_mean) {
+        SNK_CUDA(cudaMalloc(&db->std_mean, (size_t)db->Dt * 8));
+        SNK_CUDA(cudaMalloc(&db->std_sd, (size_t)db->Dt * 8));
+    }
+    SNK_CUDA(cudaMemcpyAsync(db->std_mean, mean, (size_t)db->Dt * 8, cudaMemcpyHostToDevice, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(db->std_sd, std, (size_t)db->Dt * 8, cudaMemcpyHostToDevice, db->stream));
+    SNK_CUDA(cudaStreamSynchronize(db->stream));
+    db->uv_special = special_uv_value;
+    db->uv_scale = uv_scaling_factor;
+    db->std_set = true;
+    return 0;
+}
+
+int snk_prepare_targets(snk_db *db, const float *unnorm, int64_t rows, double *out) {
+    SNK_CHECK(db && db->std_set, "snk_db_set_standardisation has not been called");
+    SNK_CHECK(rows >= 0, "bad row count");
+    if (rows == 0) return 0;
+    SNK_CHECK(unnorm && out, "NULL argument");
+    SNK_CUDA(cudaSetDevice(db->device));
+    const size_t n = (size_t)rows * db->Dt;
+    SNK_TRY(snk_buf_reserve(&db->ws_h0, n * 4));
+    SNK_TRY(snk_buf_reserve(&db->ws_h1, n * 8));
+    SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, unnorm, n * 4, cudaMemcpyHostToDevice, db->stream));
+    SNK_TRY(snk_prepare_targets_dev(db, (const float *)db->ws_h0.p, rows, (double *)db->ws_h1.p, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(out, db->ws_h1.p, n * 8, cudaMemcpyDeviceToHost, db->stream));
+    SNK_CUDA(cudaStreamSynchronize(db->stream));
+    return 0;
+}
+
+// host entry point shared by the weighted-float64 and the un-normalised-float32 forms (elem = 8 / 4)
+static int greedy_batch_host(snk_db *db, const void *targets, size_t elem, const int64_t *lens, int B,
+                             const int64_t *start_state, int64_t *paths, double *step_dist) {
     SNK_CHECK(db && lens && paths, "NULL argument");
     SNK_CHECK(B >= 0, "bad batch size");
     if (B == 0) return 0;
@@ -273,7 +309,7 @@ int snk_greedy_batch(snk_db *db, const double *targets, const int64_t *lens, int
         steps += lens[b] / db->m;
     }
     SNK_CHECK(targets || frames == 0, "targets is NULL");
-    SNK_TRY(snk_buf_reserve(&db->ws_h0, (size_t)std::max<int64_t>(frames, 1) * db->Dt * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_h0, (size_t)std::max<int64_t>(frames, 1) * db->Dt * elem));
     SNK_TRY(snk_buf_reserve(&db->ws_h1, (size_t)std::max<int64_t>(steps, 1) * 8));
     SNK_TRY(snk_buf_reserve(&db->ws_h2, (size_t)std::max<int64_t>(steps, 1) * 8));
     // Upload.  Equal-length utterances (the common batch) go up in time slices on a second stream: step t
@@ -284,19 +320,19 @@ int snk_greedy_batch(snk_db *db, const double *targets, const int64_t *lens, int
     const int64_t T = lens[0], nsteps = T / db->m;
     const int NSLICE = 8;
     db->step_waits.clear();
-    if (equal && nsteps >= 4 * NSLICE && frames * db->Dt * 8 >= ((int64_t)8 << 20)) {
+    if (equal && nsteps >= 4 * NSLICE && frames * db->Dt >= ((int64_t)1 << 20)) {
         while ((int)db->upload_events.size() < NSLICE) {
             cudaEvent_t e;
             SNK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             db->upload_events.push_back(e);
         }
-        const size_t pitch = (size_t)T * db->Dt * 8;
+        const size_t pitch = (size_t)T * db->Dt * elem;
         // slice boundaries in steps: a short first slice, the rest even
         int64_t s0 = 0;
         for (int c = 0; c < NSLICE; ++c) {
             const int64_t s1 = c == NSLICE - 1 ? nsteps : std::max<int64_t>(2, (c + 1) * nsteps / NSLICE - nsteps / (2 * NSLICE));
             const int64_t f0 = s0 * db->m, f1 = c == NSLICE - 1 ? T : s1 * db->m;   // the last slice carries the cut remainder
-            const size_t off = (size_t)f0 * db->Dt * 8, width = (size_t)(f1 - f0) * db->Dt * 8;
+            const size_t off = (size_t)f0 * db->Dt * elem, width = (size_t)(f1 - f0) * db->Dt * elem;
             SNK_CUDA(cudaMemcpy2DAsync((char *)db->ws_h0.p + off, pitch, (const char *)targets + off, pitch, width,
                                        (size_t)B, cudaMemcpyHostToDevice, db->copy_stream));
             SNK_CUDA(cudaEventRecord(db->upload_events[c], db->copy_stream));
@@ -304,11 +340,14 @@ int snk_greedy_batch(snk_db *db, const double *targets, const int64_t *lens, int
             s0 = s1;
         }
     } else if (frames) {
-        SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, targets, (size_t)frames * db->Dt * 8, cudaMemcpyHostToDevice, db->stream));
+        SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, targets, (size_t)frames * db->Dt * elem, cudaMemcpyHostToDevice, db->stream));
     }
-    const int rc_greedy = snk_greedy_batch_dev(db, (const double *)db->ws_h0.p, lens, B, start_state,
-                                               (int64_t *)db->ws_h1.p, step_dist ? (double *)db->ws_h2.p : nullptr,
-                                               db->stream);
+    int64_t *d_paths = (int64_t *)db->ws_h1.p;
+    double *d_sd = step_dist ? (double *)db->ws_h2.p : nullptr;
+    const int rc_greedy =
+        elem == 8 ? snk_greedy_batch_dev(db, (const double *)db->ws_h0.p, lens, B, start_state, d_paths, d_sd, db->stream)
+                  : snk_greedy_batch_unnorm_dev(db, (const float *)db->ws_h0.p, lens, B, start_state, d_paths, d_sd,
+                                                db->stream);
     db->step_waits.clear();
     if (rc_greedy) {
         cudaStreamSynchronize(db->copy_stream);
@@ -321,6 +360,17 @@ int snk_greedy_batch(snk_db *db, const double *targets, const int64_t *lens, int
     }
     SNK_CUDA(cudaStreamSynchronize(db->stream));
     return 0;
+}
+
+int snk_greedy_batch(snk_db *db, const double *targets, const int64_t *lens, int B, const int64_t *start_state,
+                     int64_t *paths, double *step_dist) {
+    return greedy_batch_host(db, targets, 8, lens, B, start_state, paths, step_dist);
+}
+
+int snk_greedy_batch_unnorm(snk_db *db, const float *unnorm, const int64_t *lens, int B, const int64_t *start_state,
+                            int64_t *paths, double *step_dist) {
+    SNK_CHECK(db && db->std_set, "snk_db_set_standardisation has not been called");
+    return greedy_batch_host(db, unnorm, 4, lens, B, start_state, paths, step_dist);
 }
 
 int snk_candidate_distances(snk_db *db, const int64_t *cand, const double *targets, int64_t T, int K, double *dist) {

@@ -75,6 +75,10 @@ struct snk_db {
     float *Jc_raw = nullptr;  // [N+1, Dj]
     double *wt = nullptr;     // [Dt]
     double *wj = nullptr;     // [Dj]
+    // target standardisation (snk_db_set_standardisation): lets the search read un-normalised f32 speech
+    double *std_mean = nullptr, *std_sd = nullptr;   // [Dt] each
+    double uv_special = -1000.0, uv_scale = 20.0;
+    bool std_set = false;
     float *Fw32 = nullptr;    // [N, Dt]       weighted, rounded to f32
     float *Jw32 = nullptr;    // [N+1, ldJ32]  weighted, rounded to f32, zero padded
     int ldJ32 = 0;
@@ -169,6 +173,7 @@ int snk_merge_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t 
 // d_sticky (optional, [nq] preset to 1, followed by one int failure counter): deferred certificate mode --
 // uncertified queries only clear their flag / bump the counter, nothing is synchronised or re-searched;
 // the caller inspects the flags later (greedy batches do, once per batch).
+int snk_prepare_targets_dev(snk_db *db, const float *d_unnorm, int64_t rows, double *d_out, void *stream);
 int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist,
                    int64_t *d_idx, int64_t out_stride, int64_t id_offset, int *d_sticky, int *d_sticky_count,
                    cudaStream_t st);

@@ -202,10 +202,33 @@ struct greedy_meta {
     int64_t start_state;
 };
 
+// standardise() then weight() of one un-normalised target value, in the reference's float64 arithmetic
+// (data_manipulation.py:162-186: (x - mean) / std, unvoiced marker -> std * -1.0 * uv_scaling_factor;
+// speech_manip.py:209-213: * weight).  x is the float32 value compose_speech produced.
+struct std_params {
+    const double *mean, *sd, *w;
+    double uv_special, uv_scale;
+};
+__device__ __forceinline__ double standardise_weight(float x, int c, const std_params &sp) {
+    const double sd = sp.sd[c];
+    const double v = (double)x == sp.uv_special ? __dmul_rn(__dmul_rn(sd, -1.0), sp.uv_scale)
+                                                : __ddiv_rn(__dsub_rn((double)x, sp.mean[c]), sd);
+    return __dmul_rn(v, sp.w[c]);
+}
+
+__global__ void prepare_targets_kernel(const float *__restrict__ x, int64_t total, int Dt, std_params sp,
+                                       double *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = standardise_weight(x[i], (int)(i % Dt), sp);
+}
+
 // Query b of step t = [ prev_join_vector || m consecutive target frames ]   (synth_simple.py:467-470,488,501)
 // Also scatters the previous step's result into the output path.
+// targets: weighted float64 frames, or (targets32 != nullptr) un-normalised float32 frames that are
+// standardised and weighted on the fly (synth_simple.py:371-391).
 __global__ void greedy_assemble_kernel(const greedy_meta *__restrict__ meta, int nact_prev, int nact, int64_t t,
-                                       const double *__restrict__ targets, int Dt, int m,
+                                       const double *__restrict__ targets, const float *__restrict__ targets32,
+                                       std_params stp, int Dt, int m,
                                        const float *__restrict__ Jc_raw, const double *__restrict__ wj, int Dj,
                                        int Djq, int prev_row_off, int prev_col, int cur_row_off, int cur_col,
                                        const int64_t *__restrict__ ix_prev, const double *__restrict__ dist_prev,
@@ -233,7 +256,8 @@ __global__ void greedy_assemble_kernel(const greedy_meta *__restrict__ meta, int
         if (d < Djq) {
             v = row >= 0 ? (double)Jc_raw[row * Dj + col + d] * wj[col + d] : 0.0;
         } else {
-            v = targets[(mt.tgt_off + t * m) * Dt + (d - Djq)];
+            const int64_t i = (mt.tgt_off + t * m) * Dt + (d - Djq);
+            v = targets32 ? standardise_weight(targets32[i], (d - Djq) % Dt, stp) : targets[i];
         }
         q[d] = v;
     }
@@ -246,9 +270,10 @@ namespace {
 // One pass of the greedy chain over the utterances in `meta` (sorted longest first).  With deferred
 // certificates no step synchronises: flags [n] are preset to 1 and cleared by any step whose
 // tensor-core answer could not be certified.
-int greedy_run(snk_db *db, const std::vector<greedy_meta> &meta, const double *d_targets, int64_t *d_paths,
-               double *d_step_dist, int *d_flags, int *d_count, cudaStream_t st) {
+int greedy_run(snk_db *db, const std::vector<greedy_meta> &meta, const double *d_targets, const float *d_unnorm,
+               int64_t *d_paths, double *d_step_dist, int *d_flags, int *d_count, cudaStream_t st) {
     const int B = (int)meta.size();
+    const std_params stp{db->std_mean, db->std_sd, db->wt, db->uv_special, db->uv_scale};
     const int m = db->m;
     const snk_space sp = snk_make_space(db, SNK_SPACE_JOINT);
     int64_t maxsteps = 0;
@@ -274,7 +299,7 @@ int greedy_run(snk_db *db, const std::vector<greedy_meta> &meta, const double *d
         // chunked uploads (host entry point): step t may start once its target frames have landed
         while (next_wait < db->step_waits.size() && db->step_waits[next_wait].first <= t)
             SNK_CUDA(cudaStreamWaitEvent(st, db->step_waits[next_wait++].second, 0));
-        greedy_assemble_kernel<<<grid, 128, 0, st>>>(d_meta, nact_prev, nact, t, d_targets, db->Dt, m, db->Jc_raw,
+        greedy_assemble_kernel<<<grid, 128, 0, st>>>(d_meta, nact_prev, nact, t, d_targets, d_unnorm, stp, db->Dt, m, db->Jc_raw,
                                                      db->wj, db->Dj, db->Djq, db->prev_row_off, db->prev_col,
                                                      db->cur_row_off, db->cur_col, ix, dist, d_paths, d_step_dist, Q);
         SNK_CUDA(cudaGetLastError());
@@ -292,8 +317,36 @@ __global__ void fill_int_kernel(int *p, int64_t n, int v) {
 
 }  // namespace
 
+static int greedy_batch_core(snk_db *db, const double *d_targets, const float *d_unnorm, const int64_t *lens, int B,
+                             const int64_t *start_state, int64_t *d_paths, double *d_step_dist, void *stream);
+
 int snk_greedy_batch_dev(snk_db *db, const double *d_targets, const int64_t *lens, int B,
                          const int64_t *start_state, int64_t *d_paths, double *d_step_dist, void *stream) {
+    return greedy_batch_core(db, d_targets, nullptr, lens, B, start_state, d_paths, d_step_dist, stream);
+}
+
+int snk_greedy_batch_unnorm_dev(snk_db *db, const float *d_unnorm, const int64_t *lens, int B,
+                                const int64_t *start_state, int64_t *d_paths, double *d_step_dist, void *stream) {
+    SNK_CHECK(db && db->std_set, "snk_db_set_standardisation has not been called");
+    return greedy_batch_core(db, nullptr, d_unnorm, lens, B, start_state, d_paths, d_step_dist, stream);
+}
+
+int snk_prepare_targets_dev(snk_db *db, const float *d_unnorm, int64_t rows, double *d_out, void *stream) {
+    SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    SNK_CHECK(db->std_set, "snk_db_set_standardisation has not been called");
+    if (rows <= 0) return 0;
+    SNK_CUDA(cudaSetDevice(db->device));
+    const std_params stp{db->std_mean, db->std_sd, db->wt, db->uv_special, db->uv_scale};
+    const int64_t total = rows * db->Dt;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)db->sm_count * 8);
+    prepare_targets_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_unnorm, total, db->Dt, stp, d_out);
+    SNK_CUDA(cudaGetLastError());
+    db->counters[2] += 1;
+    return 0;
+}
+
+static int greedy_batch_core(snk_db *db, const double *d_targets, const float *d_unnorm, const int64_t *lens, int B,
+                             const int64_t *start_state, int64_t *d_paths, double *d_step_dist, void *stream) {
     SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
     SNK_CUDA(cudaSetDevice(db->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -324,7 +377,7 @@ int snk_greedy_batch_dev(snk_db *db, const double *d_targets, const int64_t *len
     fill_int_kernel<<<64, 256, 0, st>>>(flags, B, 1);
     SNK_CUDA(cudaGetLastError());
     SNK_CUDA(cudaMemsetAsync(count, 0, 4, st));
-    SNK_TRY(greedy_run(db, meta, d_targets, d_paths, d_step_dist, flags, count, st));
+    SNK_TRY(greedy_run(db, meta, d_targets, d_unnorm, d_paths, d_step_dist, flags, count, st));
     int nfail = 0;
     SNK_CUDA(cudaMemcpyAsync(&nfail, count, 4, cudaMemcpyDeviceToHost, st));
     SNK_CUDA(cudaStreamSynchronize(st));
@@ -339,7 +392,7 @@ int snk_greedy_batch_dev(snk_db *db, const double *d_targets, const int64_t *len
         db->counters[1] += (int64_t)redo.size();
         const int saved = db->engine;
         db->engine = SNK_ENGINE_SIMT;
-        const int rc = greedy_run(db, redo, d_targets, d_paths, d_step_dist, nullptr, nullptr, st);
+        const int rc = greedy_run(db, redo, d_targets, d_unnorm, d_paths, d_step_dist, nullptr, nullptr, st);
         db->engine = saved;
         SNK_TRY(rc);
     }

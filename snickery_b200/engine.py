@@ -62,6 +62,10 @@ def load_library(path=None):
         "snk_topk_merge_dev": [i32, vp, vp, i32, i64, i32, vp, vp, vp],
         "snk_greedy_batch": [vp, P(dbl), P(i64), i32, P(i64), P(i64), P(dbl)],
         "snk_greedy_batch_dev": [vp, vp, P(i64), i32, P(i64), vp, vp, vp],
+        "snk_db_set_standardisation": [vp, P(dbl), P(dbl), dbl, dbl],
+        "snk_prepare_targets": [vp, P(flt), i64, P(dbl)],
+        "snk_greedy_batch_unnorm": [vp, P(flt), P(i64), i32, P(i64), P(i64), P(dbl)],
+        "snk_greedy_batch_unnorm_dev": [vp, vp, P(i64), i32, P(i64), vp, vp, vp],
         "snk_candidate_distances": [vp, P(i64), P(dbl), i64, i32, P(dbl)],
         "snk_join_tiles": [vp, P(i64), P(i64), i32, i32, P(flt)],
         "snk_join_viterbi_batch": [vp, P(i64), P(dbl), P(i64), i32, i32, C.c_uint, P(i64), P(i64), P(dbl), P(dbl), P(dbl)],
@@ -83,6 +87,8 @@ EXPORTED_SYMBOLS = ["snk_last_error", "snk_version", "snk_device_count", "snk_db
                     "snk_db_info", "snk_db_set_weights", "snk_db_set_engine", "snk_db_counters", "snk_db_profile_enable",
                     "snk_db_profile_read", "snk_knn",
                     "snk_knn_dev", "snk_topk_merge_dev", "snk_greedy_batch", "snk_greedy_batch_dev",
+                    "snk_db_set_standardisation", "snk_prepare_targets", "snk_greedy_batch_unnorm",
+                    "snk_greedy_batch_unnorm_dev",
                     "snk_candidate_distances", "snk_join_tiles", "snk_join_viterbi_batch",
                     "snk_join_viterbi_batch_dev", "snk_greedy_path_scores", "snk_frames_create", "snk_frames_destroy",
                     "snk_concat_magphase_epoch"]
@@ -171,8 +177,28 @@ class UnitDatabase:
                                       _ptr(idx, C.c_int64)))
         return dist, idx
 
-    def greedy_batch_cat(self, cat, lens, start_states=None, return_dists=False):
-        """Batch given as one concatenated float64 array [sum T_b, Dt] (may be pinned) + lengths."""
+    def set_standardisation(self, mean, std, special_uv_value=-1000.0, uv_scaling_factor=20.0):
+        """mean_vec_target / std_vec_target of the voice + the constants of const.py:12-14 (row N4)."""
+        mean = np.ascontiguousarray(np.asarray(mean, dtype=np.float64).reshape(-1))
+        std = np.ascontiguousarray(np.asarray(std, dtype=np.float64).reshape(-1))
+        if mean.size != self.Dt or std.size != self.Dt:
+            raise ValueError("mean / std must have %d entries" % self.Dt)
+        _check(load_library().snk_db_set_standardisation(self._h, _ptr(mean, C.c_double), _ptr(std, C.c_double),
+                                                         float(special_uv_value), float(uv_scaling_factor)))
+
+    def prepare_targets(self, unnorm):
+        """weight(standardise(unnorm)) on the device: float32 [T, Dt] -> float64 [T, Dt]."""
+        unnorm = np.ascontiguousarray(unnorm, dtype=np.float32)
+        if unnorm.ndim != 2 or unnorm.shape[1] != self.Dt:
+            raise ValueError("unnorm speech must be [T, %d]" % self.Dt)
+        out = np.empty(unnorm.shape, dtype=np.float64)
+        _check(load_library().snk_prepare_targets(self._h, _ptr(unnorm, C.c_float), unnorm.shape[0],
+                                                  _ptr(out, C.c_double)))
+        return out
+
+    def greedy_batch_cat(self, cat, lens, start_states=None, return_dists=False, unnorm=False):
+        """Batch given as one concatenated array [sum T_b, Dt] (may be pinned) + lengths: weighted float64
+        unit features, or (unnorm=True) un-normalised float32 speech that the device standardises and weights."""
         m = self.multiepoch
         lens = np.ascontiguousarray(lens, dtype=np.int64)
         B = lens.size
@@ -180,7 +206,7 @@ class UnitDatabase:
             return ([], []) if return_dists else []
         if np.any(lens < m):
             raise ValueError("Not enough data points to segment array in 'cut' mode")  # segmentaxis.py:94-96
-        cat = np.ascontiguousarray(cat, dtype=np.float64)
+        cat = np.ascontiguousarray(cat, dtype=np.float32 if unnorm else np.float64)
         if cat.ndim != 2 or cat.shape[1] != self.Dt or cat.shape[0] != int(lens.sum()):
             raise ValueError("targets must be [sum(lens), %d]" % self.Dt)
         steps = lens // m
@@ -189,15 +215,17 @@ class UnitDatabase:
         ss = None
         if start_states is not None:
             ss = np.ascontiguousarray(start_states, dtype=np.int64)
-        _check(load_library().snk_greedy_batch(self._h, _ptr(cat, C.c_double), _ptr(lens, C.c_int64), B,
-                                               _ptr(ss, C.c_int64), _ptr(paths, C.c_int64), _ptr(dists, C.c_double)))
+        lib = load_library()
+        fn, ct = (lib.snk_greedy_batch_unnorm, C.c_float) if unnorm else (lib.snk_greedy_batch, C.c_double)
+        _check(fn(self._h, _ptr(cat, ct), _ptr(lens, C.c_int64), B, _ptr(ss, C.c_int64), _ptr(paths, C.c_int64),
+                  _ptr(dists, C.c_double)))
         cuts = np.cumsum(steps)[:-1]
         p = [x.tolist() for x in np.split(paths, cuts)]
         if return_dists:
             return p, np.split(dists, cuts)
         return p
 
-    def greedy_batch(self, targets_list, start_states=None, return_dists=False):
+    def greedy_batch(self, targets_list, start_states=None, return_dists=False, unnorm=False):
         for t in targets_list:
             if t.ndim != 2 or t.shape[1] != self.Dt:
                 raise ValueError("each target utterance must be [T, %d]" % self.Dt)
@@ -205,7 +233,7 @@ class UnitDatabase:
             return ([], []) if return_dists else []
         lens = np.array([t.shape[0] for t in targets_list], dtype=np.int64)
         cat = np.concatenate(targets_list, axis=0)
-        return self.greedy_batch_cat(cat, lens, start_states, return_dists)
+        return self.greedy_batch_cat(cat, lens, start_states, return_dists, unnorm=unnorm)
 
     def candidate_distances(self, cand, targets):
         cand = np.ascontiguousarray(cand, dtype=np.int64)

@@ -240,6 +240,26 @@ class Synthesiser:
         feats = [self._full_width(u) for u in unit_features_list]
         return self.db.greedy_batch(feats, start_states, return_dists=return_dists)
 
+    # ---- target preparation on the device (synth_simple.py:371-391)
+    def set_standardisation(self, mean_vec_target, std_vec_target, special_uv_value=-1000.0, uv_scaling_factor=20.0):
+        """The voice's mean_vec_target / std_vec_target (synth_simple.py:96-97) and const.py:12-14."""
+        self.mean_vec_target = np.asarray(mean_vec_target, dtype=np.float64)
+        self.std_vec_target = np.asarray(std_vec_target, dtype=np.float64)
+        self.db.set_standardisation(self.mean_vec_target, self.std_vec_target, special_uv_value, uv_scaling_factor)
+
+    def prepare_targets(self, unnorm_speech):
+        """weight(standardise(unnorm_speech), target_weight_vector): compose_speech's float32 output in,
+        the float64 unit_features of synth_utt out (full width; truncated columns carry zero weight)."""
+        self._push_weights()
+        return self.db.prepare_targets(unnorm_speech)
+
+    def greedy_joint_search_unnorm_batch(self, unnorm_speech_list, start_states=None, return_dists=False):
+        """greedy_joint_search straight from un-normalised speech: standardise + weight are fused into the
+        device-side query assembly, so the host does no per-utterance numpy and uploads float32."""
+        self._push_weights()
+        feats = [np.asarray(u, dtype=np.float32) for u in unnorm_speech_list]
+        return self.db.greedy_batch(feats, start_states, return_dists=return_dists, unnorm=True)
+
     # ---- preselection (synth_halfphone.py:1359-1366, 1346-1351)
     def preselect_units_acoustic(self, unit_features):
         self._push_weights()

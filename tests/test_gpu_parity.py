@@ -753,3 +753,65 @@ def test_config1_slt_simplified_mini():
     # the per-stream cost report the balancing loop reads (C1)
     ts, js = g.get_scores_per_stream(utts[0], paths[0])
     assert ts.shape == (108, 2) and js.shape == (107, 4) and np.all(ts >= 0) and np.all(js >= 0)
+
+
+# ------------------------------------------------------------------------------------ N4: target preparation
+def _unnorm_speech(F, n_utts, T, seed):
+    """compose_speech-like float32 input: de-standardised frames with the unvoiced marker in the f0 column."""
+    rng = np.random.default_rng(seed)
+    Dt = F.shape[1]
+    mean = rng.normal(size=Dt) * 3.0
+    std = rng.uniform(0.5, 4.0, size=Dt)
+    utts = []
+    for x in syn.make_targets(F, n_utts, T, seed=seed):
+        u = (x.astype(np.float64) * std + mean).astype(np.float32)
+        uv = rng.random(u.shape[0]) < 0.3
+        u[uv, Dt - 1] = np.float32(O.SPECIAL_UV_VALUE)     # the lf0 stream is the last column
+        utts.append(u)
+    return utts, mean, std
+
+
+def test_prepare_targets_bit_exact():
+    db = syn.make_epoch_db(n_units=3000, seed=77)
+    cfg = epoch_config(multiepoch=4, jcw=0.3)
+    o = O.OracleSynthesiser(cfg, db["F"], db["Jc"])
+    g = Synthesiser(cfg, db["F"], db["Jc"])
+    utts, mean, std = _unnorm_speech(db["F"], 3, 57, seed=5)
+    g.set_standardisation(mean, std)
+    for u in utts:
+        ref = O.weight(O.standardise(u, mean, std), o.target_weight_vector)
+        got = g.prepare_targets(u)
+        assert got.dtype == np.float64 and np.array_equal(got, ref)
+    assert g.prepare_targets(np.zeros((0, db["F"].shape[1]), np.float32)).shape == (0, db["F"].shape[1])
+
+
+def test_greedy_from_unnormalised_speech():
+    """The fused form (float32 upload, standardise + weight inside the query assembly) selects exactly what
+    the reference's order of operations does: standardise -> weight -> greedy_joint_search."""
+    db = syn.make_epoch_db(n_units=20000, seed=78)
+    cfg = epoch_config(multiepoch=6, jcw=0.2)
+    o = O.OracleSynthesiser(cfg, db["F"], db["Jc"])
+    o.get_tree_for_greedy_search()
+    g = Synthesiser(cfg, db["F"], db["Jc"])
+    utts, mean, std = _unnorm_speech(db["F"], 5, 90, seed=6)
+    utts[1] = utts[1][:43]                                    # ragged batch
+    with pytest.raises(engine.EngineError, match="standardisation"):
+        g.greedy_joint_search_unnorm_batch(utts)             # standardisation not set yet
+    g.set_standardisation(mean, std)
+    paths, dists = g.greedy_joint_search_unnorm_batch(utts, return_dists=True)
+    feats = [O.weight(O.standardise(u, mean, std), o.target_weight_vector) for u in utts]
+    p64, d64 = g.greedy_joint_search_batch(feats, return_dists=True)
+    assert paths == p64
+    for a, b in zip(dists, d64):
+        assert np.array_equal(a, b)
+    for u, p, d in zip(feats, paths, dists):
+        ref, rd = o.greedy_joint_search(u, return_dists=True)
+        if p == ref:
+            np.testing.assert_allclose(d, rd, rtol=COST_RTOL)
+        else:
+            assert_greedy_path_ok(o, u, p, d)
+    # a re-weighting is picked up without touching the standardisation
+    g.reconfigure_settings({"join_cost_weight": 0.6})
+    o2 = O.OracleSynthesiser(dict(cfg, join_cost_weight=0.6), db["F"], db["Jc"])
+    feats2 = [O.weight(O.standardise(u, mean, std), o2.target_weight_vector) for u in utts]
+    assert g.greedy_joint_search_unnorm_batch(utts) == g.greedy_joint_search_batch(feats2)

@@ -192,3 +192,16 @@ def test_magphase_concatenation_oracle_known_answers():
     assert frag.shape == (m + 2, w) and np.all(frag[0] == 0.0) and frag.dtype == np.float64
     with pytest.raises(AssertionError):
         o.concatenate(path, overlap=1)
+
+
+def test_standardise_known_answer():
+    """data_manipulation.py:162-186 by hand: plain columns are (x - mean) / std, the unvoiced marker becomes
+    -20 * std whatever the mean, and the input is left untouched."""
+    x = np.array([[1.0, 5.0], [3.0, O.SPECIAL_UV_VALUE], [5.0, 7.0]], dtype=np.float32)
+    keep = x.copy()
+    y = O.standardise(x, np.array([3.0, 6.0]), np.array([[2.0, 0.5]]))
+    assert y.dtype == np.float64
+    np.testing.assert_array_equal(y, np.array([[-1.0, -2.0], [0.0, -10.0], [1.0, 2.0]]))
+    np.testing.assert_array_equal(x, keep)
+    w = O.weight(y, [2.0, 0.5])
+    np.testing.assert_array_equal(w, np.array([[-2.0, -1.0], [0.0, -5.0], [2.0, 1.0]]))
