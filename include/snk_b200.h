@@ -116,11 +116,16 @@ int snk_greedy_batch_dev(snk_db *db, const double *d_targets, const int64_t *len
  * (speech_manip.py:209-213), in the reference's float64 arithmetic on its float32 input:
  *   y[r,c] = (x[r,c] == special_uv_value ? std[c] * -1.0 * uv_scaling_factor
  *                                        : (x[r,c] - mean[c]) / std[c]) * target_weight[c]
- * snk_db_set_standardisation stores mean_vec_target / std_vec_target (float64 [Dt]) and the
- * two constants of const.py:12-14 (-1000.0, 20.0).  The weights are those of
- * snk_db_set_weights, so a re-weighting needs no second call here.                        */
+ * snk_db_set_standardisation stores mean_vec_target / std_vec_target ([Dt]) and the two
+ * constants of const.py:12-14 (-1000.0, 20.0).  The weights are those of snk_db_set_weights,
+ * so a re-weighting needs no second call here.  flags: SNK_STD_FLOAT32 when the statistics
+ * are float32 values (the voice file stores them as 'f', train_simple.py:94-97): numpy then
+ * keeps subtraction, division and the unvoiced value in float32, and so does the kernel;
+ * without the flag the arithmetic is float64 (float64 statistics promote the float32 speech). */
+#define SNK_STD_FLOAT32 1u
 int snk_db_set_standardisation(snk_db *db, const double *mean, const double *std,
-                               double special_uv_value, double uv_scaling_factor);
+                               double special_uv_value, double uv_scaling_factor,
+                               unsigned flags);
 /* unnorm float32 [rows, Dt] (compose_speech output) -> out float64 [rows, Dt], host buffers */
 int snk_prepare_targets(snk_db *db, const float *unnorm, int64_t rows, double *out);
 /* snk_greedy_batch on un-normalised float32 speech: the standardise+weight step is fused

@@ -47,12 +47,14 @@ UV_SCALING_FACTOR = 20.0     # const.py:14
 
 
 def standardise(speech, mean_vec, std_vec):
-    """data_manipulation.py:162-186 -- (speech - mean) / std in float64; entries that held the unvoiced marker
-    before standardisation become std * -1.0 * uv_scaling_factor.  Weighting is left to weight()."""
+    """data_manipulation.py:162-186 -- (speech - mean) / std; entries that held the unvoiced marker before
+    standardisation become std * -1.0 * uv_scaling_factor.  Weighting is left to weight().
+    The arithmetic type is numpy's: the voice file stores mean / std as float32 (train_simple.py:94-97), so with
+    float32 speech everything here stays float32; float64 statistics promote it to float64."""
     speech = np.asarray(speech)
     uv_positions = (speech == SPECIAL_UV_VALUE)
-    mean_vec = np.asarray(mean_vec, dtype=np.float64).reshape((1, -1))
-    std_vec = np.asarray(std_vec, dtype=np.float64).reshape((1, -1))
+    mean_vec = np.asarray(mean_vec).reshape((1, -1))
+    std_vec = np.asarray(std_vec).reshape((1, -1))
     speech = (speech - mean_vec) / std_vec
     uv_values = std_vec * -1.0 * UV_SCALING_FACTOR
     for column in range(speech.shape[1]):

@@ -262,7 +262,7 @@ int snk_knn(snk_db *db, int space, const double *Q, int64_t nq, int k, double *d
 }
 
 int snk_db_set_standardisation(snk_db *db, const double *mean, const double *std, double special_uv_value,
-                               double uv_scaling_factor) {
+                               double uv_scaling_factor, unsigned flags) {
     SNK_CHECK(db && mean && std, "NULL argument");
     SNK_CUDA(cudaSetDevice(db->device));
     for (int c = 0; c < db->Dt; ++c) SNK_CHECK(std[c] != 0.0 && std[c] == std[c], "std[%d] is zero or NaN", c);
@@ -275,6 +275,7 @@ int snk_db_set_standardisation(snk_db *db, const double *mean, const double *std
     SNK_CUDA(cudaStreamSynchronize(db->stream));
     db->uv_special = special_uv_value;
     db->uv_scale = uv_scaling_factor;
+    db->std_f32 = (flags & SNK_STD_FLOAT32) ? 1 : 0;
     db->std_set = true;
     return 0;
 }

@@ -79,6 +79,7 @@ struct snk_db {
     double *std_mean = nullptr, *std_sd = nullptr;   // [Dt] each
     double uv_special = -1000.0, uv_scale = 20.0;
     bool std_set = false;
+    int std_f32 = 0;          // SNK_STD_FLOAT32
     float *Fw32 = nullptr;    // [N, Dt]       weighted, rounded to f32
     float *Jw32 = nullptr;    // [N+1, ldJ32]  weighted, rounded to f32, zero padded
     int ldJ32 = 0;

@@ -205,14 +205,24 @@ struct greedy_meta {
 // standardise() then weight() of one un-normalised target value, in the reference's float64 arithmetic
 // (data_manipulation.py:162-186: (x - mean) / std, unvoiced marker -> std * -1.0 * uv_scaling_factor;
 // speech_manip.py:209-213: * weight).  x is the float32 value compose_speech produced.
+// f32: the statistics are float32 (as read from the voice file, train_simple.py:94-97) and numpy keeps the
+// whole standardisation in float32; otherwise float64 statistics promote it to float64.
 struct std_params {
     const double *mean, *sd, *w;
     double uv_special, uv_scale;
+    int f32;
 };
 __device__ __forceinline__ double standardise_weight(float x, int c, const std_params &sp) {
-    const double sd = sp.sd[c];
-    const double v = (double)x == sp.uv_special ? __dmul_rn(__dmul_rn(sd, -1.0), sp.uv_scale)
-                                                : __ddiv_rn(__dsub_rn((double)x, sp.mean[c]), sd);
+    double v;
+    if (sp.f32) {
+        const float sd = (float)sp.sd[c];
+        v = (double)(x == (float)sp.uv_special ? __fmul_rn(__fmul_rn(sd, -1.0f), (float)sp.uv_scale)
+                                               : __fdiv_rn(__fsub_rn(x, (float)sp.mean[c]), sd));
+    } else {
+        const double sd = sp.sd[c];
+        v = (double)x == sp.uv_special ? __dmul_rn(__dmul_rn(sd, -1.0), sp.uv_scale)
+                                       : __ddiv_rn(__dsub_rn((double)x, sp.mean[c]), sd);
+    }
     return __dmul_rn(v, sp.w[c]);
 }
 
@@ -273,7 +283,7 @@ namespace {
 int greedy_run(snk_db *db, const std::vector<greedy_meta> &meta, const double *d_targets, const float *d_unnorm,
                int64_t *d_paths, double *d_step_dist, int *d_flags, int *d_count, cudaStream_t st) {
     const int B = (int)meta.size();
-    const std_params stp{db->std_mean, db->std_sd, db->wt, db->uv_special, db->uv_scale};
+    const std_params stp{db->std_mean, db->std_sd, db->wt, db->uv_special, db->uv_scale, db->std_f32};
     const int m = db->m;
     const snk_space sp = snk_make_space(db, SNK_SPACE_JOINT);
     int64_t maxsteps = 0;
@@ -336,7 +346,7 @@ int snk_prepare_targets_dev(snk_db *db, const float *d_unnorm, int64_t rows, dou
     SNK_CHECK(db->std_set, "snk_db_set_standardisation has not been called");
     if (rows <= 0) return 0;
     SNK_CUDA(cudaSetDevice(db->device));
-    const std_params stp{db->std_mean, db->std_sd, db->wt, db->uv_special, db->uv_scale};
+    const std_params stp{db->std_mean, db->std_sd, db->wt, db->uv_special, db->uv_scale, db->std_f32};
     const int64_t total = rows * db->Dt;
     const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)db->sm_count * 8);
     prepare_targets_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_unnorm, total, db->Dt, stp, d_out);

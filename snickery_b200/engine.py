@@ -62,7 +62,7 @@ def load_library(path=None):
         "snk_topk_merge_dev": [i32, vp, vp, i32, i64, i32, vp, vp, vp],
         "snk_greedy_batch": [vp, P(dbl), P(i64), i32, P(i64), P(i64), P(dbl)],
         "snk_greedy_batch_dev": [vp, vp, P(i64), i32, P(i64), vp, vp, vp],
-        "snk_db_set_standardisation": [vp, P(dbl), P(dbl), dbl, dbl],
+        "snk_db_set_standardisation": [vp, P(dbl), P(dbl), dbl, dbl, C.c_uint],
         "snk_prepare_targets": [vp, P(flt), i64, P(dbl)],
         "snk_greedy_batch_unnorm": [vp, P(flt), P(i64), i32, P(i64), P(i64), P(dbl)],
         "snk_greedy_batch_unnorm_dev": [vp, vp, P(i64), i32, P(i64), vp, vp, vp],
@@ -82,6 +82,8 @@ def load_library(path=None):
     _lib = lib
     return lib
 
+
+STD_FLOAT32 = 1
 
 EXPORTED_SYMBOLS = ["snk_last_error", "snk_version", "snk_device_count", "snk_db_create", "snk_db_destroy",
                     "snk_db_info", "snk_db_set_weights", "snk_db_set_engine", "snk_db_counters", "snk_db_profile_enable",
@@ -178,13 +180,16 @@ class UnitDatabase:
         return dist, idx
 
     def set_standardisation(self, mean, std, special_uv_value=-1000.0, uv_scaling_factor=20.0):
-        """mean_vec_target / std_vec_target of the voice + the constants of const.py:12-14 (row N4)."""
+        """mean_vec_target / std_vec_target of the voice + the constants of const.py:12-14 (row N4).
+        float32 statistics (what the voice file holds) select numpy's float32 arithmetic, anything else float64."""
+        f32 = np.asarray(mean).dtype == np.float32 and np.asarray(std).dtype == np.float32
         mean = np.ascontiguousarray(np.asarray(mean, dtype=np.float64).reshape(-1))
         std = np.ascontiguousarray(np.asarray(std, dtype=np.float64).reshape(-1))
         if mean.size != self.Dt or std.size != self.Dt:
             raise ValueError("mean / std must have %d entries" % self.Dt)
         _check(load_library().snk_db_set_standardisation(self._h, _ptr(mean, C.c_double), _ptr(std, C.c_double),
-                                                         float(special_uv_value), float(uv_scaling_factor)))
+                                                         float(special_uv_value), float(uv_scaling_factor),
+                                                         STD_FLOAT32 if f32 else 0))
 
     def prepare_targets(self, unnorm):
         """weight(standardise(unnorm)) on the device: float32 [T, Dt] -> float64 [T, Dt]."""

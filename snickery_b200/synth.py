@@ -114,6 +114,24 @@ class Synthesiser:
             self.tree = GpuKDTree(None, _db=self.db, _space=engine.SPACE_TARGET)
 
     # ---- clocks, as the reference prints them (synth_simple.py:760-768)
+    @classmethod
+    def from_voice(cls, config, datafile, device=0, verbose=False):
+        """Load the reference's database dump (synth_simple.py:76-106) and build the resident
+        database from it.  The file's float32 mean_target / std_target become the device-side
+        standardisation, so un-normalised test speech can go straight to greedy_joint_search_unnorm_batch."""
+        from .hdf5_voice import load_voice
+        voice = load_voice(datafile)
+        names = voice.get("train_unit_names")
+        if names is not None:
+            names = [n.decode("ascii", "replace") if isinstance(n, bytes) else str(n) for n in names.tolist()]
+        self = cls(config, voice["train_unit_features"], voice["join_contexts"], device=device, verbose=verbose,
+                   train_unit_names=names)
+        self.train_filenames = voice.get("filenames")
+        self.unit_index_within_sentence = voice.get("unit_index_within_sentence_dset")
+        self.mean_vec_join, self.std_vec_join = voice["mean_join"], voice["std_join"]
+        self.set_standardisation(voice["mean_target"], voice["std_target"])
+        return self
+
     def start_clock(self, comment):
         if self.verbose:
             print("%s... " % comment, end="")
@@ -243,8 +261,8 @@ class Synthesiser:
     # ---- target preparation on the device (synth_simple.py:371-391)
     def set_standardisation(self, mean_vec_target, std_vec_target, special_uv_value=-1000.0, uv_scaling_factor=20.0):
         """The voice's mean_vec_target / std_vec_target (synth_simple.py:96-97) and const.py:12-14."""
-        self.mean_vec_target = np.asarray(mean_vec_target, dtype=np.float64)
-        self.std_vec_target = np.asarray(std_vec_target, dtype=np.float64)
+        self.mean_vec_target = np.asarray(mean_vec_target)      # dtype kept: float32 statistics -> float32 arithmetic
+        self.std_vec_target = np.asarray(std_vec_target)
         self.db.set_standardisation(self.mean_vec_target, self.std_vec_target, special_uv_value, uv_scaling_factor)
 
     def prepare_targets(self, unnorm_speech):

@@ -771,13 +771,16 @@ def _unnorm_speech(F, n_utts, T, seed):
     return utts, mean, std
 
 
-def test_prepare_targets_bit_exact():
+@pytest.mark.parametrize("stats_dtype", [np.float64, np.float32])
+def test_prepare_targets_bit_exact(stats_dtype):
     db = syn.make_epoch_db(n_units=3000, seed=77)
     cfg = epoch_config(multiepoch=4, jcw=0.3)
     o = O.OracleSynthesiser(cfg, db["F"], db["Jc"])
     g = Synthesiser(cfg, db["F"], db["Jc"])
     utts, mean, std = _unnorm_speech(db["F"], 3, 57, seed=5)
+    mean, std = mean.astype(stats_dtype), std.astype(stats_dtype)     # the voice file holds float32 statistics
     g.set_standardisation(mean, std)
+    assert O.standardise(utts[0], mean, std).dtype == stats_dtype
     for u in utts:
         ref = O.weight(O.standardise(u, mean, std), o.target_weight_vector)
         got = g.prepare_targets(u)
@@ -815,3 +818,32 @@ def test_greedy_from_unnormalised_speech():
     o2 = O.OracleSynthesiser(dict(cfg, join_cost_weight=0.6), db["F"], db["Jc"])
     feats2 = [O.weight(O.standardise(u, mean, std), o2.target_weight_vector) for u in utts]
     assert g.greedy_joint_search_unnorm_batch(utts) == g.greedy_joint_search_batch(feats2)
+
+
+# ------------------------------------------------------------------------------------ N3: voice file -> device
+def test_synthesiser_from_voice_file(tmp_path):
+    """A database dump in the reference's HDF5 layout loads into the resident database; its float32
+    mean / std drive the fused float32 standardisation (what numpy does with the file's arrays)."""
+    from snickery_b200.hdf5_voice import save_voice
+    db = syn.make_epoch_db(n_units=8000, seed=79)
+    utts, mean, std = _unnorm_speech(db["F"], 3, 60, seed=7)
+    mean, std = mean.astype(np.float32), std.astype(np.float32)
+    Dj = db["Jc"].shape[1]
+    path = str(tmp_path / "voice.hdf5")
+    save_voice(path, {"train_unit_features": db["F"], "join_contexts": db["Jc"], "mean_target": mean,
+                      "std_target": std, "mean_join": np.zeros(Dj // 4, np.float32),
+                      "std_join": np.ones(Dj // 4, np.float32)}, chunk_bytes=1 << 16)
+    cfg = epoch_config(multiepoch=6, jcw=0.2)
+    g = Synthesiser.from_voice(cfg, path)
+    assert g.number_of_units == 8000 and g.mean_vec_target.dtype == np.float32
+    o = O.OracleSynthesiser(cfg, db["F"], db["Jc"])
+    o.get_tree_for_greedy_search()
+    paths, dists = g.greedy_joint_search_unnorm_batch(utts, return_dists=True)
+    for u, p, d in zip(utts, paths, dists):
+        feats = O.weight(O.standardise(u, mean, std), o.target_weight_vector)     # float32 standardise, float64 weight
+        assert np.array_equal(g.prepare_targets(u), feats)
+        ref, rd = o.greedy_joint_search(feats, return_dists=True)
+        if p == ref:
+            np.testing.assert_allclose(d, rd, rtol=COST_RTOL)
+        else:
+            assert_greedy_path_ok(o, feats, p, d)

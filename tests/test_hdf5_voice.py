@@ -1,0 +1,90 @@
+"""Row N3: the voice-file reader.  Pinned against a file written by the real HDF5 library (a MATLAB 7.3
+MAT-file from scipy's test data, copied to tests/golden/libhdf5_testdouble.mat: user block, version-0
+superblock, symbol-table root group, contiguous float64 dataset); the voice schema itself is exercised
+through save_voice, which lays files out the way h5py's defaults do for train_simple.py:93-142."""
+import os
+
+import numpy as np
+import pytest
+
+from snickery_b200.hdf5_voice import Hdf5File, Hdf5FormatError, load_voice, save_voice
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def make_voice(N=1200, Dt=61, Dj=148, seed=0):
+    rng = np.random.default_rng(seed)
+    return {
+        "train_unit_features": rng.normal(size=(N, Dt)).astype(np.float32),
+        "join_contexts": rng.normal(size=(N + 1, Dj)).astype(np.float32),
+        "mean_target": rng.normal(size=Dt).astype(np.float32),
+        "std_target": rng.uniform(0.5, 2, size=Dt).astype(np.float32),
+        "mean_join": rng.normal(size=Dj // 4).astype(np.float32),
+        "std_join": rng.uniform(0.5, 2, size=Dj // 4).astype(np.float32),
+        "train_unit_names": np.array([b"a/b/c_L/d/e_%d" % i for i in range(N)], dtype="S50"),
+        "filenames": np.array([b"utt_%04d" % (i // 100) for i in range(N)], dtype="S50"),
+        "unit_index_within_sentence_dset": (np.arange(N) % 100).astype(np.int32),
+    }
+
+
+def test_reads_file_written_by_libhdf5():
+    f = Hdf5File(os.path.join(GOLDEN, "libhdf5_testdouble.mat"))
+    assert f.keys() == ["testdouble"]
+    info = f.info("testdouble")
+    assert info.layout == "contiguous" and info.dtype == np.float64
+    a = f["testdouble"]
+    # scipy's expectation for this test variable: pi/4 * arange(9); MATLAB stores it column-major
+    np.testing.assert_allclose(a.ravel(), np.pi / 4 * np.arange(9), rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(chunk_bytes=4096), dict(chunk_bytes=700, gzip=4, shuffle=True),
+                                dict(chunked=())])
+def test_voice_round_trip(tmp_path, kw):
+    v = make_voice()
+    path = str(tmp_path / "voice.hdf5")
+    save_voice(path, v, **kw)
+    f = Hdf5File(path)
+    assert sorted(f.keys()) == sorted(v)
+    w = load_voice(path)
+    for k in v:
+        assert w[k].dtype == v[k].dtype and w[k].shape == v[k].shape and np.array_equal(w[k], v[k]), k
+    if kw.get("chunk_bytes") == 700:       # one row per chunk: a three-level chunk index
+        assert f.info("join_contexts").chunk == (1, 148, 4) and len(f.info("join_contexts").filters) == 2
+    # reading into caller-provided (e.g. pinned) memory
+    out = np.empty(v["join_contexts"].shape, np.float32)
+    assert f.read("join_contexts", out=out) is out and np.array_equal(out, v["join_contexts"])
+    with pytest.raises(ValueError):
+        f.read("join_contexts", out=np.empty((3, 3), np.float32))
+
+
+def test_optional_magphase_and_empty(tmp_path):
+    v = make_voice(N=50)
+    v["mp_mag"] = np.random.default_rng(1).normal(size=(200, 33)).astype(np.float32)
+    v["mp_fz"] = np.zeros((0,), np.float32)
+    path = str(tmp_path / "v.hdf5")
+    save_voice(path, v)
+    w = load_voice(path)
+    assert np.array_equal(w["mp_mag"], v["mp_mag"]) and w["mp_fz"].shape == (0,)
+    assert "mp_mag" not in load_voice(path, optional=False)
+
+
+def test_errors(tmp_path):
+    p = str(tmp_path / "x.hdf5")
+    with open(p, "wb") as f:
+        f.write(b"not an hdf5 file" * 100)
+    with pytest.raises(Hdf5FormatError, match="signature"):
+        Hdf5File(p)
+    with open(p, "wb") as f:      # libver='latest' superblock
+        f.write(b"\x89HDF\r\n\x1a\n" + bytes([2, 8, 8, 0]) + b"\0" * 64)
+    with pytest.raises(Hdf5FormatError, match="superblock version 2"):
+        Hdf5File(p)
+    v = make_voice(N=20)
+    del v["join_contexts"]
+    save_voice(p, v)
+    with pytest.raises(Hdf5FormatError, match="join_contexts"):
+        load_voice(p)
+    v = make_voice(N=20)
+    v["join_contexts"] = v["join_contexts"][:-1]
+    save_voice(p, v)
+    with pytest.raises(Hdf5FormatError, match=r"N \+ 1"):
+        load_voice(p)
