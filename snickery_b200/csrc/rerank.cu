@@ -15,8 +15,26 @@
 
 namespace {
 
-constexpr int RR_THREADS = 256;
+constexpr int RR_THREADS = 256;      // block size for few queries (latency matters: more warps per query)
+constexpr int RR_THREADS_SMALL = 128;   // block size for many queries: 12 blocks per SM, so 1024 queries are one wave
 constexpr int RR_MAX_MERGE = 2048;   // most list entries a block merges in shared memory
+
+// (key, row id) packed so that one 64-bit compare orders by key, then id.  Padding entries (no row)
+// sort after every real one and stay distinct through their position.
+__device__ __forceinline__ unsigned long long pack_key(float v, int id) {
+    unsigned u = __float_as_uint(v + 0.0f);            // -0 -> +0
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);    // order-preserving map of IEEE floats to unsigned
+    return ((unsigned long long)u << 32) | (unsigned)id;
+}
+__device__ __forceinline__ unsigned long long pad_key(int pos) {
+    return 0xFFFFFFFF00000000ull | (0x80000000u + (unsigned)pos);
+}
+__device__ __forceinline__ void unpack_key(unsigned long long k, float &v, int &id) {
+    const unsigned hi = (unsigned)(k >> 32);
+    if (hi == 0xFFFFFFFFu) { v = INFINITY; id = INT_MAX; return; }
+    v = __uint_as_float((hi & 0x80000000u) ? (hi & 0x7FFFFFFFu) : ~hi);
+    id = (int)(unsigned)k;
+}
 
 struct rr_space {
     const float *A;    // Jc_raw
@@ -27,9 +45,6 @@ struct rr_space {
 };
 
 __device__ __forceinline__ bool dpair_lt(double v1, int i1, double v2, int i2) {
-    return v1 < v2 || (v1 == v2 && i1 < i2);
-}
-__device__ __forceinline__ bool fpair_lt(float v1, int i1, float v2, int i2) {
     return v1 < v2 || (v1 == v2 && i1 < i2);
 }
 
@@ -80,8 +95,8 @@ __device__ __forceinline__ void row_pair_dist(const rr_space &sp, const double *
     out1 = two ? a1 : INFINITY;
 }
 
-template <bool kMerge>
-__global__ void __launch_bounds__(RR_THREADS)
+template <bool kMerge, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict__ val, const int *__restrict__ id,
               int KP, int nlists, int lsz, int k, double *__restrict__ odist, int64_t *__restrict__ oidx,
               int64_t ostride, int64_t id_offset, int64_t nrows, const float *__restrict__ qerr,
@@ -95,75 +110,71 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
     double *d2 = wB_s + sp.dB;              // [KP]
     int *ids = reinterpret_cast<int *>(d2 + KP);          // [KP]
     float *sval = reinterpret_cast<float *>(ids + KP);    // [KP] approximate keys of the selected rows
-    const int nm = kMerge ? nlists * lsz : 0, nwin = kMerge ? (RR_THREADS / 32) * KP : 0;
-    float *mval = sval + KP;                               // kMerge: [n] all list keys, then [nwarp*KP] phase-1 winners
-    int *mid = reinterpret_cast<int *>(mval + nm + nwin);  // kMerge: [n] all list ids, then the winners' ids
-    __shared__ float s_wtau[RR_THREADS / 32];
+    // kMerge: [n] packed list entries, then [nwarp * KP] phase-1 winners
+    unsigned long long *mkey = reinterpret_cast<unsigned long long *>(sval + KP);
+    __shared__ float s_wtau[THREADS / 32];
 
     const int64_t ql = blockIdx.x;                    // index into the (compact) shortlist arrays
     const int64_t q = qsel ? qsel[ql] : ql;           // index into queries / outputs / per-query bounds
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = RR_THREADS >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = THREADS >> 5;
 
-    for (int d = tid; d < sp.D; d += RR_THREADS) q_s[d] = Q[q * (int64_t)sp.D + d];
-    for (int d = tid; d < sp.dA; d += RR_THREADS) wA_s[d] = sp.wA[sp.a_col + d];
-    for (int d = tid; d < sp.dB; d += RR_THREADS) wB_s[d] = sp.wB[d % sp.Dt];
+    for (int d = tid; d < sp.D; d += THREADS) q_s[d] = Q[q * (int64_t)sp.D + d];
+    for (int d = tid; d < sp.dA; d += THREADS) wA_s[d] = sp.wA[sp.a_col + d];
+    for (int d = tid; d < sp.dB; d += THREADS) wB_s[d] = sp.wB[d % sp.Dt];
 
     if (kMerge) {
         const int n = nlists * lsz;
         const float *gv = val + ql * (int64_t)n;
         const int *gi = id + ql * (int64_t)n;
-        for (int t = tid; t < n; t += RR_THREADS) {
-            const int i = gi[t];
-            mval[t] = i >= 0 ? gv[t] : INFINITY;
-            mid[t] = i >= 0 ? i : INT_MAX;
-        }
-        for (int t = tid; t < KP; t += RR_THREADS) { sval[t] = INFINITY; ids[t] = INT_MAX; }
-        __syncthreads();
+        for (int t = tid; t < KP; t += THREADS) { sval[t] = INFINITY; ids[t] = INT_MAX; }   // n may be < KP
         // a row dropped inside a list has a key >= that list's largest kept key
         float tl = INFINITY;
-        for (int l = tid; l < nlists; l += RR_THREADS) tl = fminf(tl, mval[l * lsz + lsz - 1]);
+        for (int t = tid; t < n; t += THREADS) {
+            const int i = gi[t];
+            const float v = gv[t];
+            mkey[t] = i >= 0 ? pack_key(v, i) : pad_key(t);
+            if (t % lsz == lsz - 1) tl = fminf(tl, i >= 0 ? v : INFINITY);
+        }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) tl = fminf(tl, __shfl_xor_sync(0xffffffffu, tl, off));
         if (lane == 0) s_wtau[warp] = tl;
+        __syncthreads();
+        // selection by rank counting: the packed entries are distinct, so ranks are a permutation
         if (n <= 256) {
-            for (int t = tid; t < n; t += RR_THREADS) {
-                const float v = mval[t];
-                const int i = mid[t];
+            for (int t = tid; t < n; t += THREADS) {
+                const unsigned long long me = mkey[t];
                 int rank = 0;
-                for (int j = 0; j < n; ++j)
-                    rank += (fpair_lt(mval[j], mid[j], v, i) || (mval[j] == v && mid[j] == i && j < t)) ? 1 : 0;
-                if (rank < KP) { sval[rank] = v; ids[rank] = i; }
+#pragma unroll 4
+                for (int j = 0; j < n; ++j) rank += mkey[j] < me ? 1 : 0;
+                if (rank < KP) unpack_key(me, sval[rank], ids[rank]);
             }
         } else {
             // two phases: every warp ranks its own slice and keeps the slice's KP smallest, then the
             // nwarp * KP winners are ranked.  An entry dropped in phase 1 is >= its slice's KP-th smallest,
             // hence >= the final KP-th smallest, so the final list's maximum still bounds every drop.
-            float *wv = mval + n;                       // [nwarp * KP] winners
-            int *wi = mid + n;
-            for (int t = tid; t < nwarp * KP; t += RR_THREADS) { wv[t] = INFINITY; wi[t] = INT_MAX; }
+            unsigned long long *wk = mkey + n;          // [nwarp * KP] winners
+            for (int t = tid; t < nwarp * KP; t += THREADS) wk[t] = pad_key(n + t);
             __syncthreads();
             const int ns = (n + nwarp - 1) / nwarp, s0 = warp * ns, s1 = min(n, s0 + ns);
             for (int t = s0 + lane; t < s1; t += 32) {
-                const float v = mval[t];
-                const int i = mid[t];
+                const unsigned long long me = mkey[t];
                 int rank = 0;
-                for (int j = s0; j < s1; ++j)
-                    rank += (fpair_lt(mval[j], mid[j], v, i) || (mval[j] == v && mid[j] == i && j < t)) ? 1 : 0;
-                if (rank < KP) { wv[warp * KP + rank] = v; wi[warp * KP + rank] = i; }
+#pragma unroll 4
+                for (int j = s0; j < s1; ++j) rank += mkey[j] < me ? 1 : 0;
+                if (rank < KP) wk[warp * KP + rank] = me;
             }
             __syncthreads();
             const int nw = nwarp * KP;
-            for (int t = tid; t < nw; t += RR_THREADS) {
-                const float v = wv[t];
-                const int i = wi[t];
+            for (int t = tid; t < nw; t += THREADS) {
+                const unsigned long long me = wk[t];
                 int rank = 0;
-                for (int j = 0; j < nw; ++j)
-                    rank += (fpair_lt(wv[j], wi[j], v, i) || (wv[j] == v && wi[j] == i && j < t)) ? 1 : 0;
-                if (rank < KP) { sval[rank] = v; ids[rank] = i; }
+#pragma unroll 4
+                for (int j = 0; j < nw; ++j) rank += wk[j] < me ? 1 : 0;
+                if (rank < KP) unpack_key(me, sval[rank], ids[rank]);
             }
         }
     } else {
-        for (int t = tid; t < KP; t += RR_THREADS) {
+        for (int t = tid; t < KP; t += THREADS) {
             const int i = id[ql * KP + t];
             sval[t] = i >= 0 ? val[ql * KP + t] : INFINITY;
             ids[t] = i >= 0 ? i : INT_MAX;
@@ -188,7 +199,7 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
     }
     __syncthreads();
 
-    for (int t = tid; t < KP; t += RR_THREADS) {
+    for (int t = tid; t < KP; t += THREADS) {
         const double v = d2[t];
         const int i = ids[t];
         int rank = 0;
@@ -209,7 +220,7 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
                 if (!full) mx = INFINITY;                       // the final merge dropped nothing
                 if (tau_extra) mx = fminf(mx, tau_extra[q]);    // ... but an earlier stage may have
                 if (kMerge)
-                    for (int w = 0; w < RR_THREADS / 32; ++w) mx = fminf(mx, s_wtau[w]);
+                    for (int w = 0; w < THREADS / 32; ++w) mx = fminf(mx, s_wtau[w]);
                 int good = 1;
                 if (mx < INFINITY) {
                     const float qq = qn ? qn[q] : 0.f;
@@ -244,6 +255,9 @@ size_t rr_smem(const rr_space &rs, int KP, int nmerge) {
            (nmerge ? (size_t)(RR_THREADS / 32) * KP * 8 : 0) + 16;
 }
 
+// many queries: small blocks (one wave of 12 per SM); few queries: large blocks (shorter chain per query)
+bool rr_small_blocks(const snk_db *db, int64_t nq) { return nq > (int64_t)6 * db->sm_count; }
+
 }  // namespace
 
 int snk_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, const float *d_val,
@@ -255,10 +269,15 @@ int snk_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, co
     SNK_CHECK(k <= KP, "rerank: k (%d) exceeds shortlist (%d)", k, KP);
     const rr_space rs = make_rr(db, sp);
     const size_t smem = rr_smem(rs, KP, 0);
-    rerank_kernel<false><<<(unsigned)nq, RR_THREADS, smem, st>>>(rs, dQ, d_val, d_id, KP, 0, 0, k, d_dist, d_idx,
-                                                                   out_stride, id_offset, sp.rows, d_qerr, d_dberr,
-                                                                   d_qn, d_maxn, d_tau_extra, d_cert, d_nfail, sticky,
-                                                                   d_qsel, d_cert ? db->debug_fail_mod : 0);
+    const int dbg = d_cert ? db->debug_fail_mod : 0;
+    if (rr_small_blocks(db, nq))
+        rerank_kernel<false, RR_THREADS_SMALL><<<(unsigned)nq, RR_THREADS_SMALL, smem, st>>>(
+            rs, dQ, d_val, d_id, KP, 0, 0, k, d_dist, d_idx, out_stride, id_offset, sp.rows, d_qerr, d_dberr, d_qn,
+            d_maxn, d_tau_extra, d_cert, d_nfail, sticky, d_qsel, dbg);
+    else
+        rerank_kernel<false, RR_THREADS><<<(unsigned)nq, RR_THREADS, smem, st>>>(
+            rs, dQ, d_val, d_id, KP, 0, 0, k, d_dist, d_idx, out_stride, id_offset, sp.rows, d_qerr, d_dberr, d_qn,
+            d_maxn, d_tau_extra, d_cert, d_nfail, sticky, d_qsel, dbg);
     SNK_CUDA(cudaGetLastError());
     db->counters[2] += 1;
     return 0;
@@ -276,10 +295,15 @@ int snk_merge_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t 
     SNK_CHECK(snk_merge_rerank_fits(nlists, lsz), "merge_rerank: %d list entries exceed the in-block merge", nlists * lsz);
     const rr_space rs = make_rr(db, sp);
     const size_t smem = rr_smem(rs, KP, nlists * lsz);
-    rerank_kernel<true><<<(unsigned)nq, RR_THREADS, smem, st>>>(rs, dQ, d_lval, d_lid, KP, nlists, lsz, k, d_dist,
-                                                                  d_idx, out_stride, id_offset, sp.rows, d_qerr,
-                                                                  d_dberr, d_qn, d_maxn, nullptr, d_cert, d_nfail, sticky,
-                                                                  nullptr, d_cert ? db->debug_fail_mod : 0);
+    const int dbg = d_cert ? db->debug_fail_mod : 0;
+    if (rr_small_blocks(db, nq))
+        rerank_kernel<true, RR_THREADS_SMALL><<<(unsigned)nq, RR_THREADS_SMALL, smem, st>>>(
+            rs, dQ, d_lval, d_lid, KP, nlists, lsz, k, d_dist, d_idx, out_stride, id_offset, sp.rows, d_qerr, d_dberr,
+            d_qn, d_maxn, nullptr, d_cert, d_nfail, sticky, nullptr, dbg);
+    else
+        rerank_kernel<true, RR_THREADS><<<(unsigned)nq, RR_THREADS, smem, st>>>(
+            rs, dQ, d_lval, d_lid, KP, nlists, lsz, k, d_dist, d_idx, out_stride, id_offset, sp.rows, d_qerr, d_dberr,
+            d_qn, d_maxn, nullptr, d_cert, d_nfail, sticky, nullptr, dbg);
     SNK_CUDA(cudaGetLastError());
     db->counters[2] += 1;
     return 0;
