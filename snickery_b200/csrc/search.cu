@@ -46,16 +46,17 @@ __global__ void cvt_q32_kernel(const double *__restrict__ Q, int D, int64_t nq, 
 }
 
 // fp16 query operand in K-block order + squared norm of the rounded query + rounding error norm.
-// One warp per (padded) query row.
-__global__ void cvt_q16_kernel(const double *__restrict__ Q, int D, int64_t nq, int64_t nq_pad,
-                               const short *__restrict__ qmap, int ld16, __half *__restrict__ out,
-                               float *__restrict__ qn, float *__restrict__ qerr) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t q = warp; q < nq_pad; q += nwarp) {
+// One block of CVT_THREADS per (padded) query row: a row is only ~600 columns, so a warp per row would
+// walk it in ~18 dependent gathers; four warps finish in five.
+constexpr int CVT_THREADS = 128;
+__global__ void __launch_bounds__(CVT_THREADS)
+cvt_q16_kernel(const double *__restrict__ Q, int D, int64_t nq, int64_t nq_pad, const short *__restrict__ qmap,
+               int ld16, __half *__restrict__ out, float *__restrict__ qn, float *__restrict__ qerr) {
+    __shared__ float red[2][CVT_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t q = blockIdx.x; q < nq_pad; q += gridDim.x) {
         float n2 = 0.f, e2 = 0.f;
-        for (int c = lane; c < ld16; c += 32) {
+        for (int c = threadIdx.x; c < ld16; c += CVT_THREADS) {
             __half h = __float2half_rn(0.f);
             const int d = qmap[c];
             if (q < nq && d == -2) h = __float2half_rn(-0.5f);   // multiplies the norm pieces embedded in the row
@@ -74,10 +75,15 @@ __global__ void cvt_q16_kernel(const double *__restrict__ Q, int D, int64_t nq, 
             n2 += __shfl_xor_sync(0xffffffffu, n2, off);
             e2 += __shfl_xor_sync(0xffffffffu, e2, off);
         }
-        if (lane == 0 && q < nq) {
-            qn[q] = n2;
-            qerr[q] = sqrtf(e2);
+        if (lane == 0) { red[0][warp] = n2; red[1][warp] = e2; }
+        __syncthreads();
+        if (threadIdx.x == 0 && q < nq) {
+            float a = 0.f, b = 0.f;
+            for (int w = 0; w < CVT_THREADS / 32; ++w) { a += red[0][w]; b += red[1][w]; }
+            qn[q] = a;
+            qerr[q] = sqrtf(b);
         }
+        __syncthreads();
     }
 }
 
@@ -153,8 +159,8 @@ int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, d
         int *id = (int *)(val + (size_t)qn_ * KP);
         const double *Qb = dQ + qb * sp.D;
 
-        cvt_q16_kernel<<<db->sm_count * 4, 256, 0, st>>>(Qb, sp.D, qn_, qpad, snk_tc_qmap(db, space), ld16, q16, qn,
-                                                         qerr);
+        cvt_q16_kernel<<<(unsigned)std::min<int64_t>(qpad, (int64_t)db->sm_count * 16), CVT_THREADS, 0, st>>>(
+            Qb, sp.D, qn_, qpad, snk_tc_qmap(db, space), ld16, q16, qn, qerr);
         SNK_CUDA(cudaGetLastError());
         db->counters[2] += 1;
         snk_tc_lists lists;
