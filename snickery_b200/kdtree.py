@@ -100,3 +100,31 @@ class GpuStashableKDTree(GpuKDTree):
             raise ValueError("query data dimension must match training data dimension")
         d, i = self._db.knn(X, int(k), self._space)
         return (d, i) if return_distance else i
+
+    # ---- persistence (StashableKDTree.py:43-83)
+    def save_hdf(self, fname):
+        """Stash the tree in the reference's HDF5 layout: ``state_0`` holds the data matrix, ``int_values`` the
+        seven integers of sklearn's state.  There is no tree to store, so ``state_1..3`` (sklearn's index /
+        node arrays) are written empty: the file round-trips through this class, not through sklearn."""
+        from .hdf5_voice import save_voice
+        if self.data is None:
+            raise ValueError("this tree is a view over a resident database and holds no data matrix of its own")
+        data = np.ascontiguousarray(self.data, dtype=np.float64)
+        ints = np.array([40, 0, 0, 0, 0, 0, 0], dtype=np.int64)       # leaf_size, n_levels, n_nodes, n_trims, ...
+        save_voice(fname, {"state_0": data, "state_1": np.zeros((0,), np.int64), "state_2": np.zeros((0,), np.float64),
+                           "state_3": np.zeros((0,), np.float64), "int_values": ints}, chunked=())
+
+    @classmethod
+    def load_hdf(cls, fname, device=0):
+        """Rebuild from a stash: only ``state_0`` (the data matrix, StashableKDTree.py:15) is needed -- files
+        written by the reference's sklearn-backed class load as well (their node arrays are skipped)."""
+        from .hdf5_voice import Hdf5File
+        f = Hdf5File(fname)
+        if "state_0" not in f:
+            raise ValueError("%s is not a StashableKDTree stash (no state_0)" % fname)
+        return cls(f["state_0"], device=device)
+
+
+def resurrect_tree(fname, device=0):
+    """StashableKDTree.py:97-102."""
+    return GpuStashableKDTree.load_hdf(fname, device=device)

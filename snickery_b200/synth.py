@@ -267,15 +267,20 @@ class Synthesiser:
 
     def prepare_targets(self, unnorm_speech):
         """weight(standardise(unnorm_speech), target_weight_vector): compose_speech's float32 output in,
-        the float64 unit_features of synth_utt out (full width; truncated columns carry zero weight)."""
+        the float64 unit_features of synth_utt out (full width; truncated columns carry zero weight).
+        With REPLICATE_IS2018_EXP the first and the last frame are dropped (synth_simple.py:384-387)."""
         self._push_weights()
-        return self.db.prepare_targets(unnorm_speech)
+        return self.db.prepare_targets(self._trim_speech(unnorm_speech))
+
+    def _trim_speech(self, unnorm_speech):
+        u = np.asarray(unnorm_speech, dtype=np.float32)
+        return u[1:-1, :] if self.config.get("REPLICATE_IS2018_EXP", False) else u
 
     def greedy_joint_search_unnorm_batch(self, unnorm_speech_list, start_states=None, return_dists=False):
         """greedy_joint_search straight from un-normalised speech: standardise + weight are fused into the
         device-side query assembly, so the host does no per-utterance numpy and uploads float32."""
         self._push_weights()
-        feats = [np.asarray(u, dtype=np.float32) for u in unnorm_speech_list]
+        feats = [self._trim_speech(u) for u in unnorm_speech_list]
         return self.db.greedy_batch(feats, start_states, return_dists=return_dists, unnorm=True)
 
     # ---- preselection (synth_halfphone.py:1359-1366, 1346-1351)

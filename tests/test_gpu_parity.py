@@ -847,3 +847,39 @@ def test_synthesiser_from_voice_file(tmp_path):
             np.testing.assert_allclose(d, rd, rtol=COST_RTOL)
         else:
             assert_greedy_path_ok(o, feats, p, d)
+
+
+def test_stashable_tree_save_and_resurrect(tmp_path):
+    """StashableKDTree.py:43-102: save_hdf / resurrect_tree round trip gives the same neighbours."""
+    from snickery_b200.kdtree import resurrect_tree
+    rng = np.random.default_rng(11)
+    data = rng.normal(size=(3000, 20))
+    tree = GpuStashableKDTree(data, leaf_size=100, metric="euclidean")
+    q = rng.normal(size=(17, 20))
+    d0, i0 = tree.query(q, k=5)
+    path = str(tmp_path / "tree.hdf5")
+    tree.save_hdf(path)
+    again = resurrect_tree(path)
+    d1, i1 = again.query(q, k=5)
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+    rd, ri = O.brute_force_knn(data.astype(np.float32).astype(np.float64), q, 5)
+    assert_knn_matches(d0, i0, rd, ri)
+
+
+def test_replicate_is2018_variant():
+    """REPLICATE_IS2018_EXP (config/IS2018_nick_simplified.cfg:4; synth_simple.py:384-387): the first and the last
+    target frame are dropped before the search."""
+    db = syn.make_epoch_db(n_units=6000, seed=80)
+    cfg = epoch_config(multiepoch=6, jcw=0.2, tsw=(0.5, 0.5))
+    cfg["REPLICATE_IS2018_EXP"] = True
+    o = O.OracleSynthesiser(cfg, db["F"], db["Jc"])
+    o.get_tree_for_greedy_search()
+    g = Synthesiser(cfg, db["F"], db["Jc"])
+    utts, mean, std = _unnorm_speech(db["F"], 2, 62, seed=8)
+    g.set_standardisation(mean, std)
+    paths, dists = g.greedy_joint_search_unnorm_batch(utts, return_dists=True)
+    for u, p, d in zip(utts, paths, dists):
+        feats = O.weight(O.standardise(u, mean, std)[1:-1, :], o.target_weight_vector)
+        assert np.array_equal(g.prepare_targets(u), feats)
+        assert len(p) == 60 // 6
+        assert_greedy_path_ok(o, feats, p, d)

@@ -88,3 +88,24 @@ def test_errors(tmp_path):
     save_voice(p, v)
     with pytest.raises(Hdf5FormatError, match=r"N \+ 1"):
         load_voice(p)
+
+
+def test_stash_with_unsupported_member(tmp_path, monkeypatch):
+    """A StashableKDTree stash written by the reference holds sklearn's node array as a compound dataset; the
+    reader must still open the file and serve state_0 (all the GPU tree needs), failing only on access."""
+    import struct
+    from snickery_b200 import hdf5_voice
+    real = hdf5_voice._dtype_message
+
+    def fake(dt):   # float32 members get a compound (class 6) datatype message
+        if np.dtype(dt) == np.float32:
+            return struct.pack("<BBBBI", 0x16, 1, 0, 0, 4)
+        return real(dt)
+    monkeypatch.setattr(hdf5_voice, "_dtype_message", fake)
+    data = np.random.default_rng(3).normal(size=(40, 7))
+    path = str(tmp_path / "stash.hdf5")
+    save_voice(path, {"state_0": data, "state_2": np.zeros(9, np.float32), "int_values": np.arange(7)}, chunked=())
+    f = Hdf5File(path)
+    assert np.array_equal(f["state_0"], data) and np.array_equal(f["int_values"], np.arange(7))
+    with pytest.raises(Hdf5FormatError, match="datatype class 6"):
+        f["state_2"]
