@@ -342,6 +342,8 @@ def run_ours(args):
                          "flops_per_launch": prof["work"] / max(prof["launches"], 1),
                          "kernel_share_of_step": prof["ms"] / (ms_max / args.steps)},
             "exactness": {"queries": int(c1["queries"] - c0["queries"]), "recertified_by_simt": int(recert)},
+            "rates": {"search_steps_per_s": value / MULTIEPOCH, "utterances_per_s": value / T,
+                      "frames_per_utterance": int(T), "multiepoch": MULTIEPOCH},
         }
     if world > 1:
         dist.barrier()
