@@ -464,7 +464,8 @@ int snk_join_viterbi_batch_dev(snk_db *db, const int64_t *d_cand, const double *
         for (int b = 0; b < B; ++b) maxT = std::max(maxT, lens[b]);
         int bp_frames = 0;
         if (K <= 254 && maxT * K + maxT * 4 <= 24 * 1024 && !getenv("SNK_VIT_NOBPSMEM")) bp_frames = (int)maxT;
-        const size_t bp_bytes = bp_frames ? (((size_t)bp_frames * K + 3) & ~(size_t)3) + (size_t)bp_frames * 4 : 0;
+        size_t bp_bytes = bp_frames ? (((size_t)bp_frames * K + 3) & ~(size_t)3) + (size_t)bp_frames * 4 : 0;
+        if (2 * per_stage + 3 * K * sizeof(float) + bp_bytes > 224 * 1024) { bp_frames = 0; bp_bytes = 0; }   // widest tiles: no room
         // a third tile stage only if all B utterances stay resident in a single wave with it (measured:
         // a second wave costs far more than the deeper prefetch gains)
         if (!getenv("SNK_VIT_STAGES") && nst == 3) {
