@@ -198,13 +198,15 @@ __global__ void viterbi_kernel(const vit_meta *__restrict__ meta, const int64_t 
     extern __shared__ __align__(16) float vsm[];
     const int KK = K * K;
     const int KKp = (KK + 3) & ~3;
+    const int Kp2 = (K + 1) & ~1;
     float *tile_s = vsm;                       // [VIT_STAGES][KKp]
-    float *dcur = vsm + VIT_STAGES * KKp;      // [K] cost of reaching state a (arcs 0..t-1 consumed)
-    float *dnext = dcur + K;                   // [K]
-    float *Dt_s = dnext + K;                   // [K] target cost row t as float32
+    // per state a: {cost of reaching a (arcs 0..t-1 consumed), target cost D[t, a] as float32}, interleaved so
+    // that the relaxation reads both (for two states) with one 16-byte broadcast load
+    float2 *dcur = reinterpret_cast<float2 *>(vsm + VIT_STAGES * KKp);   // [Kp2]
+    float2 *dnext = dcur + Kp2;                                          // [Kp2]
     // shared-memory mirror of the backpointers (the HBM copy is still written): the back-trace is a chain of
     // T dependent reads, far cheaper from shared memory.  Used when the utterance fits (bp_smem_frames).
-    unsigned char *bp_s = reinterpret_cast<unsigned char *>(Dt_s + K);          // [bp_smem_frames][K]
+    unsigned char *bp_s = reinterpret_cast<unsigned char *>(dnext + Kp2);       // [bp_smem_frames][K]
     int *col_s = reinterpret_cast<int *>(bp_s + (((size_t)bp_smem_frames * K + 3) & ~(size_t)3));   // [bp_smem_frames]
     __shared__ double s_red[2][32];
     __shared__ float s_best;
@@ -239,27 +241,37 @@ __global__ void viterbi_kernel(const vit_meta *__restrict__ meta, const int64_t 
     };
     for (int s = 0; s < VIT_STAGES - 1; ++s) prefetch(s);
 
-    if (c < K) dcur[c] = admissible(cand[f0 * K + c], N) ? 0.f : INFINITY;
+    if (c < K) dcur[c].x = admissible(cand[f0 * K + c], N) ? 0.f : INFINITY;
     float d_next_row = c < K ? (float)tdist[f0 * K + c] : 0.f;
     for (int64_t t = 0; t < T - 1; ++t) {
         prefetch(t + VIT_STAGES - 1);
         if (c < K) {
-            Dt_s[c] = d_next_row;
+            dcur[c].y = d_next_row;
             d_next_row = (float)tdist[(f0 + t + 1) * K + c];   // next step's target costs, a step early
         }
         cp_async_wait<VIT_STAGES - 1>();                        // tile t has landed (for this thread's copies)
-        __syncthreads();                                        // ... and for everyone's; Dt_s / dcur visible
+        __syncthreads();                                        // ... and for everyone's; dcur visible
         if (c < K) {
             const float *tile = tile_s + (size_t)(t % VIT_STAGES) * KKp;
             float best = INFINITY;
             int arg = -1;
+            int a = 0;
 #pragma unroll 5
-            for (int a = 0; a < K; ++a) {
-                const float arc = Dt_s[a] + tile[a * K + c];   // Times(target arc, join arc)
-                const float v = dcur[a] + arc;                  // Times(distance so far, arc)
+            for (; a + 1 < K; a += 2) {
+                const float4 q = *reinterpret_cast<const float4 *>(dcur + a);   // {d[a], D[a], d[a+1], D[a+1]}
+                const float arc0 = q.y + tile[a * K + c];       // Times(target arc, join arc)
+                const float v0 = q.x + arc0;                    // Times(distance so far, arc)
+                if (v0 < best) { best = v0; arg = a; }
+                const float arc1 = q.w + tile[(a + 1) * K + c];
+                const float v1 = q.z + arc1;
+                if (v1 < best) { best = v1; arg = a + 1; }
+            }
+            if (a < K) {
+                const float2 q = dcur[a];
+                const float v = q.x + (q.y + tile[a * K + c]);
                 if (v < best) { best = v; arg = a; }
             }
-            dnext[c] = best;
+            dnext[c].x = best;
             bp[(f0 + t + 1) * K + c] = (short)arg;
             if (bp_local) bp_s[(t + 1) * K + c] = (unsigned char)(arg < 0 ? 255 : arg);
         }
@@ -270,7 +282,7 @@ __global__ void viterbi_kernel(const vit_meta *__restrict__ meta, const int64_t 
                 float bv = INFINITY;
                 int bi = -1;
                 for (int a = c; a < K; a += 32)
-                    if (dnext[a] < bv) { bv = dnext[a]; bi = a; }
+                    if (dnext[a].x < bv) { bv = dnext[a].x; bi = a; }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
                     const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
@@ -280,20 +292,20 @@ __global__ void viterbi_kernel(const vit_meta *__restrict__ meta, const int64_t 
                 if (c == 0) s_arg = bi;
             }
             __syncthreads();
-            if (c < K && c != s_arg) dnext[c] = INFINITY;
+            if (c < K && c != s_arg) dnext[c].x = INFINITY;
             __syncthreads();
         }
-        float *tmp = dcur; dcur = dnext; dnext = tmp;
+        float2 *tmp = dcur; dcur = dnext; dnext = tmp;
     }
     cp_async_wait<0>();
     // final arc: D[T-1, a] + 0 (exit arcs carry no weight, fst_functions_wrapped.py:206-208)
-    if (c < K) Dt_s[c] = d_next_row;
+    if (c < K) dcur[c].y = d_next_row;
     __syncthreads();
     if (c < 32) {
         float bv = INFINITY;
         int bi = -1;
         for (int a = c; a < K; a += 32) {
-            const float v = dcur[a] + (Dt_s[a] + 0.f);
+            const float v = dcur[a].x + (dcur[a].y + 0.f);
             if (v < bv) { bv = v; bi = a; }
         }
 #pragma unroll
@@ -457,7 +469,7 @@ int snk_join_viterbi_batch_dev(snk_db *db, const int64_t *d_cand, const double *
         const size_t per_stage = (size_t)((K * K + 3) & ~3) * sizeof(float);
         int nst = 3;                                      // tiles in flight ahead of the DP front
         if (const char *e = getenv("SNK_VIT_STAGES")) nst = atoi(e);
-        while (nst > 2 && nst * per_stage + 3 * K * sizeof(float) > 200 * 1024) --nst;
+        while (nst > 2 && nst * per_stage + 4 * ((K + 1) & ~1) * sizeof(float) > 200 * 1024) --nst;
         nst = std::max(2, std::min(nst, 5));
         // shared-memory backpointer mirror for utterances up to bp_frames frames (K <= 254: one byte each)
         int64_t maxT = 0;
@@ -465,15 +477,15 @@ int snk_join_viterbi_batch_dev(snk_db *db, const int64_t *d_cand, const double *
         int bp_frames = 0;
         if (K <= 254 && maxT * K + maxT * 4 <= 24 * 1024 && !getenv("SNK_VIT_NOBPSMEM")) bp_frames = (int)maxT;
         size_t bp_bytes = bp_frames ? (((size_t)bp_frames * K + 3) & ~(size_t)3) + (size_t)bp_frames * 4 : 0;
-        if (2 * per_stage + 3 * K * sizeof(float) + bp_bytes > 224 * 1024) { bp_frames = 0; bp_bytes = 0; }   // widest tiles: no room
+        if (2 * per_stage + 4 * ((K + 1) & ~1) * sizeof(float) + bp_bytes > 224 * 1024) { bp_frames = 0; bp_bytes = 0; }   // widest tiles: no room
         // a third tile stage only if all B utterances stay resident in a single wave with it (measured:
         // a second wave costs far more than the deeper prefetch gains)
         if (!getenv("SNK_VIT_STAGES") && nst == 3) {
-            const size_t s3 = 3 * per_stage + 3 * K * sizeof(float) + bp_bytes + 1024;
+            const size_t s3 = 3 * per_stage + 4 * ((K + 1) & ~1) * sizeof(float) + bp_bytes + 1024;
             const int64_t resident = (int64_t)std::min<size_t>(32, (227 * 1024) / s3) * db->sm_count;
             if (resident < B) nst = 2;
         }
-        const size_t vsmem = nst * per_stage + 3 * K * sizeof(float) + bp_bytes;
+        const size_t vsmem = nst * per_stage + 4 * ((K + 1) & ~1) * sizeof(float) + bp_bytes;
 #define SNK_LAUNCH_VIT(NST_)                                                                                              \
     do {                                                                                                                \
         SNK_CUDA(cudaFuncSetAttribute(viterbi_kernel<NST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));     \
