@@ -132,8 +132,10 @@ int snk_apply_weights(snk_db *db, cudaStream_t st);
 int snk_shortlist_simt(snk_db *db, const snk_space &sp, const float *dQ32, int ldq, int64_t nq, int KP,
                        float *d_val, int *d_id, cudaStream_t st);
 // generic row-wise top-KP scan (see knn_simt.cu)
+// d_seg_cnt (optional): the row is n / seg_cap buffers of seg_cap slots, only the first d_seg_cnt[q, buffer] filled
 int snk_topk_scan(snk_db *db, const float *d_vals, const int *d_ids, int64_t nq, int64_t n, int64_t ld,
-                  int id_base, int KP, bool init, float *d_val, int *d_id, cudaStream_t st);
+                  int id_base, int KP, bool init, float *d_val, int *d_id, cudaStream_t st,
+                  const int *d_seg_cnt = nullptr, int seg_cap = 0);
 
 // ---- knn_tc.cu : tcgen05 shortlist
 bool snk_tc_supported(const snk_db *db, const snk_space &sp, int KP);

@@ -153,10 +153,13 @@ struct warp_list {
 
 // grid (nsplit, nq), block 32.  vals [nq, ld] (first n valid); ids optional (same layout).
 // out [nq, nsplit, KP].  If init == false and nsplit == 1 the existing out list is merged in.
+// Segmented rows (seg_cnt != nullptr; ids required): the row is n / seg_cap buffers of seg_cap slots of which only
+// the first seg_cnt[q, buffer] are filled (the emit epilogue of knn_tc.cu); the unfilled tails are never read.
 template <int E>
 __global__ void __launch_bounds__(32)
 topk_scan_kernel(const float *__restrict__ vals, const int *__restrict__ ids, int64_t n, int64_t ld,
-                 int id_base, bool init, float *__restrict__ oval, int *__restrict__ oid) {
+                 int id_base, bool init, float *__restrict__ oval, int *__restrict__ oid,
+                 const int *__restrict__ seg_cnt, int seg_cap) {
     constexpr int KP = 32 * E;
     const int lane = threadIdx.x;
     const int64_t q = blockIdx.y;
@@ -178,22 +181,35 @@ topk_scan_kernel(const float *__restrict__ vals, const int *__restrict__ ids, in
     }
     const float *row = vals + q * ld;
     const int *irow = ids ? ids + q * ld : nullptr;
-    for (int64_t base = beg; base < end; base += 128) {
-        float v[4];
-        int id[4];
+    auto consume = [&](int64_t from, int64_t to) {
+        for (int64_t base = from; base < to; base += 128) {
+            float v[4];
+            int id[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t p = base + j * 32 + lane;
-            v[j] = INFINITY;
-            id[j] = INT_MAX;
-            if (p < end) {
-                v[j] = __ldg(row + p);
-                id[j] = irow ? __ldg(irow + p) : (int)(id_base + p);
-                if (id[j] < 0) v[j] = INFINITY;
+            for (int j = 0; j < 4; ++j) {
+                const int64_t p = base + j * 32 + lane;
+                v[j] = INFINITY;
+                id[j] = INT_MAX;
+                if (p < to) {
+                    v[j] = __ldg(row + p);
+                    id[j] = irow ? __ldg(irow + p) : (int)(id_base + p);
+                    if (id[j] < 0) v[j] = INFINITY;
+                }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) L.offer_lanes(v[j], id[j]);
+            for (int j = 0; j < 4; ++j) L.offer_lanes(v[j], id[j]);
+        }
+    };
+    if (seg_cnt) {
+        const int nseg = (int)(n / seg_cap);
+        const int per = (nseg + nsplit - 1) / nsplit;
+        const int s1 = min(nseg, (s + 1) * per);
+        for (int seg = s * per; seg < s1; ++seg) {
+            const int64_t from = (int64_t)seg * seg_cap;
+            consume(from, from + min(seg_cap, seg_cnt[q * nseg + seg]));
+        }
+    } else {
+        consume(beg, end);
     }
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -204,18 +220,18 @@ topk_scan_kernel(const float *__restrict__ vals, const int *__restrict__ ids, in
 
 template <int E>
 void launch_scan(const float *vals, const int *ids, int64_t nq, int64_t n, int64_t ld, int id_base,
-                 int nsplit, bool init, float *oval, int *oid, cudaStream_t st) {
+                 int nsplit, bool init, float *oval, int *oid, const int *seg_cnt, int seg_cap, cudaStream_t st) {
     dim3 grid(nsplit, (unsigned)nq);
-    topk_scan_kernel<E><<<grid, 32, 0, st>>>(vals, ids, n, ld, id_base, init, oval, oid);
+    topk_scan_kernel<E><<<grid, 32, 0, st>>>(vals, ids, n, ld, id_base, init, oval, oid, seg_cnt, seg_cap);
 }
 
 int scan_dispatch(int KP, const float *vals, const int *ids, int64_t nq, int64_t n, int64_t ld, int id_base,
-                  int nsplit, bool init, float *oval, int *oid, cudaStream_t st) {
+                  int nsplit, bool init, float *oval, int *oid, const int *seg_cnt, int seg_cap, cudaStream_t st) {
     switch (KP) {
-    case 32: launch_scan<1>(vals, ids, nq, n, ld, id_base, nsplit, init, oval, oid, st); break;
-    case 64: launch_scan<2>(vals, ids, nq, n, ld, id_base, nsplit, init, oval, oid, st); break;
-    case 128: launch_scan<4>(vals, ids, nq, n, ld, id_base, nsplit, init, oval, oid, st); break;
-    case 256: launch_scan<8>(vals, ids, nq, n, ld, id_base, nsplit, init, oval, oid, st); break;
+    case 32: launch_scan<1>(vals, ids, nq, n, ld, id_base, nsplit, init, oval, oid, seg_cnt, seg_cap, st); break;
+    case 64: launch_scan<2>(vals, ids, nq, n, ld, id_base, nsplit, init, oval, oid, seg_cnt, seg_cap, st); break;
+    case 128: launch_scan<4>(vals, ids, nq, n, ld, id_base, nsplit, init, oval, oid, seg_cnt, seg_cap, st); break;
+    case 256: launch_scan<8>(vals, ids, nq, n, ld, id_base, nsplit, init, oval, oid, seg_cnt, seg_cap, st); break;
     default: snk_set_error("shortlist size %d not supported (32/64/128/256)", KP); return 1;
     }
     SNK_CUDA(cudaGetLastError());
@@ -225,19 +241,22 @@ int scan_dispatch(int KP, const float *vals, const int *ids, int64_t nq, int64_t
 }  // namespace
 
 int snk_topk_scan(snk_db *db, const float *d_vals, const int *d_ids, int64_t nq, int64_t n, int64_t ld,
-                  int id_base, int KP, bool init, float *d_val, int *d_id, cudaStream_t st) {
+                  int id_base, int KP, bool init, float *d_val, int *d_id, cudaStream_t st, const int *d_seg_cnt,
+                  int seg_cap) {
     if (nq <= 0) return 0;
     SNK_CHECK(nq <= 65535, "topk scan: too many queries per launch (%lld)", (long long)nq);
+    SNK_CHECK(!d_seg_cnt || (d_ids && seg_cap > 0 && n % seg_cap == 0), "topk scan: bad segment description");
     // split long rows over several warps when there are few queries
     int nsplit = 1;
     const int64_t want_warps = (int64_t)db->sm_count * 16;
     if (nq < want_warps && n > 4096) {
         nsplit = (int)std::min<int64_t>(snk_cdiv(want_warps, nq), snk_cdiv(n, 2048));
+        if (d_seg_cnt) nsplit = (int)std::min<int64_t>(nsplit, n / seg_cap);
         if (nsplit < 1) nsplit = 1;
     }
     if (nsplit == 1) {
         db->counters[2] += 1;
-        return scan_dispatch(KP, d_vals, d_ids, nq, n, ld, id_base, 1, init, d_val, d_id, st);
+        return scan_dispatch(KP, d_vals, d_ids, nq, n, ld, id_base, 1, init, d_val, d_id, d_seg_cnt, seg_cap, st);
     }
     // two-level: nsplit partial lists per query, then one more scan over them that also merges the
     // carried-in list (init == false)
@@ -245,8 +264,9 @@ int snk_topk_scan(snk_db *db, const float *d_vals, const int *d_ids, int64_t nq,
     float *pv = (float *)db->ws_misc.p;
     int *pi = (int *)(pv + (size_t)nq * nsplit * KP);
     db->counters[2] += 2;
-    SNK_TRY(scan_dispatch(KP, d_vals, d_ids, nq, n, ld, id_base, nsplit, true, pv, pi, st));
-    SNK_TRY(scan_dispatch(KP, pv, pi, nq, (int64_t)nsplit * KP, (int64_t)nsplit * KP, 0, 1, init, d_val, d_id, st));
+    SNK_TRY(scan_dispatch(KP, d_vals, d_ids, nq, n, ld, id_base, nsplit, true, pv, pi, d_seg_cnt, seg_cap, st));
+    SNK_TRY(scan_dispatch(KP, pv, pi, nq, (int64_t)nsplit * KP, (int64_t)nsplit * KP, 0, 1, init, d_val, d_id, nullptr, 0,
+                          st));
     return 0;
 }
 

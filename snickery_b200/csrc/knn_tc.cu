@@ -80,6 +80,7 @@ struct tc_params {
     const float *thr;       // [nq]
     float *bufv;            // [nq_pad, nchunks * split, cap]
     int *bufi;
+    int *bufn;              // [nq_pad, nchunks * split] filled slots of every buffer
     int cap;
     float *tau;             // [nq] preset to thr; a buffer overflow writes -inf (certificate must fail)
 };
@@ -591,7 +592,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 }
             }
         }
-        if (MODE == MODE_EMIT && ecnt > p.cap && q < p.nq) p.tau[q] = -INFINITY;   // rows were lost: never certify
+        if (MODE == MODE_EMIT) {
+            p.bufn[((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half] = min(ecnt, p.cap);
+            if (ecnt > p.cap && q < p.nq) p.tau[q] = -INFINITY;   // rows were lost: never certify
+        }
         if (MODE == MODE_LIST) {
             float *ov = p.oval + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * LSZ;
             int *oi = p.oid + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * LSZ;
@@ -998,13 +1002,15 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         const int cap = getenv("SNK_TC_EMIT_CAP") ? atoi(getenv("SNK_TC_EMIT_CAP")) :
                         (int)snk_round_up(std::min<int64_t>(2048, std::max<int64_t>(256, (int64_t)20 * k)), 32);
         const size_t nent = (size_t)nq_pad * nlists * cap;
-        SNK_TRY(snk_buf_reserve(&db->ws_tc, nent * 8));
+        SNK_TRY(snk_buf_reserve(&db->ws_tc, nent * 8 + (size_t)nq_pad * nlists * 4));
         p.bufv = (float *)db->ws_tc.p;
         p.bufi = (int *)(p.bufv + nent);
+        p.bufn = p.bufi + nent;
         p.cap = cap; p.thr = thr; p.tau = d_tau;
         p.row_lo = 0; p.row_hi = sp.rows; p.nchunks = nchunks;
         p.chunk_rows = snk_cdiv(row_tiles, nchunks) * BN;
-        SNK_CUDA(cudaMemsetAsync(p.bufi, 0xFF, nent * 4, st));     // unused slots read as id -1
+        // every (query, chunk, part) buffer gets its fill count from the kernel: no clearing, and the scan
+        // below touches only filled slots
         {
             snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)sp.rows * sp.D, st);
             SNK_TRY(launch_tc(pick_kernel(MODE_EMIT, 4, h.sched), ws.nqt_pad * nchunks, num_threads_of(h.sched), smem, st, mapQ,
@@ -1016,7 +1022,7 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
             const int64_t n = std::min<int64_t>(32768, nq - q0);
             SNK_TRY(snk_topk_scan(db, p.bufv + (size_t)q0 * nlists * cap, p.bufi + (size_t)q0 * nlists * cap, n,
                                   (int64_t)nlists * cap, (int64_t)nlists * cap, 0, KP, true, d_val + q0 * KP, d_id + q0 * KP,
-                                  st));
+                                  st, p.bufn + (size_t)q0 * nlists, cap));
         }
         return 0;
     }
