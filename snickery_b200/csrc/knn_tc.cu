@@ -76,6 +76,8 @@ struct tc_params {
     float *odist;           // store : [nq, ldo] keys of the scanned tiles, compacted (tile_stride > 1 = sample)
     int64_t ldo;
     int tile_stride;        // scan every tile_stride-th tile of a chunk (1 = all)
+    int flush_tiles, nparts;   // list mode: hand the lists out and start afresh every flush_tiles tiles (nparts per chunk;
+                               // 0 / 1 = one list set per chunk).  Output [nq_pad, nchunks * nparts * split, LSZ]
     // emit mode: every row whose key is <= thr[q] is appended to the (query, chunk, half) buffer
     const float *thr;       // [nq]
     float *bufv;            // [nq_pad, nchunks * split, cap]
@@ -493,7 +495,18 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         int ecnt = 0;
         float *ebv = MODE == MODE_EMIT ? p.bufv + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * p.cap : nullptr;
         int *ebi = MODE == MODE_EMIT ? p.bufi + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * p.cap : nullptr;
+        // list mode: lists may be handed out several times per chunk (sampling pass of the larger-k path)
+        const int NP = (MODE == MODE_LIST && p.nparts > 1) ? p.nparts : 1;
+        int part = 0;
+        auto flush_lists = [&](int r) {
+            const size_t slot = (((size_t)q * p.nchunks + chunk) * NP + r) * EPI_SPLIT + half;
+            float *ov = p.oval + slot * LSZ;
+            int *oi = p.oid + slot * LSZ;
+#pragma unroll
+            for (int i = 0; i < LSZ; ++i) { ov[i] = lv[i]; oi[i] = li[i]; lv[i] = INFINITY; li[i] = -1; }
+        };
         for (int t = 0; t < ntiles; ++t) {
+            if (MODE == MODE_LIST && NP > 1 && t > 0 && t % p.flush_tiles == 0 && part + 1 < NP) flush_lists(part++);
             const int acc = t & 1;
             const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
             const int64_t r0 = row_beg + (int64_t)t * tstep;
@@ -597,10 +610,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             if (ecnt > p.cap && q < p.nq) p.tau[q] = -INFINITY;   // rows were lost: never certify
         }
         if (MODE == MODE_LIST) {
-            float *ov = p.oval + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * LSZ;
-            int *oi = p.oid + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * LSZ;
-#pragma unroll
-            for (int i = 0; i < LSZ; ++i) { ov[i] = lv[i]; oi[i] = li[i]; }
+            flush_lists(part);
+            for (int r = part + 1; r < NP; ++r) flush_lists(r);     // parts this chunk had no tiles for: empty lists
         }
     }
     tc_fence_before();
@@ -987,7 +998,43 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
     // Rows above the bound cannot be among the k nearest, so the bound itself is the certificate's tau.
     constexpr int SAMPLE = 8;
     if (!getenv("SNK_TC_NOEMIT") && sp.rows / SAMPLE >= (int64_t)16 * k && row_tiles >= 4 * SAMPLE) {
-        SNK_TRY(store_scan(SAMPLE, KP, d_val, d_id));
+        {
+            // Sampling pass in list mode: every SAMPLE-th tile, the 8 smallest keys per (query, chunk part, column
+            // range), lists handed out `parts` times per chunk so that their union holds >= 2k + 16 actual rows.
+            // The k-th smallest of ANY set of actual rows bounds the k-th smallest overall from above, so the
+            // k-th of that union is a valid (and, with 2k+ entries, tight) threshold -- and no key goes to HBM.
+            const int lsz = 8;
+            const int64_t stiles = snk_cdiv(row_tiles, SAMPLE);
+            const tc_split ss = make_split(db, h, nqt, stiles);
+            const int per_chunk = ss.nchunks * epi_split_of(h.sched) * lsz;
+            int parts = 1;
+            while (per_chunk * parts < 2 * k + 16 && parts < 32) parts *= 2;
+            const int64_t chunk_tiles = snk_cdiv(stiles, ss.nchunks);
+            p.cluster = ss.cluster;
+            p.tile_stride = SAMPLE;
+            p.row_lo = 0; p.row_hi = sp.rows; p.nchunks = ss.nchunks;
+            p.chunk_rows = chunk_tiles * BN * SAMPLE;
+            p.nparts = parts;
+            p.flush_tiles = (int)std::max<int64_t>(1, snk_cdiv(chunk_tiles, parts));
+            const int nl = ss.nchunks * parts * epi_split_of(h.sched);
+            const size_t nlist = (size_t)nq_pad * nl * lsz;
+            SNK_TRY(snk_buf_reserve(&db->ws_dist, nlist * 8));
+            p.oval = (float *)db->ws_dist.p;
+            p.oid = (int *)(p.oval + nlist);
+            {
+                snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)stiles * BN * sp.D, st);
+                SNK_TRY(launch_tc(pick_kernel(MODE_LIST, lsz, h.sched), ss.nqt_pad * ss.nchunks, num_threads_of(h.sched), smem,
+                                  st, mapQ, s, p));
+            }
+            SNK_CUDA(cudaGetLastError());
+            db->counters[2] += 1;
+            for (int64_t q0 = 0; q0 < nq; q0 += 32768) {
+                const int64_t n = std::min<int64_t>(32768, nq - q0);
+                SNK_TRY(snk_topk_scan(db, p.oval + (size_t)q0 * nl * lsz, p.oid + (size_t)q0 * nl * lsz, n, (int64_t)nl * lsz,
+                                      (int64_t)nl * lsz, 0, KP, true, d_val + q0 * KP, d_id + q0 * KP, st));
+            }
+            p.tile_stride = 1; p.nparts = 0; p.flush_tiles = 0; p.oval = nullptr; p.oid = nullptr;
+        }
         SNK_TRY(snk_buf_reserve(&db->ws_misc, (size_t)nq_pad * 4));
         float *thr = (float *)db->ws_misc.p;
         kth_select_kernel<<<(unsigned)snk_cdiv(nq * 32, 256), 256, 0, st>>>(d_val, d_id, nq, KP, k, thr, d_tau);
