@@ -20,7 +20,8 @@
 //    mbarrier ring; two TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
 //  * for the shapes the reference ships the ring and the K-block sequence are compile-time
 //    schedules (sched_traits); other shapes run a table-driven variant of the same kernel.
-//  * three epilogues: MODE_LIST (register lists of the 4 / 8 best per query, k <= 4), MODE_STORE
+//  * epilogues: MODE_LIST (register lists of the 4 / 8 best per query, k <= 4; MODE_PARTS hands the lists out
+//    several times per chunk for the sampling pass of larger k), MODE_STORE
 //    (keys to HBM, small databases and the sampling pass of larger k), MODE_EMIT (append every row
 //    at or below a per-query bound; larger k).
 //  * each CTA scans one (query tile, database chunk) pair; per-chunk results are merged by
@@ -86,7 +87,7 @@ struct tc_params {
     int cap;
     float *tau;             // [nq] preset to thr; a buffer overflow writes -inf (certificate must fail)
 };
-constexpr int MODE_LIST = 0, MODE_STORE = 1, MODE_EMIT = 2;
+constexpr int MODE_LIST = 0, MODE_STORE = 1, MODE_EMIT = 2, MODE_PARTS = 3;   // PARTS: LIST with several list sets per chunk
 // half-box tensor maps of the multicast path: each CTA of a pair fetches half of every database tile
 struct tc_maps_mc { CUtensorMap S_h, G_h, Gslab72; };
 constexpr int MC_ROWS0 = 72;   // rows of a frame slab fetched by rank 0 (9 swizzle atoms); rank 1 takes the other 64
@@ -496,7 +497,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         float *ebv = MODE == MODE_EMIT ? p.bufv + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * p.cap : nullptr;
         int *ebi = MODE == MODE_EMIT ? p.bufi + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * p.cap : nullptr;
         // list mode: lists may be handed out several times per chunk (sampling pass of the larger-k path)
-        const int NP = (MODE == MODE_LIST && p.nparts > 1) ? p.nparts : 1;
+        const int NP = (MODE == MODE_PARTS && p.nparts > 1) ? p.nparts : 1;
         int part = 0;
         auto flush_lists = [&](int r) {
             const size_t slot = (((size_t)q * p.nchunks + chunk) * NP + r) * EPI_SPLIT + half;
@@ -506,7 +507,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             for (int i = 0; i < LSZ; ++i) { ov[i] = lv[i]; oi[i] = li[i]; lv[i] = INFINITY; li[i] = -1; }
         };
         for (int t = 0; t < ntiles; ++t) {
-            if (MODE == MODE_LIST && NP > 1 && t > 0 && t % p.flush_tiles == 0 && part + 1 < NP) flush_lists(part++);
+            if (MODE == MODE_PARTS && NP > 1 && t > 0 && t % p.flush_tiles == 0 && part + 1 < NP) flush_lists(part++);
             const int acc = t & 1;
             const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
             const int64_t r0 = row_beg + (int64_t)t * tstep;
@@ -609,7 +610,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             p.bufn[((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half] = min(ecnt, p.cap);
             if (ecnt > p.cap && q < p.nq) p.tau[q] = -INFINITY;   // rows were lost: never certify
         }
-        if (MODE == MODE_LIST) {
+        if (MODE == MODE_LIST || MODE == MODE_PARTS) {
             flush_lists(part);
             for (int r = part + 1; r < NP; ++r) flush_lists(r);     // parts this chunk had no tiles for: empty lists
         }
@@ -800,6 +801,7 @@ tc_kernel_fn pick_sched(int sched) {
 tc_kernel_fn pick_kernel(int mode, int lsz, int sched) {
     if (mode == MODE_STORE) return pick_sched<MODE_STORE, 4>(sched);
     if (mode == MODE_EMIT) return pick_sched<MODE_EMIT, 4>(sched);
+    if (mode == MODE_PARTS) return pick_sched<MODE_PARTS, 8>(sched);
     return lsz == 4 ? pick_sched<MODE_LIST, 4>(sched) : pick_sched<MODE_LIST, 8>(sched);
 }
 
@@ -868,8 +870,8 @@ int snk_tc_prepare(snk_db *db) {
         if (s->sp[sp].ok) s->smem[sp] = s->sp[sp].smem;
     }
     for (int sched : {0, 2, 11, 13, 14, 16})
-        for (int v = 0; v < 4; ++v)
-            SNK_CUDA(cudaFuncSetAttribute((const void *)pick_kernel(v == 2 ? MODE_STORE : (v == 3 ? MODE_EMIT : MODE_LIST),
+        for (int v = 0; v < 5; ++v)
+            SNK_CUDA(cudaFuncSetAttribute((const void *)pick_kernel(v == 2 ? MODE_STORE : v == 3 ? MODE_EMIT : v == 4 ? MODE_PARTS : MODE_LIST,
                                                                     v == 1 ? 8 : 4, sched),
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return 0;
@@ -1023,7 +1025,7 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
             p.oid = (int *)(p.oval + nlist);
             {
                 snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)stiles * BN * sp.D, st);
-                SNK_TRY(launch_tc(pick_kernel(MODE_LIST, lsz, h.sched), ss.nqt_pad * ss.nchunks, num_threads_of(h.sched), smem,
+                SNK_TRY(launch_tc(pick_kernel(MODE_PARTS, lsz, h.sched), ss.nqt_pad * ss.nchunks, num_threads_of(h.sched), smem,
                                   st, mapQ, s, p));
             }
             SNK_CUDA(cudaGetLastError());
