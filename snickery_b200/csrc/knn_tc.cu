@@ -196,10 +196,15 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-// three-input minimum (sm_100)
+// three-input minimum / maximum (sm_100)
 __device__ __forceinline__ float min3(float a, float b, float c) {
     float r;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
 
@@ -490,9 +495,15 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < LSZ; ++i) { lv[i] = INFINITY; li[i] = -1; }
         const bool embed = SCHED != 0 || p.embed != 0;
+        // Static schedules always embed the norms, so key = -2 * accumulator.  Lists, votes and thresholds then work on
+        // HALF keys (-accumulator, a sign flip the compiler folds into the comparisons; the group minimum is a max3 tree
+        // over the raw accumulators) and the exact factor 2 is applied only to the few values that leave the kernel:
+        // 32 multiplies per 32-column chunk and thread less, same bits out.
+        constexpr bool HALFKEY = SCHED != 0 && MODE != MODE_STORE;
+        constexpr float OSCALE = HALFKEY ? 2.f : 1.f;
         float nrm_next = (!embed && et < BN && ntiles > 0 && row_beg + et < row_end) ? __ldg(p.nrm + row_beg + et) : INFINITY;
         // emit mode state
-        const float thr = (MODE == MODE_EMIT && q < p.nq) ? p.thr[q] : -INFINITY;
+        const float thr = (MODE == MODE_EMIT && q < p.nq) ? p.thr[q] * (HALFKEY ? 0.5f : 1.f) : -INFINITY;
         int ecnt = 0;
         float *ebv = MODE == MODE_EMIT ? p.bufv + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * p.cap : nullptr;
         int *ebi = MODE == MODE_EMIT ? p.bufi + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * p.cap : nullptr;
@@ -504,7 +515,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             float *ov = p.oval + slot * LSZ;
             int *oi = p.oid + slot * LSZ;
 #pragma unroll
-            for (int i = 0; i < LSZ; ++i) { ov[i] = lv[i]; oi[i] = li[i]; lv[i] = INFINITY; li[i] = -1; }
+            for (int i = 0; i < LSZ; ++i) { ov[i] = OSCALE * lv[i]; oi[i] = li[i]; lv[i] = INFINITY; li[i] = -1; }
         };
         for (int t = 0; t < ntiles; ++t) {
             if (MODE == MODE_PARTS && NP > 1 && t > 0 && t % p.flush_tiles == 0 && part + 1 < NP) flush_lists(part++);
@@ -533,23 +544,33 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 }
                 // key = ||y~||^2 - 2 x~.y~ : with embedded norms the accumulator already holds x.y - ||y||^2 / 2
                 float key[32];
-                if (embed) {
+                if constexpr (HALFKEY) {
+                    if (partial) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) key[j] = -2.f * v[j];
+                        for (int j = 0; j < 32; ++j)
+                            if (r0 + c0 + j >= row_end) v[j] = -INFINITY;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) key[j] = -v[j];     // folded into the consumers as a source modifier
                 } else {
+                    if (embed) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) key[j] = fmaf(-2.f, v[j], nrm_s[acc * BN + c0 + j]);
-                }
-                if (partial) {
+                        for (int j = 0; j < 32; ++j) key[j] = -2.f * v[j];
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (r0 + c0 + j >= row_end) key[j] = INFINITY;
+                        for (int j = 0; j < 32; ++j) key[j] = fmaf(-2.f, v[j], nrm_s[acc * BN + c0 + j]);
+                    }
+                    if (partial) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (r0 + c0 + j >= row_end) key[j] = INFINITY;
+                    }
                 }
                 if (MODE == MODE_EMIT) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         if (key[j] <= thr) {
-                            if (ecnt < p.cap) { ebv[ecnt] = key[j]; ebi[ecnt] = (int)(r0 + c0 + j); }
+                            if (ecnt < p.cap) { ebv[ecnt] = OSCALE * key[j]; ebi[ecnt] = (int)(r0 + c0 + j); }
                             ++ecnt;
                         }
                     }
@@ -568,8 +589,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     float g[4];
 #pragma unroll
                     for (int gi = 0; gi < 4; ++gi) {
-                        const float *k8 = key + 8 * gi;
-                        g[gi] = min3(min3(k8[0], k8[1], k8[2]), min3(k8[3], k8[4], k8[5]), fminf(k8[6], k8[7]));
+                        if constexpr (HALFKEY) {     // min of the half keys = -(max of the accumulators)
+                            const float *a8 = v + 8 * gi;
+                            g[gi] = -max3(max3(a8[0], a8[1], a8[2]), max3(a8[3], a8[4], a8[5]), fmaxf(a8[6], a8[7]));
+                        } else {
+                            const float *k8 = key + 8 * gi;
+                            g[gi] = min3(min3(k8[0], k8[1], k8[2]), min3(k8[3], k8[4], k8[5]), fminf(k8[6], k8[7]));
+                        }
                     }
                     const float cmin = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
                     if (__any_sync(0xffffffffu, cmin < lv[LSZ - 1])) {
