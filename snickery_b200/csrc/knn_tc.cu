@@ -71,6 +71,8 @@ struct tc_params {
     int64_t chunk_rows;     // multiple of BN
     int nchunks;
     int64_t nq;
+    const __half *q16;      // the query operand rows (SCHED 26 reads the frame part straight into tensor memory)
+    int ldq16;
     const float *nrm;       // [rows] squared norms of the fp16 rows
     float *oval;            // fused : [nq_pad, nchunks * split, LSZ] keys (ascending)
     int *oid;               //         row ids
@@ -164,6 +166,26 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with the A operand in tensor memory (128 lanes = rows, two fp16 per 32-bit column)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 columns from registers into tensor memory (the warp's own lane quarter)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -231,16 +253,29 @@ constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >
 //   SR   : slots per join-part load.  One is enough when a tile keeps the tensor pipe busy for longer than a load
 //          takes to arrive (multiepoch 4, 6); shorter tiles (multiepoch 1, 3) need the second slot, and have the
 //          shared memory for it because their query tile is smaller
-template <int SCHED> struct sched_traits { static constexpr int NS = 0, KSL = 0, TB = 0, KTL = 0, M = 1, GR = 1, SR = 1; };
+//   ATM  : the frame part of the query operand lives in tensor memory (see SCHED 26)
+template <int SCHED> struct sched_traits {
+    static constexpr int NS = 0, KSL = 0, TB = 0, KTL = 0, M = 1, GR = 1, SR = 1;
+    static constexpr bool ATM = false;
+};
 template <int M_> struct joint_traits {   // joint 151 | M x 61
     static constexpr int NS = 3, KSL = 2, TB = 1, KTL = 4, M = M_, GR = 2, SR = M_ <= 3 ? 2 : 1;
+    static constexpr bool ATM = false;
 };
-template <> struct sched_traits<2> { static constexpr int NS = 0, KSL = 0, TB = 3, KTL = 4, M = 1, GR = 2, SR = 1; };   // target 184
+template <> struct sched_traits<2> {   // target 184
+    static constexpr int NS = 0, KSL = 0, TB = 3, KTL = 4, M = 1, GR = 2, SR = 1;
+    static constexpr bool ATM = false;
+};
 // SCHED 10 + m: the joint space at the multiepoch values the reference's configs use (config/*.cfg: 6, 1, 4, 3)
 template <> struct sched_traits<11> : joint_traits<1> {};
 template <> struct sched_traits<13> : joint_traits<3> {};
 template <> struct sched_traits<14> : joint_traits<4> {};
 template <> struct sched_traits<16> : joint_traits<6> {};
+// SCHED 26: multiepoch 6 with the six frame blocks of the query tile held in TENSOR MEMORY (192 columns next to the two
+// accumulators) instead of shared memory.  A 128x128x16 UTCHMMA with both operands in shared memory reads 8 KB per 64
+// cycles -- all of an SM's shared-memory bandwidth, with TMA writing into the same banks -- and ncu shows the tensor pipe
+// waiting on operand fetch ~20 % of the time.  With A in tensor memory 24 of the 34 UTCHMMAs of a tile read only B.
+template <> struct sched_traits<26> : joint_traits<6> { static constexpr bool ATM = true; };
 template <int SCHED> struct sched_layout {
     using S = sched_traits<SCHED>;
     static constexpr int GBYTES = S::M > 1 ? SLOT_BYTES : TILE_BYTES;
@@ -264,15 +299,20 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     const uint32_t sbase = smem_u32(smem_raw);                        // SWIZZLE_128B tiles need 1024 B alignment
     if (sbase & 1023u) __trap();
     uint8_t *gbase = smem_raw;
+    constexpr bool ATM = sched_traits<SCHED>::ATM;
+    const int NKB = ATM ? sched_traits<SCHED>::NS : p.nkb;            // query K-blocks resident in shared memory
+    constexpr uint32_t TCOLS = ATM ? 512u : TMEM_COLS;
+    constexpr uint32_t ATM_COL = 2 * BN;                              // first tensor-memory column of the A frames
     const uint32_t sA = sbase;
-    const uint32_t sB = sA + (uint32_t)p.nkb * TILE_BYTES;
+    const uint32_t sB = sA + (uint32_t)NKB * TILE_BYTES;
     const int STAGES = p.stages;
     const uint32_t sBar = sB + (uint32_t)p.b_bytes;
     // barriers: full[MAX_STAGES] empty[MAX_STAGES] a_full tmem_full[2] tmem_empty[2]
     const uint32_t bar_full = sBar, bar_empty = sBar + 8 * MAX_STAGES, bar_a = sBar + 16 * MAX_STAGES;
     const uint32_t bar_tfull = bar_a + 8, bar_tempty = bar_tfull + 16;
     const uint32_t s_tmem_ptr = bar_tempty + 16;
-    uint8_t *g_after = gbase + (size_t)p.nkb * TILE_BYTES + (size_t)p.b_bytes + 16 * MAX_STAGES + 8 + 32;
+    const uint32_t bar_atm = s_tmem_ptr + 8;                          // A frames have been written to tensor memory
+    uint8_t *g_after = gbase + (size_t)NKB * TILE_BYTES + (size_t)p.b_bytes + 16 * MAX_STAGES + 8 + 32;
     volatile uint32_t *tmem_ptr_g = reinterpret_cast<volatile uint32_t *>(g_after);
     float *nrm_s = reinterpret_cast<float *>(g_after + 24);           // [2][BN], 16-byte aligned (table-driven path only)
     uint4 *sub_s = reinterpret_cast<uint4 *>(g_after + 24 + 2 * BN * 4);   // [MAXSUB] {a start addr >> 4, b byte offset, ksteps, -}
@@ -297,13 +337,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             mbar_init(bar_empty + 8 * s, (uint32_t)p.cluster);   // one commit per CTA sharing the slot
         }
         mbar_init(bar_a, 1);
+        if (ATM) mbar_init(bar_atm, 128 * epi_split_of(SCHED));
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
             mbar_init(bar_tempty + 8 * a, NUM_EPI_THREADS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(s_tmem_ptr, TMEM_COLS);
+    if (warp == 1) tmem_alloc(s_tmem_ptr, TCOLS);
     tc_fence_before();
     __syncthreads();
     if (p.cluster > 1) cluster_sync_all();     // the peer's barriers exist before anything is multicast at them
@@ -317,8 +358,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             tma_prefetch_desc(&mapS);
             tma_prefetch_desc(&mapG);
             tma_prefetch_desc(&mapGslab);
-            mbar_expect_tx(bar_a, (uint32_t)p.nkb * TILE_BYTES);
-            for (int kb = 0; kb < p.nkb; ++kb)
+            mbar_expect_tx(bar_a, (uint32_t)NKB * TILE_BYTES);
+            for (int kb = 0; kb < NKB; ++kb)
                 tma_load_2d(sA + kb * TILE_BYTES, &mapQ, kb * BK, qt * BM, bar_a);
         }
         __syncwarp();
@@ -397,6 +438,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             __syncwarp();
         }
         mbar_wait(bar_a, 0);
+        if (ATM) mbar_wait(bar_atm, 0);
         tc_fence_after();
         constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
         if constexpr (SCHED != 0) {
@@ -436,9 +478,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                         for (int j = 0; j < S::M; ++j) {
                             const uint32_t al = a0 + (S::NS + j * S::TB + b) * (TILE_BYTES >> 4);
 #pragma unroll
-                            for (int ks = 0; ks < (b == S::TB - 1 ? S::KTL : 4); ++ks)   // window offset j = +j rows = +8 in the field
-                                umma_f16(d_tmem, DESC_HI | (uint64_t)(al + 2 * ks), DESC_HI | (uint64_t)(bl + 8 * j + 2 * ks),
-                                         IDESC, (S::NS + b + j + ks) != 0 ? 1u : 0u);
+                            for (int ks = 0; ks < (b == S::TB - 1 ? S::KTL : 4); ++ks) {   // window offset j = +j rows = +8 in the field
+                                if constexpr (ATM)   // A block (j, b): 32 columns of tensor memory, 8 per UMMA_K step
+                                    umma_f16_ts(d_tmem, tmem_base + ATM_COL + (uint32_t)((j * S::TB + b) * (BK / 2) + ks * 8),
+                                                DESC_HI | (uint64_t)(bl + 8 * j + 2 * ks), IDESC, (S::NS + b + j + ks) != 0 ? 1u : 0u);
+                                else
+                                    umma_f16(d_tmem, DESC_HI | (uint64_t)(al + 2 * ks), DESC_HI | (uint64_t)(bl + 8 * j + 2 * ks),
+                                             IDESC, (S::NS + b + j + ks) != 0 ? 1u : 0u);
+                            }
                         }
                         if (p.cluster > 1) umma_commit_mc(bar_empty + bar, cmask);
                         else umma_commit(bar_empty + bar);
@@ -494,6 +541,27 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         int li[LSZ];
 #pragma unroll
         for (int i = 0; i < LSZ; ++i) { lv[i] = INFINITY; li[i] = -1; }
+        if constexpr (ATM) {
+            // this thread's query row, frame part (K-blocks NS .. of the operand row): its half of the 32-bit columns
+            using S = sched_traits<SCHED>;
+            constexpr int ACOLS = S::M * S::TB * (BK / 2);            // 192 for multiepoch 6
+            constexpr int PER = ACOLS / EPI_SPLIT;                    // columns written by this thread
+            static_assert(PER % 32 == 0, "A frames must split into x32 stores");
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(p.q16 + q * (int64_t)p.ldq16 + S::NS * BK) + half * PER;
+#pragma unroll
+            for (int i = 0; i < PER / 32; ++i) {
+                uint32_t r[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4 *>(src + i * 32) + j);
+                    r[4 * j] = u.x; r[4 * j + 1] = u.y; r[4 * j + 2] = u.z; r[4 * j + 3] = u.w;
+                }
+                tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ATM_COL + (uint32_t)(half * PER + i * 32), r);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_atm);
+        }
         const bool embed = SCHED != 0 || p.embed != 0;
         // Static schedules always embed the norms, so key = -2 * accumulator.  Lists, votes and thresholds then work on
         // HALF keys (-accumulator, a sign flip the compiler folds into the comparisons; the group minimum is a max3 tree
@@ -644,7 +712,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (p.cluster > 1) cluster_sync_all();     // the peer may still multicast into this CTA's ring / arrive on its barriers
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
 }
 
 // per query: tau = min over chunks of the chunk list's largest key (a row dropped inside a chunk has a
@@ -784,7 +852,7 @@ int build_space(snk_db *db, int space, tc_space_host *h) {
     if (!getenv("SNK_TC_NOSCHED") && h->embed) {
         if (space == SNK_SPACE_JOINT && (slab || m == 1) && (m == 1 || m == 3 || m == 4 || m == 6) && tblocks == 1 &&
             Dt + 3 > 48 && db->Djq + 3 > 144 && db->Djq + 3 <= 160)
-            h->sched = 10 + m;
+            h->sched = (m == 6 && getenv("SNK_TC_ATMEM")) ? 26 : 10 + m;
         else if (space == SNK_SPACE_TARGET && tblocks == 3 && Dt + 3 > 176)
             h->sched = 2;
     }
@@ -795,6 +863,7 @@ int build_space(snk_db *db, int space, tc_space_host *h) {
     case 13: h->b_bytes = sched_layout<13>::B_BYTES; h->stages = sched_layout<13>::NSLOT; break;
     case 14: h->b_bytes = sched_layout<14>::B_BYTES; h->stages = sched_layout<14>::NSLOT; break;
     case 16: h->b_bytes = sched_layout<16>::B_BYTES; h->stages = sched_layout<16>::NSLOT; break;
+    case 26: h->b_bytes = sched_layout<26>::B_BYTES; h->stages = sched_layout<26>::NSLOT; break;
     default: break;
     }
     if (h->sched != 0 && (size_t)h->nkb * TILE_BYTES + h->b_bytes + aux_bytes(h->sched) > budget) h->sched = 0;
@@ -821,6 +890,7 @@ tc_kernel_fn pick_sched(int sched) {
     case 13: return knn_tc_kernel<MODE, LSZ, 13>;
     case 14: return knn_tc_kernel<MODE, LSZ, 14>;
     case 16: return knn_tc_kernel<MODE, LSZ, 16>;
+    case 26: return knn_tc_kernel<MODE, LSZ, 26>;
     default: return knn_tc_kernel<MODE, LSZ, 0>;
     }
 }
@@ -895,7 +965,7 @@ int snk_tc_prepare(snk_db *db) {
         SNK_TRY(build_space(db, sp, &s->sp[sp]));
         if (s->sp[sp].ok) s->smem[sp] = s->sp[sp].smem;
     }
-    for (int sched : {0, 2, 11, 13, 14, 16})
+    for (int sched : {0, 2, 11, 13, 14, 16, 26})
         for (int v = 0; v < 5; ++v)
             SNK_CUDA(cudaFuncSetAttribute((const void *)pick_kernel(v == 2 ? MODE_STORE : v == 3 ? MODE_EMIT : v == 4 ? MODE_PARTS : MODE_LIST,
                                                                     v == 1 ? 8 : 4, sched),
@@ -941,6 +1011,7 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
     memcpy(p.load, h.load, sizeof(h.load));
     memcpy(p.sub, h.sub, sizeof(h.sub));
     p.nq = nq;
+    p.q16 = dQ16; p.ldq16 = ldq16;
     p.tile_stride = 1;
     p.nrm = space == SNK_SPACE_JOINT ? db->nrm_j16 : db->nrm_t16;
     const size_t smem = s->smem[space];
