@@ -20,6 +20,8 @@
 //    mbarrier ring; two TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
 //  * for the shapes the reference ships the ring and the K-block sequence are compile-time
 //    schedules (sched_traits); other shapes run a table-driven variant of the same kernel.
+//  * multiepoch 6 keeps the query operand in TENSOR memory (written once per CTA with tcgen05.st): the UTCHMMAs then
+//    read only the database operand from shared memory, whose bandwidth is what two smem operands saturate.
 //  * epilogues: MODE_LIST (register lists of the 4 / 8 best per query, k <= 4; MODE_PARTS hands the lists out
 //    several times per chunk for the sampling pass of larger k), MODE_STORE
 //    (keys to HBM, small databases and the sampling pass of larger k), MODE_EMIT (append every row
@@ -39,7 +41,7 @@ namespace {
 constexpr int BM = 128;        // queries per tile (UMMA M)
 constexpr int BN = 128;        // database rows per tile (UMMA N)
 constexpr int BK = 64;         // fp16 elements per K-block = one 128-byte swizzle row
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 12;
 constexpr int MAXKB = 10;      // resident query K-blocks
 constexpr int MAXLOAD = 10;    // TMA loads per database tile
 constexpr int MAXSUB = 16;     // MMA K-blocks per database tile
@@ -48,7 +50,7 @@ constexpr int SLAB_EXTRA = 8;  // extra rows of a frame slab: serves window offs
 // half-phone target shape (K = 192: a tile is only 768 tensor-pipe cycles, the epilogue is the longer stage and
 // more warps hide its latency; measured 22.7 -> 20.1 ms on the k = 50 pipeline).  The one-frame joint shape
 // (multiepoch 1) does not gain: it is bound by the 64 KB per tile it pulls from L2.
-__host__ __device__ constexpr int epi_split_of(int sched) { return sched == 2 ? 4 : 2; }
+__host__ __device__ constexpr int epi_split_of(int sched) { return (sched == 2 || sched == 12) ? 4 : 2; }
 constexpr int TILE_BYTES = BM * BK * 2;                    // 16 KiB query K-block
 constexpr int SLOT_BYTES = (BN + SLAB_EXTRA) * BK * 2;     // 17 KiB ring slot (plain tile or frame slab)
 __host__ __device__ constexpr int num_threads_of(int sched) { return 64 + 128 * epi_split_of(sched); }
@@ -174,16 +176,10 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// 32 lanes x 32 columns from registers into tensor memory (the warp's own lane quarter)
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+// 32 lanes x 8 columns from registers into tensor memory (the warp's own lane quarter)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4 &a, const uint4 &b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
@@ -253,29 +249,42 @@ constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >
 //   SR   : slots per join-part load.  One is enough when a tile keeps the tensor pipe busy for longer than a load
 //          takes to arrive (multiepoch 4, 6); shorter tiles (multiepoch 1, 3) need the second slot, and have the
 //          shared memory for it because their query tile is smaller
-//   ATM  : the frame part of the query operand lives in tensor memory (see SCHED 26)
+//   ATM  : the query operand lives in TENSOR MEMORY instead of shared memory (SCHED 20 + m, SCHED 12): all frame
+//          blocks plus the first AS join-part blocks, next to the two accumulators (512 columns in all).  A 128x128x16
+//          UTCHMMA with both operands in shared memory reads 8 KB per 64 cycles -- all of an SM's shared-memory
+//          bandwidth, with TMA writing into the same banks -- and ncu showed the tensor pipe waiting on operand fetch
+//          ~20 % of the time.  With A in tensor memory the UTCHMMA reads only B from shared memory.  (Spending the freed
+//          shared memory on a deeper database ring was measured slower: 10.1 vs 10.35 M frames/s.)
 template <int SCHED> struct sched_traits {
-    static constexpr int NS = 0, KSL = 0, TB = 0, KTL = 0, M = 1, GR = 1, SR = 1;
+    static constexpr int NS = 0, KSL = 0, TB = 0, KTL = 0, M = 1, GR = 1, SR = 1, AS = 0;
     static constexpr bool ATM = false;
 };
 template <int M_> struct joint_traits {   // joint 151 | M x 61
-    static constexpr int NS = 3, KSL = 2, TB = 1, KTL = 4, M = M_, GR = 2, SR = M_ <= 3 ? 2 : 1;
+    static constexpr int NS = 3, KSL = 2, TB = 1, KTL = 4, M = M_, GR = 2, SR = M_ <= 3 ? 2 : 1, AS = 0;
     static constexpr bool ATM = false;
 };
+template <int M_> struct joint_traits_tm {   // the same with the query operand in tensor memory
+    static constexpr int NS = 3, KSL = 2, TB = 1, KTL = 4, M = M_, GR = 2, SR = M_ <= 3 ? 2 : 1;   // same ring as the smem variants
+    static constexpr int AS = M_ * 32 + 3 * 32 <= 256 ? 3 : 2;     // multiepoch 6: 192 + 64 columns, the last join block stays in smem
+    static constexpr bool ATM = true;
+};
 template <> struct sched_traits<2> {   // target 184
-    static constexpr int NS = 0, KSL = 0, TB = 3, KTL = 4, M = 1, GR = 2, SR = 1;
+    static constexpr int NS = 0, KSL = 0, TB = 3, KTL = 4, M = 1, GR = 2, SR = 1, AS = 0;
     static constexpr bool ATM = false;
+};
+template <> struct sched_traits<12> {   // target 184, query operand in tensor memory
+    static constexpr int NS = 0, KSL = 0, TB = 3, KTL = 4, M = 1, GR = 2, SR = 1, AS = 0;
+    static constexpr bool ATM = true;
 };
 // SCHED 10 + m: the joint space at the multiepoch values the reference's configs use (config/*.cfg: 6, 1, 4, 3)
 template <> struct sched_traits<11> : joint_traits<1> {};
 template <> struct sched_traits<13> : joint_traits<3> {};
 template <> struct sched_traits<14> : joint_traits<4> {};
 template <> struct sched_traits<16> : joint_traits<6> {};
-// SCHED 26: multiepoch 6 with the six frame blocks of the query tile held in TENSOR MEMORY (192 columns next to the two
-// accumulators) instead of shared memory.  A 128x128x16 UTCHMMA with both operands in shared memory reads 8 KB per 64
-// cycles -- all of an SM's shared-memory bandwidth, with TMA writing into the same banks -- and ncu shows the tensor pipe
-// waiting on operand fetch ~20 % of the time.  With A in tensor memory 24 of the 34 UTCHMMAs of a tile read only B.
-template <> struct sched_traits<26> : joint_traits<6> { static constexpr bool ATM = true; };
+template <> struct sched_traits<21> : joint_traits_tm<1> {};
+template <> struct sched_traits<23> : joint_traits_tm<3> {};
+template <> struct sched_traits<24> : joint_traits_tm<4> {};
+template <> struct sched_traits<26> : joint_traits_tm<6> {};
 template <int SCHED> struct sched_layout {
     using S = sched_traits<SCHED>;
     static constexpr int GBYTES = S::M > 1 ? SLOT_BYTES : TILE_BYTES;
@@ -300,9 +309,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     if (sbase & 1023u) __trap();
     uint8_t *gbase = smem_raw;
     constexpr bool ATM = sched_traits<SCHED>::ATM;
-    const int NKB = ATM ? sched_traits<SCHED>::NS : p.nkb;            // query K-blocks resident in shared memory
+    constexpr int AS = sched_traits<SCHED>::AS;                       // join-part blocks of the query held in tensor memory
+    const int NKB = ATM ? sched_traits<SCHED>::NS - AS : p.nkb;       // query K-blocks resident in shared memory
     constexpr uint32_t TCOLS = ATM ? 512u : TMEM_COLS;
-    constexpr uint32_t ATM_COL = 2 * BN;                              // first tensor-memory column of the A frames
+    constexpr uint32_t ATM_COL = 2 * BN;                              // tensor-memory columns of A: [AS join blocks][frame blocks], 32 each
     const uint32_t sA = sbase;
     const uint32_t sB = sA + (uint32_t)NKB * TILE_BYTES;
     const int STAGES = p.stages;
@@ -359,8 +369,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             tma_prefetch_desc(&mapG);
             tma_prefetch_desc(&mapGslab);
             mbar_expect_tx(bar_a, (uint32_t)NKB * TILE_BYTES);
-            for (int kb = 0; kb < NKB; ++kb)
-                tma_load_2d(sA + kb * TILE_BYTES, &mapQ, kb * BK, qt * BM, bar_a);
+            for (int kb = 0; kb < NKB; ++kb)      // ATM: only the join blocks that did not fit in tensor memory
+                tma_load_2d(sA + kb * TILE_BYTES, &mapQ, (kb + (ATM ? AS : 0)) * BK, qt * BM, bar_a);
         }
         __syncwarp();
         if constexpr (SCHED != 0) {
@@ -460,11 +470,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     for (int l = 0; l < S::NS; ++l) {
                         mbar_wait(bar_full + 8 * (uint32_t)L::s_slot(l, sr), ph_s);
                         tc_fence_after();
-                        const uint32_t al = a0 + l * (TILE_BYTES >> 4), bl = b0 + (L::s_off(l, sr) >> 4);
+                        const uint32_t al = a0 + (l - (ATM ? AS : 0)) * (TILE_BYTES >> 4), bl = b0 + (L::s_off(l, sr) >> 4);
 #pragma unroll
-                        for (int ks = 0; ks < (l == S::NS - 1 ? S::KSL : 4); ++ks)
-                            umma_f16(d_tmem, DESC_HI | (uint64_t)(al + 2 * ks), DESC_HI | (uint64_t)(bl + 2 * ks), IDESC,
-                                     (l | ks) != 0 ? 1u : 0u);
+                        for (int ks = 0; ks < (l == S::NS - 1 ? S::KSL : 4); ++ks) {
+                            if (ATM && l < AS)
+                                umma_f16_ts(d_tmem, tmem_base + ATM_COL + (uint32_t)(l * (BK / 2) + ks * 8),
+                                            DESC_HI | (uint64_t)(bl + 2 * ks), IDESC, (l | ks) != 0 ? 1u : 0u);
+                            else
+                                umma_f16(d_tmem, DESC_HI | (uint64_t)(al + 2 * ks), DESC_HI | (uint64_t)(bl + 2 * ks), IDESC,
+                                         (l | ks) != 0 ? 1u : 0u);
+                        }
                         if (p.cluster > 1) umma_commit_mc(bar_empty + 8 * (uint32_t)L::s_slot(l, sr), cmask);
                         else umma_commit(bar_empty + 8 * (uint32_t)L::s_slot(l, sr));
                     }
@@ -480,7 +495,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
 #pragma unroll
                             for (int ks = 0; ks < (b == S::TB - 1 ? S::KTL : 4); ++ks) {   // window offset j = +j rows = +8 in the field
                                 if constexpr (ATM)   // A block (j, b): 32 columns of tensor memory, 8 per UMMA_K step
-                                    umma_f16_ts(d_tmem, tmem_base + ATM_COL + (uint32_t)((j * S::TB + b) * (BK / 2) + ks * 8),
+                                    umma_f16_ts(d_tmem, tmem_base + ATM_COL + (uint32_t)((AS + j * S::TB + b) * (BK / 2) + ks * 8),
                                                 DESC_HI | (uint64_t)(bl + 8 * j + 2 * ks), IDESC, (S::NS + b + j + ks) != 0 ? 1u : 0u);
                                 else
                                     umma_f16(d_tmem, DESC_HI | (uint64_t)(al + 2 * ks), DESC_HI | (uint64_t)(bl + 8 * j + 2 * ks),
@@ -542,21 +557,17 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < LSZ; ++i) { lv[i] = INFINITY; li[i] = -1; }
         if constexpr (ATM) {
-            // this thread's query row, frame part (K-blocks NS .. of the operand row): its half of the 32-bit columns
+            // This thread's query row goes to its tensor-memory lane: the first AS join blocks and every frame block of
+            // the operand row (K-block order), 8 columns (16 fp16) per store, the chunks dealt out over the EPI_SPLIT
+            // threads that share the lane.
             using S = sched_traits<SCHED>;
-            constexpr int ACOLS = S::M * S::TB * (BK / 2);            // 192 for multiepoch 6
-            constexpr int PER = ACOLS / EPI_SPLIT;                    // columns written by this thread
-            static_assert(PER % 32 == 0, "A frames must split into x32 stores");
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(p.q16 + q * (int64_t)p.ldq16 + S::NS * BK) + half * PER;
-#pragma unroll
-            for (int i = 0; i < PER / 32; ++i) {
-                uint32_t r[32];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint4 u = __ldg(reinterpret_cast<const uint4 *>(src + i * 32) + j);
-                    r[4 * j] = u.x; r[4 * j + 1] = u.y; r[4 * j + 2] = u.z; r[4 * j + 3] = u.w;
-                }
-                tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ATM_COL + (uint32_t)(half * PER + i * 32), r);
+            constexpr int CH_S = AS * (BK / 16), CH = CH_S + S::M * S::TB * (BK / 16);     // 8-column chunks
+            const uint4 *row = reinterpret_cast<const uint4 *>(p.q16 + q * (int64_t)p.ldq16);   // 8 fp16 per uint4
+            const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + ATM_COL;
+            for (int c = half; c < CH; c += EPI_SPLIT) {
+                const int src = c < CH_S ? c : c - CH_S + S::NS * (BK / 16);     // chunk index in the operand row
+                const uint4 u0 = __ldg(row + 2 * src), u1 = __ldg(row + 2 * src + 1);
+                tmem_st8(lane_base + (uint32_t)c * 8, u0, u1);
             }
             tmem_wait_st();
             tc_fence_before();
@@ -852,9 +863,12 @@ int build_space(snk_db *db, int space, tc_space_host *h) {
     if (!getenv("SNK_TC_NOSCHED") && h->embed) {
         if (space == SNK_SPACE_JOINT && (slab || m == 1) && (m == 1 || m == 3 || m == 4 || m == 6) && tblocks == 1 &&
             Dt + 3 > 48 && db->Djq + 3 > 144 && db->Djq + 3 <= 160)
-            h->sched = (m == 6 && getenv("SNK_TC_ATMEM")) ? 26 : 10 + m;
+            // query operand in tensor memory: on by default where it was measured faster (multiepoch 6: 1387-1403 ->
+            // 1492-1497 TFLOP/s; multiepoch 4 and 1 neutral, multiepoch 3 and the half-phone target shape slower --
+            // their short tiles are bound by tensor-memory reads, which the A operand then competes for)
+            h->sched = ((m == 6 && !getenv("SNK_TC_NOATMEM")) || getenv("SNK_TC_ATMEM") ? 20 : 10) + m;
         else if (space == SNK_SPACE_TARGET && tblocks == 3 && Dt + 3 > 176)
-            h->sched = 2;
+            h->sched = getenv("SNK_TC_ATMEM") ? 12 : 2;
     }
     const size_t budget = 227 * 1024;
     switch (h->sched) {
@@ -863,17 +877,24 @@ int build_space(snk_db *db, int space, tc_space_host *h) {
     case 13: h->b_bytes = sched_layout<13>::B_BYTES; h->stages = sched_layout<13>::NSLOT; break;
     case 14: h->b_bytes = sched_layout<14>::B_BYTES; h->stages = sched_layout<14>::NSLOT; break;
     case 16: h->b_bytes = sched_layout<16>::B_BYTES; h->stages = sched_layout<16>::NSLOT; break;
+    case 12: h->b_bytes = sched_layout<12>::B_BYTES; h->stages = sched_layout<12>::NSLOT; break;
+    case 21: h->b_bytes = sched_layout<21>::B_BYTES; h->stages = sched_layout<21>::NSLOT; break;
+    case 23: h->b_bytes = sched_layout<23>::B_BYTES; h->stages = sched_layout<23>::NSLOT; break;
+    case 24: h->b_bytes = sched_layout<24>::B_BYTES; h->stages = sched_layout<24>::NSLOT; break;
     case 26: h->b_bytes = sched_layout<26>::B_BYTES; h->stages = sched_layout<26>::NSLOT; break;
+
     default: break;
     }
-    if (h->sched != 0 && (size_t)h->nkb * TILE_BYTES + h->b_bytes + aux_bytes(h->sched) > budget) h->sched = 0;
+    // query K-blocks that stay in shared memory (tensor-memory variants keep at most the last join block there)
+    const int nkb_smem = h->sched == 26 ? 1 : (h->sched == 12 || h->sched > 20) ? 0 : h->nkb;
+    if (h->sched != 0 && (size_t)nkb_smem * TILE_BYTES + h->b_bytes + aux_bytes(h->sched) > budget) h->sched = 0;
     if (h->sched == 0) {
         const size_t fixed = (size_t)h->nkb * TILE_BYTES + aux_bytes(0);
         if (fixed + 2 * SLOT_BYTES > budget) { h->ok = false; return 0; }
         h->stages = (int)std::min<size_t>(4, (budget - fixed) / SLOT_BYTES);
         h->b_bytes = h->stages * SLOT_BYTES;
     }
-    h->smem = (size_t)h->nkb * TILE_BYTES + h->b_bytes + aux_bytes(h->sched);
+    h->smem = (size_t)(h->sched != 0 ? nkb_smem : h->nkb) * TILE_BYTES + h->b_bytes + aux_bytes(h->sched);
     SNK_CUDA(cudaMalloc((void **)&h->d_qmap, qmap.size() * sizeof(short)));
     SNK_CUDA(cudaMemcpy(h->d_qmap, qmap.data(), qmap.size() * sizeof(short), cudaMemcpyHostToDevice));
     return 0;
@@ -890,7 +911,12 @@ tc_kernel_fn pick_sched(int sched) {
     case 13: return knn_tc_kernel<MODE, LSZ, 13>;
     case 14: return knn_tc_kernel<MODE, LSZ, 14>;
     case 16: return knn_tc_kernel<MODE, LSZ, 16>;
+    case 12: return knn_tc_kernel<MODE, LSZ, 12>;
+    case 21: return knn_tc_kernel<MODE, LSZ, 21>;
+    case 23: return knn_tc_kernel<MODE, LSZ, 23>;
+    case 24: return knn_tc_kernel<MODE, LSZ, 24>;
     case 26: return knn_tc_kernel<MODE, LSZ, 26>;
+
     default: return knn_tc_kernel<MODE, LSZ, 0>;
     }
 }
@@ -932,7 +958,7 @@ tc_split make_split(const snk_db *db, const tc_space_host &h, int nqt, int64_t t
     tc_split sp;
     // Pairs of CTAs sharing every database tile by TMA multicast halve the L2 reads.  Measured neutral on B200
     // (m = 6: 1418 vs 1394 TFLOP/s, m = 4: 1278 vs 1329): these kernels are not L2-bound, so it is opt-in.
-    sp.cluster = (h.sched != 0 && nqt >= 2 && getenv("SNK_TC_CLUSTER")) ? 2 : 1;
+    sp.cluster = (h.sched != 0 && h.sched != 12 && h.sched < 20 && nqt >= 2 && getenv("SNK_TC_CLUSTER")) ? 2 : 1;
     sp.nqt_pad = (int)snk_round_up(nqt, sp.cluster);
     sp.nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(db->sm_count / std::max(sp.nqt_pad, 1), tiles));
     if (sp.nqt_pad > db->sm_count) sp.nchunks = 1;
@@ -965,7 +991,7 @@ int snk_tc_prepare(snk_db *db) {
         SNK_TRY(build_space(db, sp, &s->sp[sp]));
         if (s->sp[sp].ok) s->smem[sp] = s->sp[sp].smem;
     }
-    for (int sched : {0, 2, 11, 13, 14, 16, 26})
+    for (int sched : {0, 2, 11, 13, 14, 16, 12, 21, 23, 24, 26})
         for (int v = 0; v < 5; ++v)
             SNK_CUDA(cudaFuncSetAttribute((const void *)pick_kernel(v == 2 ? MODE_STORE : v == 3 ? MODE_EMIT : v == 4 ? MODE_PARTS : MODE_LIST,
                                                                     v == 1 ? 8 : 4, sched),
