@@ -31,6 +31,7 @@
 //    database tile by TMA multicast (SNK_TC_CLUSTER=1).
 #include "common.cuh"
 #include <cuda.h>
+#pragma nv_diag_suppress 177   // traits members a given schedule does not use
 #include <algorithm>
 #include <string.h>
 #include <stdlib.h>

@@ -123,9 +123,25 @@ int search_simt(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, c
 
 }  // namespace
 
-int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist,
-                   int64_t *d_idx, int64_t out_stride, int64_t id_offset, int *d_sticky, int *d_sticky_count,
-                   cudaStream_t st) {
+// A greedy step hands the search a recipe for its queries instead of finished rows (greedy_src, below): the
+// tensor-core path then builds, converts and norms every row in ONE kernel; other paths assemble first.
+namespace { struct greedy_src; }
+static int greedy_launch_assemble(snk_db *db, const greedy_src *gs, int nact, double *Q, cudaStream_t st);
+static int greedy_launch_assemble_cvt(snk_db *db, const greedy_src *gs, int64_t nq, int64_t qpad, int D, const short *qmap,
+                                      int ld16, double *Q, __half *q16, float *qn, float *qerr, cudaStream_t st);
+static int search_dev_impl(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist, int64_t *d_idx,
+                           int64_t out_stride, int64_t id_offset, int *d_sticky, int *d_sticky_count, cudaStream_t st,
+                           const greedy_src *gs);
+
+int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist, int64_t *d_idx,
+                   int64_t out_stride, int64_t id_offset, int *d_sticky, int *d_sticky_count, cudaStream_t st) {
+    return search_dev_impl(db, space, dQ, nq, k, d_dist, d_idx, out_stride, id_offset, d_sticky, d_sticky_count, st, nullptr);
+}
+
+// gs != nullptr: dQ [nq, D] is filled here (by the assemble kernels) before it is searched
+static int search_dev_impl(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist, int64_t *d_idx,
+                           int64_t out_stride, int64_t id_offset, int *d_sticky, int *d_sticky_count, cudaStream_t st,
+                           const greedy_src *gs) {
     SNK_CHECK(db->weights_set, "snk_db_set_weights has not been called");
     SNK_CHECK(k >= 1, "k must be >= 1");
     if (nq <= 0) return 0;
@@ -136,11 +152,13 @@ int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, d
     SNK_CHECK(KP > 0, "k = %d too large (max 248)", k);
     const bool use_tc = db->engine != SNK_ENGINE_SIMT && snk_tc_supported(db, sp, KP);
     SNK_CHECK(use_tc || db->engine != SNK_ENGINE_TC, "tensor-core engine requested but this search shape is not supported by it");
+    const int64_t QB = 16384;
+    const bool fuse = gs && use_tc && nq <= QB;          // one batch: assemble + convert in one kernel
+    if (gs && !fuse) SNK_TRY(greedy_launch_assemble(db, gs, (int)nq, const_cast<double *>(dQ), st));
     if (!use_tc) return search_simt(db, sp, dQ, nq, nullptr, k, d_dist, d_idx, out_stride, id_offset, st);
 
     // ---- tensor-core shortlist + float64 re-rank + certificate, in query batches
     const int ld16 = snk_tc_query_ld(db, space);
-    const int64_t QB = 16384;
     for (int64_t qb = 0; qb < nq; qb += QB) {
         const int64_t qn_ = std::min(QB, nq - qb);
         const int64_t qpad = snk_round_up(qn_, 256);   // two query tiles: the tensor-core kernel may pair CTAs
@@ -159,10 +177,15 @@ int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, d
         int *id = (int *)(val + (size_t)qn_ * KP);
         const double *Qb = dQ + qb * sp.D;
 
-        cvt_q16_kernel<<<(unsigned)std::min<int64_t>(qpad, (int64_t)db->sm_count * 16), CVT_THREADS, 0, st>>>(
-            Qb, sp.D, qn_, qpad, snk_tc_qmap(db, space), ld16, q16, qn, qerr);
-        SNK_CUDA(cudaGetLastError());
-        db->counters[2] += 1;
+        if (fuse) {
+            SNK_TRY(greedy_launch_assemble_cvt(db, gs, qn_, qpad, sp.D, snk_tc_qmap(db, space), ld16, const_cast<double *>(Qb),
+                                               q16, qn, qerr, st));
+        } else {
+            cvt_q16_kernel<<<(unsigned)std::min<int64_t>(qpad, (int64_t)db->sm_count * 16), CVT_THREADS, 0, st>>>(
+                Qb, sp.D, qn_, qpad, snk_tc_qmap(db, space), ld16, q16, qn, qerr);
+            SNK_CUDA(cudaGetLastError());
+            db->counters[2] += 1;
+        }
         snk_tc_lists lists;
         SNK_TRY(snk_shortlist_tc(db, space, q16, ld16, qn_, k, KP, val, id, tau, &lists, st));
         const bool joint = space == SNK_SPACE_JOINT;
@@ -238,48 +261,136 @@ __global__ void prepare_targets_kernel(const float *__restrict__ x, int64_t tota
         out[i] = standardise_weight(x[i], (int)(i % Dt), sp);
 }
 
-// Query b of step t = [ prev_join_vector || m consecutive target frames ]   (synth_simple.py:467-470,488,501)
-// Also scatters the previous step's result into the output path.
+// Query b of step t = [ prev_join_vector || m consecutive target frames ]   (synth_simple.py:467-470,488,501).
+// The recipe: where the previous choices and the target frames are, and where finished steps go.
 // targets: weighted float64 frames, or (targets32 != nullptr) un-normalised float32 frames that are
 // standardised and weighted on the fly (synth_simple.py:371-391).
-__global__ void greedy_assemble_kernel(const greedy_meta *__restrict__ meta, int nact_prev, int nact, int64_t t,
-                                       const double *__restrict__ targets, const float *__restrict__ targets32,
-                                       std_params stp, int Dt, int m,
-                                       const float *__restrict__ Jc_raw, const double *__restrict__ wj, int Dj,
-                                       int Djq, int prev_row_off, int prev_col, int cur_row_off, int cur_col,
-                                       const int64_t *__restrict__ ix_prev, const double *__restrict__ dist_prev,
-                                       int64_t *__restrict__ paths, double *__restrict__ step_dist,
-                                       double *__restrict__ Q) {
-    const int b = blockIdx.x;
-    const greedy_meta mt = meta[b];
-    const int D = Djq + m * Dt;
-    if (t > 0 && b < nact_prev && threadIdx.x == 0) {
-        paths[mt.path_off + t - 1] = ix_prev[b];
-        if (step_dist) step_dist[mt.path_off + t - 1] = dist_prev[b];
+struct greedy_src {
+    const greedy_meta *meta;
+    int nact_prev;
+    int64_t t;
+    const double *targets;
+    const float *targets32;
+    std_params stp;
+    int Dt, m;
+    const float *Jc_raw;
+    const double *wj;
+    int Dj, Djq, prev_row_off, prev_col, cur_row_off, cur_col;
+    const int64_t *ix_prev;
+    const double *dist_prev;
+    int64_t *paths;
+    double *step_dist;
+};
+
+// the previous step's result of utterance b goes to its place in the output path
+__device__ __forceinline__ void greedy_scatter(const greedy_src &g, const greedy_meta &mt, int64_t b) {
+    if (g.t > 0 && b < g.nact_prev) {
+        g.paths[mt.path_off + g.t - 1] = g.ix_prev[b];
+        if (g.step_dist) g.step_dist[mt.path_off + g.t - 1] = g.dist_prev[b];
     }
-    if (b >= nact) return;
-    double *q = Q + (int64_t)b * D;
-    int64_t row = -1;
-    int col = 0;
-    if (t == 0) {
-        if (mt.start_state >= 0) { row = mt.start_state + prev_row_off; col = prev_col; }
+}
+// row / column of the join vector that precedes step t of utterance b (row < 0: none, zeros)
+__device__ __forceinline__ void greedy_prev(const greedy_src &g, const greedy_meta &mt, int64_t b, int64_t &row, int &col) {
+    row = -1;
+    col = 0;
+    if (g.t == 0) {
+        if (mt.start_state >= 0) { row = mt.start_state + g.prev_row_off; col = g.prev_col; }
     } else {
-        row = ix_prev[b] + cur_row_off;
-        col = cur_col;
+        row = g.ix_prev[b] + g.cur_row_off;
+        col = g.cur_col;
     }
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        double v;
-        if (d < Djq) {
-            v = row >= 0 ? (double)Jc_raw[row * Dj + col + d] * wj[col + d] : 0.0;
-        } else {
-            const int64_t i = (mt.tgt_off + t * m) * Dt + (d - Djq);
-            v = targets32 ? standardise_weight(targets32[i], (d - Djq) % Dt, stp) : targets[i];
+}
+__device__ __forceinline__ double greedy_value(const greedy_src &g, const greedy_meta &mt, int64_t row, int col, int d) {
+    if (d < g.Djq) return row >= 0 ? (double)g.Jc_raw[row * g.Dj + col + d] * g.wj[col + d] : 0.0;
+    const int64_t i = (mt.tgt_off + g.t * g.m) * g.Dt + (d - g.Djq);
+    return g.targets32 ? standardise_weight(g.targets32[i], (d - g.Djq) % g.Dt, g.stp) : g.targets[i];
+}
+
+// float64 query rows only (SIMT engine, table-free paths, the last scatter-only step)
+__global__ void greedy_assemble_kernel(const greedy_src g, int nact, double *__restrict__ Q) {
+    const int b = blockIdx.x;
+    const greedy_meta mt = g.meta[b];
+    const int D = g.Djq + g.m * g.Dt;
+    if (threadIdx.x == 0) greedy_scatter(g, mt, b);
+    if (b >= nact) return;
+    int64_t row;
+    int col;
+    greedy_prev(g, mt, b, row, col);
+    double *q = Q + (int64_t)b * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) q[d] = greedy_value(g, mt, row, col, d);
+}
+
+// The same plus what cvt_q16_kernel does, in one pass over the operand columns: float64 row (for the re-rank),
+// fp16 operand row in K-block order, squared norm of the rounded row and rounding-error norm.
+__global__ void __launch_bounds__(CVT_THREADS)
+greedy_assemble_cvt_kernel(const greedy_src g, int64_t nq, int64_t qpad, int D, const short *__restrict__ qmap, int ld16,
+                           double *__restrict__ Q, __half *__restrict__ out, float *__restrict__ qn,
+                           float *__restrict__ qerr) {
+    __shared__ float red[2][CVT_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nrows = max(qpad, (int64_t)g.nact_prev);
+    for (int64_t q = blockIdx.x; q < nrows; q += gridDim.x) {
+        const bool live = q < nq || q < g.nact_prev;
+        greedy_meta mt{};
+        if (live) mt = g.meta[q];
+        if (threadIdx.x == 0 && live) greedy_scatter(g, mt, q);
+        if (q >= qpad) continue;                      // finished utterances beyond the padded batch: scatter only
+        int64_t row = -1;
+        int col = 0;
+        if (q < nq) greedy_prev(g, mt, q, row, col);
+        float n2 = 0.f, e2 = 0.f;
+        for (int c = threadIdx.x; c < ld16; c += CVT_THREADS) {
+            __half h = __float2half_rn(0.f);
+            const int d = qmap[c];
+            if (q < nq && d == -2) h = __float2half_rn(-0.5f);   // multiplies the norm pieces embedded in the row
+            if (q < nq && d >= 0) {
+                const double x = greedy_value(g, mt, row, col, d);
+                Q[q * D + d] = x;
+                h = __double2half(x);
+                const float hf = __half2float(h);
+                n2 = fmaf(hf, hf, n2);
+                const float df = (float)(x - (double)hf);
+                e2 = fmaf(df, df, e2);
+            }
+            out[q * ld16 + c] = h;
         }
-        q[d] = v;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+            e2 += __shfl_xor_sync(0xffffffffu, e2, off);
+        }
+        if (lane == 0) { red[0][warp] = n2; red[1][warp] = e2; }
+        __syncthreads();
+        if (threadIdx.x == 0 && q < nq) {
+            float a = 0.f, b = 0.f;
+            for (int w = 0; w < CVT_THREADS / 32; ++w) { a += red[0][w]; b += red[1][w]; }
+            qn[q] = a;
+            qerr[q] = sqrtf(b);
+        }
+        __syncthreads();
     }
 }
 
 }  // namespace
+
+static int greedy_launch_assemble(snk_db *db, const greedy_src *gs, int nact, double *Q, cudaStream_t st) {
+    const int grid = std::max(nact, gs->nact_prev);
+    if (grid == 0) return 0;
+    greedy_assemble_kernel<<<grid, 128, 0, st>>>(*gs, nact, Q);
+    SNK_CUDA(cudaGetLastError());
+    db->counters[2] += 1;
+    return 0;
+}
+
+static int greedy_launch_assemble_cvt(snk_db *db, const greedy_src *gs, int64_t nq, int64_t qpad, int D, const short *qmap,
+                                      int ld16, double *Q, __half *q16, float *qn, float *qerr, cudaStream_t st) {
+    const int64_t nrows = std::max<int64_t>(qpad, gs->nact_prev);
+    greedy_assemble_cvt_kernel<<<(unsigned)std::min<int64_t>(nrows, (int64_t)db->sm_count * 16), CVT_THREADS, 0, st>>>(
+        *gs, nq, qpad, D, qmap, ld16, Q, q16, qn, qerr);
+    SNK_CUDA(cudaGetLastError());
+    db->counters[2] += 1;
+    return 0;
+}
 
 namespace {
 
@@ -310,18 +421,16 @@ int greedy_run(snk_db *db, const std::vector<greedy_meta> &meta, const double *d
     for (int64_t t = 0; t <= maxsteps; ++t) {
         int nact = 0;
         while (nact < B && meta[nact].nsteps > t) ++nact;
-        const int grid = std::max(nact, nact_prev);
-        if (grid == 0) break;
+        if (std::max(nact, nact_prev) == 0) break;
         // chunked uploads (host entry point): step t may start once its target frames have landed
         while (next_wait < db->step_waits.size() && db->step_waits[next_wait].first <= t)
             SNK_CUDA(cudaStreamWaitEvent(st, db->step_waits[next_wait++].second, 0));
-        greedy_assemble_kernel<<<grid, 128, 0, st>>>(d_meta, nact_prev, nact, t, d_targets, d_unnorm, stp, db->Dt, m, db->Jc_raw,
-                                                     db->wj, db->Dj, db->Djq, db->prev_row_off, db->prev_col,
-                                                     db->cur_row_off, db->cur_col, ix, dist, d_paths, d_step_dist, Q);
-        SNK_CUDA(cudaGetLastError());
-        db->counters[2] += 1;
-        if (nact > 0)
-            SNK_TRY(snk_search_dev(db, SNK_SPACE_JOINT, Q, nact, 1, dist, ix, 1, 0, d_flags, d_count, st));
+        const greedy_src gs{d_meta, nact_prev, t, d_targets, d_unnorm, stp, db->Dt, m, db->Jc_raw, db->wj, db->Dj, db->Djq,
+                            db->prev_row_off, db->prev_col, db->cur_row_off, db->cur_col, ix, dist, d_paths, d_step_dist};
+        if (nact > 0)   // the search builds its queries from the recipe (one fused kernel on the tensor-core path)
+            SNK_TRY(search_dev_impl(db, SNK_SPACE_JOINT, Q, nact, 1, dist, ix, 1, 0, d_flags, d_count, st, &gs));
+        else            // every utterance has finished: only the last choices remain to be written out
+            SNK_TRY(greedy_launch_assemble(db, &gs, 0, Q, st));
         nact_prev = nact;
     }
     return 0;
