@@ -383,7 +383,7 @@ def secondary_viterbi(device):
     B, T, K = 1024, 80, 50
     cands = [rng.integers(1, 89998, size=(T, K)) for _ in range(B)]
     dists = [rng.random((T, K)) for _ in range(B)]
-    g.viterbi_search_batch(cands[:8], dists[:8])
+    g.viterbi_search_batch(cands, dists)       # warm-up at full size: workspaces (0.8 GB of tiles) are allocated here
     g.db.profile_enable(True)
     t0 = time.perf_counter()
     g.viterbi_search_batch(cands, dists)
@@ -394,7 +394,8 @@ def secondary_viterbi(device):
     peaks, kind = measured_peaks()
     hbm = float(peaks["hbm_gbs"])
     res = {"workload": "hybrid_halfphone_default shape: %d utts x %d targets x %d candidates, 90k halfphones" % (B, T, K),
-           "e2e_frames_per_s": B * T / wall}
+           "e2e_frames_per_s": B * T / wall,       # host lists in, host lists out (includes the Python list handling)
+           "e2e_ms": wall * 1e3}
     for name, p in (("join_tiles", pj), ("viterbi", pv)):
         gbs = p["work"] / (p["ms"] / 1e3) / 1e9 if p["ms"] > 0 else 0.0
         res[name] = {"ms": p["ms"], "achieved_GBps": gbs, "peak_GBps": hbm, "frac": gbs / hbm, "peak_kind": kind,
