@@ -251,6 +251,9 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # every launch of the distance GEMM inside the timed region is bracketed by CUDA events on its own stream
+    # (snk_db_profile_*): roofline.achieved is the live average over exactly the launches that make up `value`
+    syn.db.profile_enable(True)
     barrier()
     e0.record(stream)
     for i in range(args.steps):
@@ -258,6 +261,8 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
+    prof = syn.db.profile_read(engine.PROF_KNN)
+    syn.db.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     c1 = syn.db.counters()
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -309,13 +314,6 @@ def run_ours(args):
                        "h2d_bytes_per_step": int(B * T * Dt * 4),
                        "note": "snk_greedy_batch_unnorm: compose_speech-style float32 in, host lists out"}
 
-    # ---- kernel time of the dominant kernel (profiled pass, outside the timed region)
-    syn.db.profile_enable(True)
-    step_dev(0)
-    torch.cuda.synchronize()
-    prof = syn.db.profile_read(engine.PROF_KNN)
-    syn.db.profile_enable(False)
-
     out = None
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -335,12 +333,12 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
             "gpu_launches": int(c1["launches"] - c0["launches"]),
-            "roofline": {"bound": "tensor", "kernel": "knn_tc_kernel<false> (tcgen05 distance GEMM + fused top-k)",
+            "roofline": {"bound": "tensor", "kernel": "knn_tc_kernel<0,4,26> (tcgen05 distance GEMM, query operand in tensor memory, fused per-query top-k lists)",
                          "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak if peak else None,
                          "traffic": traffic, "peak_kind": peak_kind + " (bf16 sustained; fp16 runs at the same rate)",
                          "launches": prof["launches"], "avg_launch_ms": prof["ms"] / max(prof["launches"], 1),
                          "flops_per_launch": prof["work"] / max(prof["launches"], 1),
-                         "kernel_share_of_step": prof["ms"] / (ms_max / args.steps)},
+                         "kernel_share_of_step": prof["ms"] / ms_max},
             "exactness": {"queries": int(c1["queries"] - c0["queries"]), "recertified_by_simt": int(recert)},
             "rates": {"search_steps_per_s": value / MULTIEPOCH, "utterances_per_s": value / T,
                       "frames_per_utterance": int(T), "multiepoch": MULTIEPOCH},
