@@ -49,41 +49,49 @@ __global__ void cvt_q32_kernel(const double *__restrict__ Q, int D, int64_t nq, 
 // One block of CVT_THREADS per (padded) query row: a row is only ~600 columns, so a warp per row would
 // walk it in ~18 dependent gathers; four warps finish in five.
 constexpr int CVT_THREADS = 128;
+// one query value -> fp16 operand element; accumulates the squared rounded value and the squared rounding error
+__device__ __forceinline__ __half cvt_element(double x, float &n2, float &e2) {
+    const __half h = __double2half(x);
+    const float hf = __half2float(h);
+    n2 = fmaf(hf, hf, n2);
+    const float df = (float)(x - (double)hf);
+    e2 = fmaf(df, df, e2);
+    return h;
+}
+// block-wide sums of (n2, e2); thread 0 returns them.  Ends with a barrier so `red` can be reused at once.
+__device__ __forceinline__ void cvt_reduce(float &n2, float &e2, float (&red)[2][CVT_THREADS / 32]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+        e2 += __shfl_xor_sync(0xffffffffu, e2, off);
+    }
+    if (lane == 0) { red[0][warp] = n2; red[1][warp] = e2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        n2 = e2 = 0.f;
+        for (int w = 0; w < CVT_THREADS / 32; ++w) { n2 += red[0][w]; e2 += red[1][w]; }
+    }
+    __syncthreads();
+}
 __global__ void __launch_bounds__(CVT_THREADS)
 cvt_q16_kernel(const double *__restrict__ Q, int D, int64_t nq, int64_t nq_pad, const short *__restrict__ qmap,
                int ld16, __half *__restrict__ out, float *__restrict__ qn, float *__restrict__ qerr) {
     __shared__ float red[2][CVT_THREADS / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t q = blockIdx.x; q < nq_pad; q += gridDim.x) {
         float n2 = 0.f, e2 = 0.f;
         for (int c = threadIdx.x; c < ld16; c += CVT_THREADS) {
             __half h = __float2half_rn(0.f);
             const int d = qmap[c];
             if (q < nq && d == -2) h = __float2half_rn(-0.5f);   // multiplies the norm pieces embedded in the row
-            if (q < nq && d >= 0) {
-                const double x = Q[q * D + d];
-                h = __double2half(x);
-                const float hf = __half2float(h);
-                n2 = fmaf(hf, hf, n2);
-                const float df = (float)(x - (double)hf);
-                e2 = fmaf(df, df, e2);
-            }
+            if (q < nq && d >= 0) h = cvt_element(Q[q * D + d], n2, e2);
             out[q * ld16 + c] = h;
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            n2 += __shfl_xor_sync(0xffffffffu, n2, off);
-            e2 += __shfl_xor_sync(0xffffffffu, e2, off);
-        }
-        if (lane == 0) { red[0][warp] = n2; red[1][warp] = e2; }
-        __syncthreads();
+        cvt_reduce(n2, e2, red);
         if (threadIdx.x == 0 && q < nq) {
-            float a = 0.f, b = 0.f;
-            for (int w = 0; w < CVT_THREADS / 32; ++w) { a += red[0][w]; b += red[1][w]; }
-            qn[q] = a;
-            qerr[q] = sqrtf(b);
+            qn[q] = n2;
+            qerr[q] = sqrtf(e2);
         }
-        __syncthreads();
     }
 }
 
@@ -327,7 +335,6 @@ greedy_assemble_cvt_kernel(const greedy_src g, int64_t nq, int64_t qpad, int D, 
                            double *__restrict__ Q, __half *__restrict__ out, float *__restrict__ qn,
                            float *__restrict__ qerr) {
     __shared__ float red[2][CVT_THREADS / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t nrows = max(qpad, (int64_t)g.nact_prev);
     for (int64_t q = blockIdx.x; q < nrows; q += gridDim.x) {
         const bool live = q < nq || q < g.nact_prev;
@@ -346,28 +353,15 @@ greedy_assemble_cvt_kernel(const greedy_src g, int64_t nq, int64_t qpad, int D, 
             if (q < nq && d >= 0) {
                 const double x = greedy_value(g, mt, row, col, d);
                 Q[q * D + d] = x;
-                h = __double2half(x);
-                const float hf = __half2float(h);
-                n2 = fmaf(hf, hf, n2);
-                const float df = (float)(x - (double)hf);
-                e2 = fmaf(df, df, e2);
+                h = cvt_element(x, n2, e2);
             }
             out[q * ld16 + c] = h;
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            n2 += __shfl_xor_sync(0xffffffffu, n2, off);
-            e2 += __shfl_xor_sync(0xffffffffu, e2, off);
-        }
-        if (lane == 0) { red[0][warp] = n2; red[1][warp] = e2; }
-        __syncthreads();
+        cvt_reduce(n2, e2, red);
         if (threadIdx.x == 0 && q < nq) {
-            float a = 0.f, b = 0.f;
-            for (int w = 0; w < CVT_THREADS / 32; ++w) { a += red[0][w]; b += red[1][w]; }
-            qn[q] = a;
-            qerr[q] = sqrtf(b);
+            qn[q] = n2;
+            qerr[q] = sqrtf(e2);
         }
-        __syncthreads();
     }
 }
 
