@@ -109,3 +109,41 @@ def test_stash_with_unsupported_member(tmp_path, monkeypatch):
     assert np.array_equal(f["state_0"], data) and np.array_equal(f["int_values"], np.arange(7))
     with pytest.raises(Hdf5FormatError, match="datatype class 6"):
         f["state_2"]
+
+
+def test_round_trip_fuzz(tmp_path):
+    """Random shapes, dtypes, chunk sizes and filter pipelines (seeded): what is written is what is read."""
+    rng = np.random.default_rng(2024)
+    for trial in range(25):
+        arrays, chunked = {}, []
+        for i in range(int(rng.integers(1, 8))):
+            kind = rng.integers(0, 5)
+            rows = int(rng.integers(0, 400))
+            shape = (rows,) if rng.random() < 0.4 else (rows, int(rng.integers(1, 70)))
+            if kind == 0:
+                a = rng.normal(size=shape).astype(np.float32)
+            elif kind == 1:
+                a = rng.normal(size=shape)
+            elif kind == 2:
+                a = rng.integers(-2 ** 31, 2 ** 31 - 1, size=shape).astype(np.int32)
+            elif kind == 3:
+                a = rng.integers(0, 2 ** 62, size=shape).astype(np.int64)
+            else:
+                a = np.array([("u%d" % v).encode() for v in rng.integers(0, 10 ** 6, size=int(np.prod(shape)))] or [b""],
+                             dtype="S%d" % int(rng.integers(8, 51)))[: int(np.prod(shape))].reshape(shape)
+            name = "d%d_%s" % (i, "x" * int(rng.integers(0, 12)))
+            arrays[name] = a
+            if rng.random() < 0.6:
+                chunked.append(name)
+        path = str(tmp_path / ("f%d.hdf5" % trial))
+        kw = {}
+        if rng.random() < 0.5:
+            kw["gzip"] = int(rng.integers(1, 9))
+        if rng.random() < 0.5:
+            kw["shuffle"] = True
+        save_voice(path, arrays, chunked=tuple(chunked), chunk_bytes=int(rng.integers(64, 20000)), **kw)
+        f = Hdf5File(path)
+        assert sorted(f.keys()) == sorted(arrays)
+        for k, a in arrays.items():
+            b = f[k]
+            assert b.shape == a.shape and b.dtype == a.dtype and np.array_equal(b, a), (trial, k, a.shape, a.dtype, kw)
