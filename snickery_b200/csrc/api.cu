@@ -465,6 +465,9 @@ int snk_greedy_path_scores(snk_db *db, const double *targets, int64_t T, const i
     for (int i = 0; i < n_jstreams; ++i) js += jwidths[i];
     SNK_CHECK(ts == db->Dt, "target stream widths sum to %d, expected %d", ts, db->Dt);
     SNK_CHECK(js == db->Djq, "join stream widths sum to %d, expected %d", js, db->Djq);
+    for (int64_t p = 0; p < P; ++p)   // the kernel gathers rows path[p] .. path[p] + m: reject ids numpy would reject
+        SNK_CHECK(path[p] >= 0 && path[p] < db->Np, "path[%lld] = %lld is not a searchable row (0 <= id < %lld)",
+                  (long long)p, (long long)path[p], (long long)db->Np);
     SNK_CUDA(cudaSetDevice(db->device));
     SNK_TRY(snk_buf_reserve(&db->ws_h0, (size_t)T * db->Dt * 8));
     SNK_TRY(snk_buf_reserve(&db->ws_h1, (size_t)P * 8));
