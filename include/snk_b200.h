@@ -14,11 +14,17 @@
  *  - "host" entry points take plain host pointers (pageable or pinned), perform
  *    H2D / D2H copies themselves and return when results are in host memory.
  *  - "_dev" entry points take device pointers on the handle's device and enqueue
- *    on the given cudaStream_t (passed as void*); they do not synchronise.
+ *    on the given cudaStream_t (passed as void*); they NEVER synchronise: launch
+ *    metadata travels through a pinned staging ring, exactness certificates stay on
+ *    the device.  The searches (snk_knn_dev, snk_greedy_batch*_dev, snk_knn_sharded_dev)
+ *    are completed by the matching *_finish call, which waits for the stream, reads the
+ *    certificate flags and repairs the (rare) uncertified answers; results are final
+ *    only after it.  Input and output buffers must stay alive until then.  All _dev
+ *    calls on one handle share its workspaces: issue them on ONE stream at a time.
  *  - there is NO CPU fallback: without a CUDA device every compute entry point
  *    fails with an error.
- *  - a handle is not thread-safe; different handles may be used from different
- *    threads.  A handle must not be shared across fork().
+ *  - thread-safe per handle: calls on one handle are serialised by an internal lock,
+ *    different handles run concurrently.  A handle must not be shared across fork().
  */
 #ifndef SNK_B200_H
 #define SNK_B200_H
@@ -65,9 +71,10 @@ int snk_db_info(const snk_db *db, int64_t *N, int64_t *Nprime, int *Dt, int *Dj,
 int snk_db_set_weights(snk_db *db, const double *wt, const double *wj);
 /* choose the shortlist engine for subsequent searches (default AUTO) */
 int snk_db_set_engine(snk_db *db, int engine);
-/* counters since creation: [0] queries searched, [1] queries whose tensor-core shortlist
- * failed the exactness certificate and were re-searched with the SIMT engine,
- * [2] kernels launched, [3] reserved */
+/* counters since creation: [0] queries searched, [1] queries (greedy: utterances) whose tensor-core
+ * shortlist failed the exactness certificate and were re-searched with the fp32 SIMT engine,
+ * [2] kernels launched, [3] queries (utterances) that also failed the fp32 certificate and were
+ * answered by the exhaustive float64 scan */
 int snk_db_counters(const snk_db *db, int64_t counters[4], int reset);
 
 /* ---- kernel timing for bench.py -----------------------------------------------------------
@@ -78,6 +85,10 @@ int snk_db_counters(const snk_db *db, int64_t counters[4], int reset);
 #define SNK_PROF_KNN 0
 #define SNK_PROF_JOIN 1
 #define SNK_PROF_VITERBI 2
+#define SNK_PROF_ALLGATHER 3 /* work = bytes received over NVLink by this rank */
+#define SNK_PROF_MERGE 4     /* work = bytes merged */
+#define SNK_PROF_JOIN_VITERBI 5 /* fused join-cost + Viterbi kernel; work = gathered bytes */
+#define SNK_PROF_RERANK 6    /* float64 re-rank of the shortlists; work = gathered bytes */
 int snk_db_profile_enable(snk_db *db, int enable);
 int snk_db_profile_read(snk_db *db, int which, double *total_ms, int64_t *launches, double *work, int reset);
 
@@ -90,10 +101,30 @@ int snk_db_profile_read(snk_db *db, int which, double *total_ms, int64_t *launch
 int snk_knn(snk_db *db, int space, const double *Q, int64_t nq, int k, double *dist, int64_t *idx);
 int snk_knn_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist,
                 int64_t *d_idx, int64_t id_offset, void *stream);
+/* completes every snk_knn_dev enqueued on this handle since the last call (see "Conventions") */
+int snk_knn_finish(snk_db *db);
 /* k-way merge of R per-shard results [R, nq, k] (ascending) into [nq, k]; used after the
  * NCCL all-gather of the sharded-database search.               */
 int snk_topk_merge_dev(int device_id, const double *d_dist_all, const int64_t *d_idx_all, int R,
                        int64_t nq, int k, double *d_dist, int64_t *d_idx, void *stream);
+
+/* ---- database sharded over the GPUs of one box --------------------------
+ * No reference call site: the reference is one process.  Every rank (one process per GPU) holds a
+ * block of database rows in its own handle and calls these collectively.
+ * snk_comm_unique_id: rank 0 obtains the 128-byte NCCL id and hands it to the other ranks through
+ * the host's own channel (MPI, a file, torch.distributed...).  snk_comm_init attaches an NCCL
+ * communicator to the handle.  NCCL is resolved with dlopen("libnccl.so.2") at that moment.
+ * snk_knn_sharded_dev: replicated queries dQ [nq, D]; local certified top-k with global ids
+ * (id_offset = first global row of this rank's block), ONE ncclAllGather of nq*k*16 bytes per rank
+ * over NVLink, k-way merge on the device (ties: lowest global id); every rank gets the global
+ * [nq, k] answer.  snk_knn_sharded_finish (collective) completes it like snk_knn_finish.      */
+#define SNK_UNIQUE_ID_BYTES 128
+int snk_comm_unique_id(void *id_out, int id_bytes);
+int snk_comm_init(snk_db *db, const void *unique_id, int rank, int nranks);
+int snk_comm_info(snk_db *db, int *rank, int *nranks, int *nccl_version);
+int snk_knn_sharded_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist,
+                        int64_t *d_idx, int64_t id_offset, void *stream);
+int snk_knn_sharded_finish(snk_db *db);
 
 /* ---- greedy joint search ------------------------------------------------------------------
  * Replaces Synthesiser.greedy_joint_search (synth_simple.py:458-503;
@@ -109,6 +140,8 @@ int snk_greedy_batch(snk_db *db, const double *targets, const int64_t *lens, int
 int snk_greedy_batch_dev(snk_db *db, const double *d_targets, const int64_t *lens, int B,
                          const int64_t *start_state, int64_t *d_paths, double *d_step_dist,
                          void *stream);
+/* completes every snk_greedy_batch_dev / snk_greedy_batch_unnorm_dev enqueued since the last call */
+int snk_greedy_batch_finish(snk_db *db);
 
 /* ---- target preparation -----------------------------------------------------
  * Replaces the per-utterance host numpy between compose_speech and the search
@@ -170,6 +203,19 @@ int snk_join_viterbi_batch_dev(snk_db *db, const int64_t *d_cand, const double *
                                const int64_t *lens, int B, int K, unsigned flags, int64_t *d_paths,
                                int64_t *d_path_len, double *d_path_cost, double *d_tcost,
                                double *d_jcost, void *stream);
+
+/* ---- acoustic preselection + join + Viterbi in one call ----------------------------------------
+ * Replaces the pair preselect_units_acoustic -> viterbi_search of synth_utt (synth_halfphone.py:1359-1366,
+ * 1399-1436, call sites :1611-1625) for B utterances: targets float64 [sum T_b, Dt] weighted unit
+ * features; the k-NN candidate lists (K = n_candidates per target) stay on the device and feed the
+ * join / Viterbi stage directly; only the paths come back.  Outputs as snk_join_viterbi_batch.    */
+int snk_acoustic_viterbi_batch(snk_db *db, const double *targets, const int64_t *lens, int B, int K,
+                               unsigned flags, int64_t *paths, int64_t *path_len, double *path_cost,
+                               double *tcost, double *jcost);
+int snk_acoustic_viterbi_batch_dev(snk_db *db, const double *d_targets, const int64_t *lens, int B, int K,
+                                   unsigned flags, int64_t *d_paths, int64_t *d_path_len,
+                                   double *d_path_cost, double *d_tcost, double *d_jcost, void *stream);
+int snk_acoustic_viterbi_finish(snk_db *db);
 
 /* ---- per-stream cost report ------------------------------------------------------------------
  * Replaces get_target_scores_per_stream / get_join_scores_per_stream

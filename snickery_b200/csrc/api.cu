@@ -15,6 +15,16 @@ int snk_path_scores_dev(snk_db *db, const double *d_targets, int64_t T, const in
                         const int *d_tw, int nts, const int *d_jw, int njs, double *d_ts, double *d_js,
                         cudaStream_t st);
 
+// ---- acoustic preselection + join + Viterbi in one call: candidates never leave the device -------------------
+struct snk_acoustic_job {
+    bool active = false;
+    std::vector<int64_t> lens;
+    int K = 0;
+    unsigned flags = 0;
+    int64_t *d_paths = nullptr, *d_plen = nullptr;
+    double *d_pcost = nullptr, *d_tcost = nullptr, *d_jcost = nullptr;
+    cudaStream_t st = nullptr;
+};
 static thread_local char g_err[1024] = "";
 
 void snk_set_error(const char *fmt, ...) {
@@ -40,6 +50,26 @@ void snk_buf_free(snk_buf *b) {
     if (b->p) cudaFree(b->p);
     b->p = nullptr;
     b->cap = 0;
+}
+
+int snk_upload_async(snk_db *db, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return 0;
+    snk_stage_slot &sl = db->stage[db->stage_next];
+    db->stage_next = (db->stage_next + 1) % SNK_STAGE_SLOTS;
+    if (!sl.ev) SNK_CUDA(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+    else SNK_CUDA(cudaEventSynchronize(sl.ev));          // the copy that last used this slot (8 uploads ago) has run
+    if (bytes > sl.cap) {
+        if (sl.host) SNK_CUDA(cudaFreeHost(sl.host));
+        sl.host = nullptr;
+        sl.cap = 0;
+        const size_t want = bytes + bytes / 2 + 4096;
+        SNK_CUDA(cudaMallocHost(&sl.host, want));
+        sl.cap = want;
+    }
+    memcpy(sl.host, h_src, bytes);
+    SNK_CUDA(cudaMemcpyAsync(d_dst, sl.host, bytes, cudaMemcpyHostToDevice, st));
+    SNK_CUDA(cudaEventRecord(sl.ev, st));
+    return 0;
 }
 
 extern "C" {
@@ -75,6 +105,7 @@ int snk_db_create(snk_db **out, int device_id, int64_t N, int Dt, int Dj, int mu
     snk_db *db = new snk_db();
     db->device = device_id;
     if (const char *e = getenv("SNK_DEBUG_CERT_FAIL")) db->debug_fail_mod = atoi(e);
+    if (const char *e = getenv("SNK_DEBUG_CERT_FAIL2")) db->debug_fail_mod2 = atoi(e);
     db->sm_count = prop.multiProcessorCount;
     db->N = N; db->Dt = Dt; db->Dj = Dj; db->m = multiepoch; db->layout = layout_flags;
     db->Np = N - (multiepoch - 1);
@@ -136,15 +167,23 @@ int snk_db_create(snk_db **out, int device_id, int64_t N, int Dt, int Dj, int mu
 int snk_db_destroy(snk_db *db) {
     if (!db) return 0;
     cudaSetDevice(db->device);
-    if (db->stream) cudaStreamSynchronize(db->stream);
+    cudaDeviceSynchronize();
+    snk_comm_free(db);
+    snk_pending_destroy(db);
+    delete db->acoustic;
     snk_tc_destroy(db);
+    for (snk_stage_slot &sl : db->stage) {
+        if (sl.ev) cudaEventDestroy(sl.ev);
+        if (sl.host) cudaFreeHost(sl.host);
+    }
     for (auto &r : db->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     cudaFree(db->F_raw); cudaFree(db->Jc_raw); cudaFree(db->wt); cudaFree(db->wj);
     cudaFree(db->std_mean); cudaFree(db->std_sd);
     cudaFree(db->Fw32); cudaFree(db->Jw32); cudaFree(db->G16); cudaFree(db->S16);
     cudaFree(db->nrm_t16); cudaFree(db->nrm_j16); cudaFree(db->err_t16);
     snk_buf *bufs[] = {&db->ws_q, &db->ws_dist, &db->ws_list, &db->ws_misc, &db->ws_io, &db->ws_io2, &db->ws_tiles,
-                       &db->ws_bp, &db->ws_tc, &db->ws_h0, &db->ws_h1, &db->ws_h2, &db->ws_h3, &db->ws_flags};
+                       &db->ws_bp, &db->ws_tc, &db->ws_h0, &db->ws_h1, &db->ws_h2, &db->ws_h3, &db->ws_flags,
+                       &db->ws_kflags, &db->ws_meta, &db->ws_ag, &db->ws_jv};
     for (snk_buf *b : bufs) snk_buf_free(b);
     if (db->ev) cudaEventDestroy(db->ev);
     for (cudaEvent_t e : db->upload_events) cudaEventDestroy(e);
@@ -168,6 +207,7 @@ int snk_db_info(const snk_db *db, int64_t *N, int64_t *Nprime, int *Dt, int *Dj,
 
 int snk_db_set_weights(snk_db *db, const double *wt, const double *wj) {
     SNK_CHECK(db && wt && wj, "NULL argument");
+    SNK_LOCK(db);
     SNK_CUDA(cudaSetDevice(db->device));
     SNK_CUDA(cudaMemcpyAsync(db->wt, wt, (size_t)db->Dt * 8, cudaMemcpyHostToDevice, db->stream));
     SNK_CUDA(cudaMemcpyAsync(db->wj, wj, (size_t)db->Dj * 8, cudaMemcpyHostToDevice, db->stream));
@@ -183,6 +223,7 @@ int snk_db_set_weights(snk_db *db, const double *wt, const double *wj) {
 
 int snk_db_set_engine(snk_db *db, int engine) {
     SNK_CHECK(db, "db is NULL");
+    SNK_LOCK(db);
     SNK_CHECK(engine == SNK_ENGINE_AUTO || engine == SNK_ENGINE_SIMT || engine == SNK_ENGINE_TC, "unknown engine %d",
               engine);
     db->engine = engine;
@@ -198,12 +239,14 @@ int snk_db_counters(const snk_db *db, int64_t counters[4], int reset) {
 
 int snk_db_profile_enable(snk_db *db, int enable) {
     SNK_CHECK(db, "db is NULL");
+    SNK_LOCK(db);
     db->prof_on = enable != 0;
     return 0;
 }
 
 int snk_db_profile_read(snk_db *db, int which, double *total_ms, int64_t *launches, double *work, int reset) {
     SNK_CHECK(db, "db is NULL");
+    SNK_LOCK(db);
     SNK_CUDA(cudaSetDevice(db->device));
     SNK_CUDA(cudaDeviceSynchronize());
     double ms = 0.0, w = 0.0;
@@ -231,13 +274,16 @@ int snk_db_profile_read(snk_db *db, int which, double *total_ms, int64_t *launch
 int snk_knn_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist, int64_t *d_idx,
                 int64_t id_offset, void *stream) {
     SNK_CHECK(db, "db is NULL");
+    SNK_LOCK(db);
     SNK_CHECK(space == SNK_SPACE_TARGET || space == SNK_SPACE_JOINT, "unknown search space %d", space);
+    SNK_CHECK(nq >= 0 && k >= 1, "bad nq / k");
     SNK_CUDA(cudaSetDevice(db->device));
-    return snk_search_dev(db, space, dQ, nq, k, d_dist, d_idx, k, id_offset, nullptr, nullptr, (cudaStream_t)stream);
+    return snk_knn_enqueue(db, space, dQ, nq, k, d_dist, d_idx, k, id_offset, (cudaStream_t)stream);
 }
 
 int snk_knn(snk_db *db, int space, const double *Q, int64_t nq, int k, double *dist, int64_t *idx) {
     SNK_CHECK(db && dist && idx, "NULL argument");
+    SNK_LOCK(db);
     SNK_CHECK(space == SNK_SPACE_TARGET || space == SNK_SPACE_JOINT, "unknown search space %d", space);
     SNK_CHECK(nq >= 0 && k >= 1, "bad nq / k");
     if (nq == 0) return 0;
@@ -252,8 +298,9 @@ int snk_knn(snk_db *db, int space, const double *Q, int64_t nq, int k, double *d
     for (int64_t q0 = 0; q0 < nq; q0 += slab) {
         const int64_t n = std::min(slab, nq - q0);
         SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, Q + q0 * sp.D, (size_t)n * sp.D * 8, cudaMemcpyHostToDevice, db->stream));
-        SNK_TRY(snk_search_dev(db, space, (const double *)db->ws_h0.p, n, k, (double *)db->ws_h1.p,
-                               (int64_t *)db->ws_h2.p, k, 0, nullptr, nullptr, db->stream));
+        SNK_TRY(snk_knn_enqueue(db, space, (const double *)db->ws_h0.p, n, k, (double *)db->ws_h1.p, (int64_t *)db->ws_h2.p, k,
+                                0, db->stream));
+        SNK_TRY(snk_knn_finish(db));
         SNK_CUDA(cudaMemcpyAsync(dist + q0 * k, db->ws_h1.p, (size_t)n * k * 8, cudaMemcpyDeviceToHost, db->stream));
         SNK_CUDA(cudaMemcpyAsync(idx + q0 * k, db->ws_h2.p, (size_t)n * k * 8, cudaMemcpyDeviceToHost, db->stream));
         SNK_CUDA(cudaStreamSynchronize(db->stream));
@@ -264,6 +311,7 @@ int snk_knn(snk_db *db, int space, const double *Q, int64_t nq, int k, double *d
 int snk_db_set_standardisation(snk_db *db, const double *mean, const double *std, double special_uv_value,
                                double uv_scaling_factor, unsigned flags) {
     SNK_CHECK(db && mean && std, "NULL argument");
+    SNK_LOCK(db);
     SNK_CUDA(cudaSetDevice(db->device));
     for (int c = 0; c < db->Dt; ++c) SNK_CHECK(std[c] != 0.0 && std[c] == std[c], "std[%d] is zero or NaN", c);
     if (!db->std_mean) {
@@ -282,6 +330,7 @@ int snk_db_set_standardisation(snk_db *db, const double *mean, const double *std
 
 int snk_prepare_targets(snk_db *db, const float *unnorm, int64_t rows, double *out) {
     SNK_CHECK(db && db->std_set, "snk_db_set_standardisation has not been called");
+    SNK_LOCK(db);
     SNK_CHECK(rows >= 0, "bad row count");
     if (rows == 0) return 0;
     SNK_CHECK(unnorm && out, "NULL argument");
@@ -300,6 +349,7 @@ int snk_prepare_targets(snk_db *db, const float *unnorm, int64_t rows, double *o
 static int greedy_batch_host(snk_db *db, const void *targets, size_t elem, const int64_t *lens, int B,
                              const int64_t *start_state, int64_t *paths, double *step_dist) {
     SNK_CHECK(db && lens && paths, "NULL argument");
+    SNK_LOCK(db);
     SNK_CHECK(B >= 0, "bad batch size");
     if (B == 0) return 0;
     SNK_CUDA(cudaSetDevice(db->device));
@@ -350,9 +400,10 @@ static int greedy_batch_host(snk_db *db, const void *targets, size_t elem, const
                   : snk_greedy_batch_unnorm_dev(db, (const float *)db->ws_h0.p, lens, B, start_state, d_paths, d_sd,
                                                 db->stream);
     db->step_waits.clear();
-    if (rc_greedy) {
+    const int rc_fin = snk_greedy_batch_finish(db);    // waits for the chain; repairs uncertified utterances
+    if (rc_greedy || rc_fin) {
         cudaStreamSynchronize(db->copy_stream);
-        return rc_greedy;
+        return 1;
     }
     if (steps) {
         SNK_CUDA(cudaMemcpyAsync(paths, db->ws_h1.p, (size_t)steps * 8, cudaMemcpyDeviceToHost, db->stream));
@@ -376,6 +427,7 @@ int snk_greedy_batch_unnorm(snk_db *db, const float *unnorm, const int64_t *lens
 
 int snk_candidate_distances(snk_db *db, const int64_t *cand, const double *targets, int64_t T, int K, double *dist) {
     SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    SNK_LOCK(db);
     SNK_CHECK(T >= 0 && K >= 1, "bad T / K");
     if (T == 0) return 0;
     SNK_CHECK(cand && targets && dist, "NULL argument");
@@ -406,6 +458,7 @@ static int count_frames(const int64_t *lens, int B, int64_t *frames, int64_t *ti
 
 int snk_join_tiles(snk_db *db, const int64_t *cand, const int64_t *lens, int B, int K, float *tiles) {
     SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    SNK_LOCK(db);
     SNK_CHECK(lens && B >= 0 && K >= 1, "bad arguments");
     SNK_CUDA(cudaSetDevice(db->device));
     int64_t frames, ntiles;
@@ -425,6 +478,7 @@ int snk_join_viterbi_batch(snk_db *db, const int64_t *cand, const double *tdist,
                            unsigned flags, int64_t *paths, int64_t *path_len, double *path_cost, double *tcost,
                            double *jcost) {
     SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    SNK_LOCK(db);
     SNK_CHECK(lens && B >= 0 && K >= 1, "bad arguments");
     if (B == 0) return 0;
     SNK_CHECK(path_len && path_cost, "NULL output");
@@ -454,10 +508,97 @@ int snk_join_viterbi_batch(snk_db *db, const int64_t *cand, const double *tdist,
     return 0;
 }
 
+static snk_acoustic_job *acoustic_job(snk_db *db) {
+    if (!db->acoustic) db->acoustic = new snk_acoustic_job();
+    return db->acoustic;
+}
+
+int snk_acoustic_viterbi_batch_dev(snk_db *db, const double *d_targets, const int64_t *lens, int B, int K, unsigned flags,
+                                   int64_t *d_paths, int64_t *d_path_len, double *d_path_cost, double *d_tcost,
+                                   double *d_jcost, void *stream) {
+    SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    SNK_LOCK(db);
+    SNK_CHECK(lens && B >= 0 && K >= 1, "bad arguments");
+    if (B == 0) return 0;
+    SNK_CUDA(cudaSetDevice(db->device));
+    int64_t frames, ntiles;
+    SNK_TRY(count_frames(lens, B, &frames, &ntiles));
+    SNK_CHECK(frames == 0 || (d_targets && d_paths), "NULL argument");
+    snk_acoustic_job *job = acoustic_job(db);
+    SNK_CHECK(!job->active, "the previous snk_acoustic_viterbi_batch_dev has not been finished");
+    const size_t fK = (size_t)std::max<int64_t>(frames, 1) * K;
+    SNK_TRY(snk_buf_reserve(&db->ws_jv, fK * 16));
+    double *d_dist = (double *)db->ws_jv.p;
+    int64_t *d_cand = (int64_t *)(d_dist + fK);
+    cudaStream_t st = (cudaStream_t)stream;
+    // preselect_units_acoustic (synth_halfphone.py:1359-1366) for every target of every utterance in one search ...
+    if (frames) SNK_TRY(snk_knn_enqueue(db, SNK_SPACE_TARGET, d_targets, frames, K, d_dist, d_cand, K, 0, st));
+    // ... and viterbi_search (synth_halfphone.py:1399-1436) on the device-resident candidate lists
+    SNK_TRY(snk_join_viterbi_batch_dev(db, d_cand, d_dist, lens, B, K, flags, d_paths, d_path_len, d_path_cost, d_tcost,
+                                       d_jcost, stream));
+    job->active = true;
+    job->lens.assign(lens, lens + B);
+    job->K = K; job->flags = flags; job->d_paths = d_paths; job->d_plen = d_path_len; job->d_pcost = d_path_cost;
+    job->d_tcost = d_tcost; job->d_jcost = d_jcost; job->st = st;
+    return 0;
+}
+
+int snk_acoustic_viterbi_finish(snk_db *db) {
+    SNK_CHECK(db, "db is NULL");
+    SNK_LOCK(db);
+    snk_acoustic_job *job = acoustic_job(db);
+    if (!job->active) return 0;
+    job->active = false;
+    const int64_t before = db->counters[1];
+    SNK_TRY(snk_knn_finish(db));                 // waits; repairs uncertified candidate lists
+    if (db->counters[1] != before) {             // the lattice changed under the search: run it again (rare)
+        int64_t frames = 0;
+        for (int64_t l : job->lens) frames += l;
+        const size_t fK = (size_t)std::max<int64_t>(frames, 1) * job->K;
+        double *d_dist = (double *)db->ws_jv.p;
+        int64_t *d_cand = (int64_t *)(d_dist + fK);
+        SNK_TRY(snk_join_viterbi_batch_dev(db, d_cand, d_dist, job->lens.data(), (int)job->lens.size(), job->K, job->flags,
+                                           job->d_paths, job->d_plen, job->d_pcost, job->d_tcost, job->d_jcost, job->st));
+        SNK_CUDA(cudaStreamSynchronize(job->st));
+    }
+    return 0;
+}
+
+int snk_acoustic_viterbi_batch(snk_db *db, const double *targets, const int64_t *lens, int B, int K, unsigned flags,
+                               int64_t *paths, int64_t *path_len, double *path_cost, double *tcost, double *jcost) {
+    SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    SNK_LOCK(db);
+    SNK_CHECK(lens && B >= 0 && K >= 1, "bad arguments");
+    if (B == 0) return 0;
+    SNK_CHECK(path_len && path_cost, "NULL output");
+    SNK_CUDA(cudaSetDevice(db->device));
+    int64_t frames, ntiles;
+    SNK_TRY(count_frames(lens, B, &frames, &ntiles));
+    SNK_CHECK(frames == 0 || (targets && paths), "NULL argument");
+    const size_t tb = (size_t)std::max<int64_t>(frames, 1) * db->Dt * 8;
+    SNK_TRY(snk_buf_reserve(&db->ws_h0, tb));
+    SNK_TRY(snk_buf_reserve(&db->ws_h2, (size_t)std::max<int64_t>(frames, 1) * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_h3, (size_t)B * 8 * 4));
+    int64_t *d_plen = (int64_t *)db->ws_h3.p;
+    double *d_pc = (double *)db->ws_h3.p + B, *d_tc = d_pc + B, *d_jc = d_tc + B;
+    if (frames) SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, targets, (size_t)frames * db->Dt * 8, cudaMemcpyHostToDevice, db->stream));
+    SNK_TRY(snk_acoustic_viterbi_batch_dev(db, (const double *)db->ws_h0.p, lens, B, K, flags, (int64_t *)db->ws_h2.p, d_plen,
+                                           d_pc, d_tc, d_jc, db->stream));
+    SNK_TRY(snk_acoustic_viterbi_finish(db));
+    if (frames) SNK_CUDA(cudaMemcpyAsync(paths, db->ws_h2.p, (size_t)frames * 8, cudaMemcpyDeviceToHost, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(path_len, d_plen, (size_t)B * 8, cudaMemcpyDeviceToHost, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(path_cost, d_pc, (size_t)B * 8, cudaMemcpyDeviceToHost, db->stream));
+    if (tcost) SNK_CUDA(cudaMemcpyAsync(tcost, d_tc, (size_t)B * 8, cudaMemcpyDeviceToHost, db->stream));
+    if (jcost) SNK_CUDA(cudaMemcpyAsync(jcost, d_jc, (size_t)B * 8, cudaMemcpyDeviceToHost, db->stream));
+    SNK_CUDA(cudaStreamSynchronize(db->stream));
+    return 0;
+}
+
 int snk_greedy_path_scores(snk_db *db, const double *targets, int64_t T, const int64_t *path, int64_t P,
                            const int *twidths, int n_tstreams, const int *jwidths, int n_jstreams, double *tscores,
                            double *jscores) {
     SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    SNK_LOCK(db);
     SNK_CHECK(targets && path && twidths && jwidths && tscores && (jscores || P < 2), "NULL argument");
     SNK_CHECK(P >= 1 && P * db->m <= T, "path length %lld does not fit %lld target frames", (long long)P, (long long)T);
     int ts = 0, js = 0;

@@ -1,0 +1,195 @@
+// Database-sharded search across the GPUs of one box (BASELINE.json configs[4]).
+//
+// The reference is a single process (its only parallelism is multiprocessing.Pool over utterances,
+// script/synth_halfphone.py:897-903), so there is no reference interface to mirror: this is the exchange step the
+// north star adds.  Every rank holds a block of database rows in its own snk_db; queries are replicated.
+//
+//   snk_knn_sharded_dev : local certified top-k (global row ids)  ->  ONE ncclAllGather of the packed
+//                         [dist f64 | id i64] results over NVLink  ->  k-way merge kernel (lowest global id on ties).
+//
+// NCCL is resolved at run time (dlopen of libnccl.so.2): inside a PyTorch process this binds to the copy torch has
+// already loaded, in a plain C host to the system library; the engine has no link-time dependency on it.
+#include "common.cuh"
+#include <dlfcn.h>
+#include <string.h>
+#include <algorithm>
+
+// the slice of nccl.h this file uses (the ABI of these entry points is stable across NCCL 2.x)
+extern "C" {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclInt8 = 0, ncclInt32 = 2, ncclInt64 = 4 } ncclDataType_t;
+typedef enum { ncclSum = 0, ncclMax = 2 } ncclRedOp_t;
+}
+
+namespace {
+
+struct nccl_api {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int *) = nullptr;
+};
+nccl_api g_nccl;
+
+int load_nccl() {
+    if (g_nccl.lib) return 0;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);     // the copy already in the process (PyTorch's), if any
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    SNK_CHECK(h, "libnccl.so.2 not found: %s", dlerror());
+#define SYM(field, name)                                                          \
+    g_nccl.field = (decltype(g_nccl.field))dlsym(h, name);                         \
+    SNK_CHECK(g_nccl.field, "libnccl lacks %s", name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllGather, "ncclAllGather");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(GetErrorString, "ncclGetErrorString");
+    SYM(GetVersion, "ncclGetVersion");
+#undef SYM
+    g_nccl.lib = h;
+    return 0;
+}
+
+#define SNK_NCCL(call)                                                                          \
+    do {                                                                                        \
+        ncclResult_t r_ = (call);                                                               \
+        if (r_ != ncclSuccess) {                                                                \
+            snk_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, g_nccl.GetErrorString(r_)); \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+}  // namespace
+
+struct snk_comm_state {
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    // a sharded search whose certificates are still pending (snk_knn_sharded_finish)
+    bool pending = false;
+    int k = 0;
+    int64_t nq = 0;
+    double *d_dist = nullptr;
+    int64_t *d_idx = nullptr;
+    cudaStream_t st = nullptr;
+    int *d_nfail = nullptr;    // [2]: local failures, sum over ranks
+};
+
+void snk_comm_free(snk_db *db) {
+    if (!db->comm) return;
+    if (db->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(db->comm->comm);
+    if (db->comm->d_nfail) cudaFree(db->comm->d_nfail);
+    delete db->comm;
+    db->comm = nullptr;
+}
+
+namespace {
+
+// exchange + merge of the local results sitting in ws_ag's send half
+int exchange_and_merge(snk_db *db, cudaStream_t st) {
+    snk_comm_state *c = db->comm;
+    const size_t half = (size_t)c->nq * c->k * 8;            // bytes of one [nq, k] array
+    char *send = (char *)db->ws_ag.p;
+    char *recv = send + snk_round_up(2 * half, 256);
+    {
+        snk_prof_scope prof(db, SNK_PROF_ALLGATHER, (double)2 * half * (c->nranks - 1), st);   // bytes this rank receives
+        SNK_NCCL(g_nccl.AllGather(send, recv, 2 * half, ncclInt8, c->comm, st));
+    }
+    {
+        snk_prof_scope prof(db, SNK_PROF_MERGE, (double)2 * half * c->nranks, st);
+        SNK_TRY(snk_topk_merge_launch((const double *)recv, (const int64_t *)(recv + half), (int64_t)(2 * half / 8),
+                                      (int64_t)(2 * half / 8), c->nranks, c->nq, c->k, c->d_dist, c->d_idx, st));
+    }
+    db->counters[2] += 2;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int snk_comm_unique_id(void *id_out, int id_bytes) {
+    SNK_CHECK(id_out && id_bytes >= (int)sizeof(ncclUniqueId), "unique id buffer must hold %d bytes", (int)sizeof(ncclUniqueId));
+    SNK_TRY(load_nccl());
+    ncclUniqueId id;
+    SNK_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));
+    return 0;
+}
+
+int snk_comm_init(snk_db *db, const void *unique_id, int rank, int nranks) {
+    SNK_CHECK(db && unique_id, "NULL argument");
+    SNK_LOCK(db);
+    SNK_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank %d of %d", rank, nranks);
+    SNK_TRY(load_nccl());
+    SNK_CUDA(cudaSetDevice(db->device));
+    snk_comm_free(db);
+    snk_comm_state *c = new snk_comm_state();
+    db->comm = c;
+    c->rank = rank;
+    c->nranks = nranks;
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof(id));
+    SNK_NCCL(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    SNK_CUDA(cudaMalloc((void **)&c->d_nfail, 8));
+    return 0;
+}
+
+int snk_comm_info(snk_db *db, int *rank, int *nranks, int *nccl_version) {
+    SNK_CHECK(db && db->comm, "snk_comm_init has not been called");
+    if (rank) *rank = db->comm->rank;
+    if (nranks) *nranks = db->comm->nranks;
+    if (nccl_version) g_nccl.GetVersion(nccl_version);
+    return 0;
+}
+
+int snk_knn_sharded_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist, int64_t *d_idx,
+                        int64_t id_offset, void *stream) {
+    SNK_CHECK(db && db->comm, "snk_comm_init has not been called");
+    SNK_LOCK(db);
+    SNK_CHECK(space == SNK_SPACE_TARGET || space == SNK_SPACE_JOINT, "unknown search space %d", space);
+    SNK_CHECK(nq >= 1 && k >= 1, "bad nq / k");
+    SNK_CHECK(!db->comm->pending, "the previous sharded search has not been finished (snk_knn_sharded_finish)");
+    SNK_CUDA(cudaSetDevice(db->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    snk_comm_state *c = db->comm;
+    const size_t half = (size_t)nq * k * 8;
+    SNK_TRY(snk_buf_reserve(&db->ws_ag, snk_round_up(2 * half, 256) + 2 * half * c->nranks));
+    char *send = (char *)db->ws_ag.p;
+    // local top-k straight into the send buffer: [nq, k] distances, then [nq, k] global row ids
+    SNK_TRY(snk_knn_enqueue(db, space, dQ, nq, k, (double *)send, (int64_t *)(send + half), k, id_offset, st));
+    c->pending = true; c->k = k; c->nq = nq; c->d_dist = d_dist; c->d_idx = d_idx; c->st = st;
+    return exchange_and_merge(db, st);
+}
+
+// Completes a sharded search: local certificate repair, then all ranks agree (one 4-byte all-reduce) whether any of
+// them changed its local answer; only then is the exchange repeated.  Collective: every rank must call it.
+int snk_knn_sharded_finish(snk_db *db) {
+    SNK_CHECK(db && db->comm, "snk_comm_init has not been called");
+    SNK_LOCK(db);
+    snk_comm_state *c = db->comm;
+    if (!c->pending) return 0;
+    SNK_CUDA(cudaSetDevice(db->device));
+    const int64_t before = db->counters[1];
+    SNK_TRY(snk_knn_finish(db));                       // syncs; re-searches flagged local queries into the send buffer
+    int local = (int)(db->counters[1] - before), total[2] = {0, 0};
+    SNK_CUDA(cudaMemcpyAsync(c->d_nfail, &local, 4, cudaMemcpyHostToDevice, c->st));
+    SNK_NCCL(g_nccl.AllReduce(c->d_nfail, c->d_nfail + 1, 1, ncclInt32, ncclSum, c->comm, c->st));
+    SNK_CUDA(cudaMemcpyAsync(total, c->d_nfail, 8, cudaMemcpyDeviceToHost, c->st));
+    SNK_CUDA(cudaStreamSynchronize(c->st));
+    if (total[1] > 0) {
+        SNK_TRY(exchange_and_merge(db, c->st));
+        SNK_CUDA(cudaStreamSynchronize(c->st));
+    }
+    c->pending = false;
+    return 0;
+}
+
+}  // extern "C"

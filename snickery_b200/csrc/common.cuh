@@ -7,6 +7,7 @@
 #include <math.h>
 #include <vector>
 #include <utility>
+#include <mutex>
 #include "snk_b200.h"
 
 void snk_set_error(const char *fmt, ...);
@@ -58,7 +59,21 @@ struct snk_space {
     int ldA32, ldB32;       // leading dims of the weighted f32 matrices
 };
 
+// One slot of the pinned staging ring: small host->device uploads of the `_dev` entry points (launch metadata)
+// are copied here first, so cudaMemcpyAsync is truly asynchronous and the caller's buffer may die at once.
+struct snk_stage_slot {
+    void *host = nullptr;
+    size_t cap = 0;
+    cudaEvent_t ev = nullptr;   // recorded after the copy was enqueued; waited on (host side) before the slot is reused
+};
+constexpr int SNK_STAGE_SLOTS = 8;
+
+struct snk_comm_state;     // comm.cu: NCCL communicator + exchange workspaces
+struct snk_pending_state;  // search.cu: deferred exactness certificates of the last _dev search / greedy batch
+struct snk_acoustic_job;   // api.cu: arguments of an snk_acoustic_viterbi_batch_dev awaiting its finish
+
 struct snk_db {
+    std::recursive_mutex mu;   // entry points on one handle are serialised; different handles run concurrently
     int device = 0;
     int sm_count = 148;
     int64_t N = 0, Np = 0;
@@ -68,7 +83,8 @@ struct snk_db {
     int Djq = 0, prev_col = 0, prev_row_off = 0, cur_col = 0, cur_row_off = 0;
     int engine = SNK_ENGINE_AUTO;
     bool weights_set = false;
-    int debug_fail_mod = 0;      // SNK_DEBUG_CERT_FAIL=n: pretend every n-th query failed its certificate (tests)
+    int debug_fail_mod = 0;      // SNK_DEBUG_CERT_FAIL=n: pretend every n-th query failed its tensor-core certificate (tests)
+    int debug_fail_mod2 = 0;     // SNK_DEBUG_CERT_FAIL2=n: ... its fp32 certificate too (exercises the exhaustive scan)
     bool tc_ok = false;          // fp16 operands of the current weighting are finite (no overflow)
     // resident arrays
     float *F_raw = nullptr;   // [N, Dt]
@@ -101,6 +117,12 @@ struct snk_db {
     std::vector<cudaEvent_t> upload_events;
     cudaEvent_t ev = nullptr;
     snk_buf ws_q, ws_dist, ws_list, ws_misc, ws_io, ws_io2, ws_tiles, ws_bp, ws_tc, ws_h0, ws_h1, ws_h2, ws_h3, ws_flags;
+    snk_buf ws_kflags, ws_meta, ws_ag, ws_jv;
+    snk_stage_slot stage[SNK_STAGE_SLOTS];
+    int stage_next = 0;
+    snk_comm_state *comm = nullptr;
+    snk_pending_state *pending = nullptr;
+    snk_acoustic_job *acoustic = nullptr;
     int64_t counters[4] = {0, 0, 0, 0};
     // optional kernel timing (snk_db_profile_*)
     bool prof_on = false;
@@ -122,7 +144,19 @@ struct snk_prof_scope {
     ~snk_prof_scope() { if (idx >= 0) cudaEventRecord(db->prof[idx].e1, st); }
 };
 
+#define SNK_ENGINE_EXACT 3   // internal: exhaustive float64 scan (last stage of the certificate chain)
+
+#define SNK_LOCK(db) std::lock_guard<std::recursive_mutex> snk_lock_guard_((db)->mu)
+
 snk_space snk_make_space(const snk_db *db, int space);
+
+// api.cu: enqueue a host->device copy through the pinned staging ring (never blocks on the GPU unless the ring wraps
+// around work that is still pending eight uploads later)
+int snk_upload_async(snk_db *db, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st);
+
+// search.cu / comm.cu: lifetime hooks called by snk_db_destroy
+void snk_pending_destroy(snk_db *db);
+void snk_comm_free(snk_db *db);
 
 // ---- weights.cu
 int snk_apply_weights(snk_db *db, cudaStream_t st);
@@ -162,13 +196,26 @@ int snk_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, co
                const int *d_id, int KP, int k, double *d_dist, int64_t *d_idx, int64_t out_stride,
                int64_t id_offset, const float *d_qerr, const float *d_dberr, const float *d_qn,
                const float *d_maxn, const float *d_tau_extra, int *d_cert, int *d_nfail, int sticky,
-               const int *d_qsel, cudaStream_t st);
+               const int *d_qsel, float eps_rel, int cert_mode, cudaStream_t st);
+// certificate arithmetic of snk_rerank (cert_mode): none / fp16 tensor-core keys / fp32 direct-difference keys
+#define SNK_CERT_MODE_NONE 0
+#define SNK_CERT_MODE_FP16 1
+#define SNK_CERT_MODE_FP32 2
+// relative fp32-accumulation slack of the tensor-core key for a D-column operand row (knn_tc.cu)
+float snk_tc_eps_rel(const snk_db *db, int space);
+
+// exhaustive float64 search of the n queries h_qidx (host array of query indices): certificate of last resort
+int snk_exact_search(snk_db *db, const snk_space &sp, const double *dQ, const int *h_qidx, int n, int k, double *d_dist,
+                     int64_t *d_idx, int64_t out_stride, int64_t id_offset, cudaStream_t st);
+// merge of R sorted per-shard lists (see rerank.cu)
+int snk_topk_merge_launch(const double *d_dist_all, const int64_t *d_idx_all, int64_t stride_d, int64_t stride_i, int R,
+                          int64_t nq, int k, double *d_dist, int64_t *d_idx, cudaStream_t st);
 
 bool snk_merge_rerank_fits(int nlists, int lsz);
 int snk_merge_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, const float *d_lval,
                      const int *d_lid, int nlists, int lsz, int KP, int k, double *d_dist, int64_t *d_idx,
                      int64_t out_stride, int64_t id_offset, const float *d_qerr, const float *d_dberr,
-                     const float *d_qn, const float *d_maxn, int *d_cert, int *d_nfail, int sticky,
+                     const float *d_qn, const float *d_maxn, int *d_cert, int *d_nfail, int sticky, float eps_rel,
                      cudaStream_t st);
 
 // ---- search.cu : k-NN driver shared by snk_knn and the greedy loop
@@ -180,3 +227,6 @@ int snk_prepare_targets_dev(snk_db *db, const float *d_unnorm, int64_t rows, dou
 int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist,
                    int64_t *d_idx, int64_t out_stride, int64_t id_offset, int *d_sticky, int *d_sticky_count,
                    cudaStream_t st);
+// enqueue a search with deferred certificates; snk_knn_finish(db) completes it (see search.cu)
+int snk_knn_enqueue(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist, int64_t *d_idx,
+                    int64_t out_stride, int64_t id_offset, cudaStream_t st);

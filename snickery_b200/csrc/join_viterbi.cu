@@ -443,6 +443,7 @@ int snk_join_viterbi_batch_dev(snk_db *db, const int64_t *d_cand, const double *
                                int B, int K, unsigned flags, int64_t *d_paths, int64_t *d_path_len,
                                double *d_path_cost, double *d_tcost, double *d_jcost, void *stream) {
     SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    SNK_LOCK(db);
     SNK_CHECK(K >= 1 && K <= 160, "n_candidates must be in [1, 160] (got %d)", K);
     SNK_CUDA(cudaSetDevice(db->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -459,9 +460,9 @@ int snk_join_viterbi_batch_dev(snk_db *db, const int64_t *d_cand, const double *
     SNK_TRY(snk_buf_reserve(&db->ws_bp, (size_t)std::max<int64_t>(nframes, 1) * K * 2));
     vit_meta *d_meta = (vit_meta *)db->ws_io.p;
     int *d_t2f = (int *)((char *)db->ws_io.p + meta_bytes);
-    SNK_CUDA(cudaMemcpyAsync(d_meta, meta.data(), sizeof(vit_meta) * B, cudaMemcpyHostToDevice, st));
-    if (ntiles) SNK_CUDA(cudaMemcpyAsync(d_t2f, t2f.data(), sizeof(int) * ntiles, cudaMemcpyHostToDevice, st));
-    SNK_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope
+    // launch metadata goes through the pinned staging ring: nothing here waits for the GPU
+    SNK_TRY(snk_upload_async(db, d_meta, meta.data(), sizeof(vit_meta) * B, st));
+    if (ntiles) SNK_TRY(snk_upload_async(db, d_t2f, t2f.data(), sizeof(int) * ntiles, st));
     SNK_TRY(launch_tiles(db, d_cand, K, d_t2f, ntiles, (float *)db->ws_tiles.p, st));
     const int threads = (int)snk_round_up(K, 32);
     {   // per (utt, t): K*K*4 tile read + K*8 target costs + K*2 backpointers
@@ -514,8 +515,7 @@ int snk_join_tiles_dev(snk_db *db, const int64_t *d_cand, const int64_t *lens, i
     const int64_t ntiles = (int64_t)t2f.size();
     if (!ntiles) return 0;
     SNK_TRY(snk_buf_reserve(&db->ws_io, sizeof(int) * ntiles));
-    SNK_CUDA(cudaMemcpyAsync(db->ws_io.p, t2f.data(), sizeof(int) * ntiles, cudaMemcpyHostToDevice, st));
-    SNK_CUDA(cudaStreamSynchronize(st));
+    SNK_TRY(snk_upload_async(db, db->ws_io.p, t2f.data(), sizeof(int) * ntiles, st));
     return launch_tiles(db, d_cand, K, (const int *)db->ws_io.p, ntiles, d_tiles, st);
 }
 

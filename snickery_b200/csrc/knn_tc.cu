@@ -1017,6 +1017,22 @@ bool snk_tc_supported(const snk_db *db, const snk_space &sp, int KP) {
     return db->tc_ok && s->sp[space].ok && sp.rows >= 1;
 }
 
+// Relative slack eps_rel of the certificate: |(qn + key) - ||x~ - y~||^2| <= eps_rel (||x~||^2 + 2 max||y~||^2).
+//  * key = -2 acc, acc = sum of the exact fp16 products (x~.y~ and the embedded -0.5 ||y~||^2 pieces) accumulated in fp32
+//    over `nsteps` UMMA K = 16 instructions.  Assumption (checked by tests/test_gpu_certificate.py, which measures the
+//    constant): one instruction adds at most two roundings of 2^-23 (truncation) relative to S = sum |x_i y_i| + ||y~||^2 / 2
+//    <= (||x~||^2 + ||y~||^2) / 2 + ||y~||^2 / 2, so |key error| <= 2 (nsteps + 1) 2^-23 (||x~||^2 + 2 ||y~||^2).
+//  * the fp32 squared norms (weights.cu, search.cu: one fma chain of <= D/32 terms per lane, shuffle tree, window sum):
+//    relative error <= (D/32 + 16) 2^-24 each.
+float snk_tc_eps_rel(const snk_db *db, int space) {
+    const tc_space_host &h = ((const tc_state *)db->tc_state)->sp[space];
+    int nsteps = 0;
+    for (int i = 0; i < h.nsub; ++i) nsteps += h.sub[i].ksteps;
+    const double g_acc = 2.0 * (nsteps + 1) * 1.1920928955078125e-7;
+    const double g_norm = (h.ldq / 32.0 + 16.0) * 5.9604644775390625e-8;
+    return (float)(1.02 * (g_acc + g_norm));
+}
+
 int snk_tc_query_ld(const snk_db *db, int space) { return ((const tc_state *)db->tc_state)->sp[space].ldq; }
 const short *snk_tc_qmap(const snk_db *db, int space) { return ((const tc_state *)db->tc_state)->sp[space].d_qmap; }
 

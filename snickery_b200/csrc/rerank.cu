@@ -15,6 +15,7 @@
 
 namespace {
 
+constexpr int SNK_CERT_FP16 = 1, SNK_CERT_FP32 = 2;   // = SNK_CERT_MODE_* of common.cuh (0: no certificate)
 constexpr int RR_THREADS = 256;      // block size for few queries (latency matters: more warps per query)
 constexpr int RR_THREADS_SMALL = 128;   // block size for many queries: 12 blocks per SM, so 1024 queries are one wave
 constexpr int RR_MAX_MERGE = 2048;   // most list entries a block merges in shared memory
@@ -102,7 +103,7 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
               int64_t ostride, int64_t id_offset, int64_t nrows, const float *__restrict__ qerr,
               const float *__restrict__ dberr, const float *__restrict__ qn, const float *__restrict__ maxn,
               const float *__restrict__ tau_extra, int *__restrict__ cert, int *__restrict__ nfail, int sticky,
-              const int *__restrict__ qsel, int debug_fail_mod) {
+              const int *__restrict__ qsel, int debug_fail_mod, float eps_rel, int cert_mode) {
     extern __shared__ double sm[];
     double *q_s = sm;                       // [D]
     double *wA_s = q_s + sp.D;              // [dA]
@@ -113,12 +114,23 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
     // kMerge: [n] packed list entries, then [nwarp * KP] phase-1 winners
     unsigned long long *mkey = reinterpret_cast<unsigned long long *>(sval + KP);
     __shared__ float s_wtau[THREADS / 32];
+    __shared__ double s_qn2[THREADS / 32];   // SNK_CERT_FP32: squared norm of the float64 query
 
     const int64_t ql = blockIdx.x;                    // index into the (compact) shortlist arrays
     const int64_t q = qsel ? qsel[ql] : ql;           // index into queries / outputs / per-query bounds
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = THREADS >> 5;
 
-    for (int d = tid; d < sp.D; d += THREADS) q_s[d] = Q[q * (int64_t)sp.D + d];
+    double qn2 = 0.0;
+    for (int d = tid; d < sp.D; d += THREADS) {
+        const double x = Q[q * (int64_t)sp.D + d];
+        q_s[d] = x;
+        qn2 += x * x;
+    }
+    if (cert_mode == SNK_CERT_FP32) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) qn2 += __shfl_xor_sync(0xffffffffu, qn2, off);
+        if (lane == 0) s_qn2[warp] = qn2;
+    }
     for (int d = tid; d < sp.dA; d += THREADS) wA_s[d] = sp.wA[sp.a_col + d];
     for (int d = tid; d < sp.dB; d += THREADS) wB_s[d] = sp.wB[d % sp.Dt];
 
@@ -222,13 +234,26 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
                 if (kMerge)
                     for (int w = 0; w < THREADS / 32; ++w) mx = fminf(mx, s_wtau[w]);
                 int good = 1;
-                if (mx < INFINITY) {
+                const double dk = ok ? sqrt(v) : INFINITY;
+                if (mx < INFINITY && cert_mode == SNK_CERT_FP32) {
+                    // fp32 direct-difference keys (knn_simt.cu) of float32-rounded operands.  A dropped row y that truly
+                    // beat the k-th answer (d(x,y) < dk) would have ||y|| < ||x|| + dk, hence a rounded-operand distance
+                    // below U = dk + 2^-24 (2||x|| + dk) and an fp32 key below U^2 (1 + eps_rel), eps_rel >= (D + 3) 2^-24
+                    // bounding the rounding of D exact-sign terms.  Every dropped key is >= mx, so U^2 (1 + eps_rel) < mx
+                    // certifies the answer.
+                    double xn2 = 0.0;
+                    for (int w = 0; w < THREADS / 32; ++w) xn2 += s_qn2[w];
+                    const double U = dk + 5.9604644775390625e-8 * (2.0 * sqrt(xn2) + dk);
+                    good = (U * U * (1.0 + (double)eps_rel) < (double)mx) ? 1 : 0;
+                } else if (mx < INFINITY) {
+                    // fp16 tensor-core keys: key + ||x~||^2 is the squared distance between the ROUNDED vectors up to
+                    // eps = eps_rel (||x~||^2 + 2 max||y~||^2), the fp32 accumulation bound derived in DESIGN.md section 2
+                    // (UMMA steps + the fp32 norm sums); the triangle inequality adds the rounding of the vectors.
                     const float qq = qn ? qn[q] : 0.f;
-                    const float eps = 4e-6f * (qq + (maxn ? *maxn : 0.f));
+                    const float eps = eps_rel * (qq + 2.f * (maxn ? *maxn : 0.f));
                     const double tau2 = (double)mx + (double)qq - (double)eps;
                     const double tau = tau2 > 0.0 ? sqrt(tau2) : 0.0;
                     const double delta = (double)(qerr ? qerr[q] : 0.f) + (double)(dberr ? *dberr : 0.f);
-                    const double dk = ok ? sqrt(v) : INFINITY;
                     good = (dk + delta <= tau) ? 1 : 0;
                 }
                 if (debug_fail_mod > 0 && q % debug_fail_mod == 0) good = 0;   // test hook: exercise the re-search paths
@@ -264,20 +289,20 @@ int snk_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, co
                const int *d_id, int KP, int k, double *d_dist, int64_t *d_idx, int64_t out_stride,
                int64_t id_offset, const float *d_qerr, const float *d_dberr, const float *d_qn,
                const float *d_maxn, const float *d_tau_extra, int *d_cert, int *d_nfail, int sticky,
-               const int *d_qsel, cudaStream_t st) {
+               const int *d_qsel, float eps_rel, int cert_mode, cudaStream_t st) {
     if (nq <= 0) return 0;
     SNK_CHECK(k <= KP, "rerank: k (%d) exceeds shortlist (%d)", k, KP);
     const rr_space rs = make_rr(db, sp);
     const size_t smem = rr_smem(rs, KP, 0);
-    const int dbg = d_cert ? db->debug_fail_mod : 0;
+    const int dbg = !d_cert ? 0 : (cert_mode == SNK_CERT_FP32 ? db->debug_fail_mod2 : db->debug_fail_mod);
     if (rr_small_blocks(db, nq))
         rerank_kernel<false, RR_THREADS_SMALL><<<(unsigned)nq, RR_THREADS_SMALL, smem, st>>>(
             rs, dQ, d_val, d_id, KP, 0, 0, k, d_dist, d_idx, out_stride, id_offset, sp.rows, d_qerr, d_dberr, d_qn,
-            d_maxn, d_tau_extra, d_cert, d_nfail, sticky, d_qsel, dbg);
+            d_maxn, d_tau_extra, d_cert, d_nfail, sticky, d_qsel, dbg, eps_rel, cert_mode);
     else
         rerank_kernel<false, RR_THREADS><<<(unsigned)nq, RR_THREADS, smem, st>>>(
             rs, dQ, d_val, d_id, KP, 0, 0, k, d_dist, d_idx, out_stride, id_offset, sp.rows, d_qerr, d_dberr, d_qn,
-            d_maxn, d_tau_extra, d_cert, d_nfail, sticky, d_qsel, dbg);
+            d_maxn, d_tau_extra, d_cert, d_nfail, sticky, d_qsel, dbg, eps_rel, cert_mode);
     SNK_CUDA(cudaGetLastError());
     db->counters[2] += 1;
     return 0;
@@ -288,7 +313,7 @@ bool snk_merge_rerank_fits(int nlists, int lsz) { return nlists * lsz <= RR_MAX_
 int snk_merge_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, const float *d_lval,
                      const int *d_lid, int nlists, int lsz, int KP, int k, double *d_dist, int64_t *d_idx,
                      int64_t out_stride, int64_t id_offset, const float *d_qerr, const float *d_dberr,
-                     const float *d_qn, const float *d_maxn, int *d_cert, int *d_nfail, int sticky,
+                     const float *d_qn, const float *d_maxn, int *d_cert, int *d_nfail, int sticky, float eps_rel,
                      cudaStream_t st) {
     if (nq <= 0) return 0;
     SNK_CHECK(k <= KP, "rerank: k (%d) exceeds shortlist (%d)", k, KP);
@@ -299,34 +324,151 @@ int snk_merge_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t 
     if (rr_small_blocks(db, nq))
         rerank_kernel<true, RR_THREADS_SMALL><<<(unsigned)nq, RR_THREADS_SMALL, smem, st>>>(
             rs, dQ, d_lval, d_lid, KP, nlists, lsz, k, d_dist, d_idx, out_stride, id_offset, sp.rows, d_qerr, d_dberr,
-            d_qn, d_maxn, nullptr, d_cert, d_nfail, sticky, nullptr, dbg);
+            d_qn, d_maxn, nullptr, d_cert, d_nfail, sticky, nullptr, dbg, eps_rel, SNK_CERT_FP16);
     else
         rerank_kernel<true, RR_THREADS><<<(unsigned)nq, RR_THREADS, smem, st>>>(
             rs, dQ, d_lval, d_lid, KP, nlists, lsz, k, d_dist, d_idx, out_stride, id_offset, sp.rows, d_qerr, d_dberr,
-            d_qn, d_maxn, nullptr, d_cert, d_nfail, sticky, nullptr, dbg);
+            d_qn, d_maxn, nullptr, d_cert, d_nfail, sticky, nullptr, dbg, eps_rel, SNK_CERT_FP16);
     SNK_CUDA(cudaGetLastError());
     db->counters[2] += 1;
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// k-way merge of per-shard results after the all-gather of a database-sharded search
-// (SURVEY.md section 8e): [R, nq, k] ascending lists -> [nq, k]; ties: lowest global row id.
+// Exhaustive float64 search: the last resort for a query that neither the tensor-core nor the fp32 shortlist could
+// certify (more than a shortlist of near-ties).  Same arithmetic as the re-rank, over EVERY row: the result is the
+// float64 brute-force answer by construction.  Slow (one query at a time) and rare.
 namespace {
-__global__ void topk_merge_kernel(const double *__restrict__ dist_all, const int64_t *__restrict__ idx_all, int R,
-                                  int64_t nq, int k, double *__restrict__ odist, int64_t *__restrict__ oidx) {
+
+__global__ void exact_dist_kernel(rr_space sp, const double *__restrict__ Q, int64_t q, int64_t rows, double *__restrict__ d2) {
+    extern __shared__ double sm[];
+    double *q_s = sm, *wA_s = q_s + sp.D, *wB_s = wA_s + sp.dA;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int d = tid; d < sp.D; d += blockDim.x) q_s[d] = Q[q * (int64_t)sp.D + d];
+    for (int d = tid; d < sp.dA; d += blockDim.x) wA_s[d] = sp.wA[sp.a_col + d];
+    for (int d = tid; d < sp.dB; d += blockDim.x) wB_s[d] = sp.wB[d % sp.Dt];
+    __syncthreads();
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + tid) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = 2 * warp; u < rows; u += 2 * nwarp) {
+        double r0, r1;
+        row_pair_dist(sp, q_s, wA_s, wB_s, (int)u, u + 1 < rows ? (int)(u + 1) : -1, lane, r0, r1);
+        if (lane == 0) {
+            d2[u] = r0;
+            if (u + 1 < rows) d2[u + 1] = r1;
+        }
+    }
+}
+
+// k rounds of "smallest (d2, id) pair after the previous one"; one block
+__global__ void __launch_bounds__(1024)
+exact_select_kernel(const double *__restrict__ d2, int64_t rows, int k, double *__restrict__ odist, int64_t *__restrict__ oidx,
+                    int64_t id_offset) {
+    __shared__ double s_v[32];
+    __shared__ int s_i[32];
+    __shared__ double s_lastv;
+    __shared__ int s_lasti;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_lastv = -1.0; s_lasti = -1; }
+    __syncthreads();
+    for (int r = 0; r < k; ++r) {
+        const double lv = s_lastv;
+        const int li = s_lasti;
+        double bv = INFINITY;
+        int bi = INT_MAX;
+        for (int64_t u = tid; u < rows; u += blockDim.x) {
+            const double v = d2[u];
+            if (dpair_lt(lv, li, v, (int)u) && dpair_lt(v, (int)u, bv, bi)) { bv = v; bi = (int)u; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (dpair_lt(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_v[warp] = bv; s_i[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            bv = lane < (int)(blockDim.x >> 5) ? s_v[lane] : INFINITY;
+            bi = lane < (int)(blockDim.x >> 5) ? s_i[lane] : INT_MAX;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (dpair_lt(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) {
+                const bool ok = bi != INT_MAX;
+                odist[r] = ok ? sqrt(bv) : INFINITY;
+                oidx[r] = ok ? (int64_t)bi + id_offset : rows;
+                s_lastv = ok ? bv : INFINITY;
+                s_lasti = bi;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+int snk_exact_search(snk_db *db, const snk_space &sp, const double *dQ, const int *h_qidx, int n, int k, double *d_dist,
+                     int64_t *d_idx, int64_t out_stride, int64_t id_offset, cudaStream_t st) {
+    if (n <= 0) return 0;
+    const rr_space rs = make_rr(db, sp);
+    SNK_TRY(snk_buf_reserve(&db->ws_dist, (size_t)sp.rows * 8));
+    double *d2 = (double *)db->ws_dist.p;
+    const size_t smem = (size_t)(rs.D + rs.dA + rs.dB) * 8;
+    for (int i = 0; i < n; ++i) {
+        const int64_t q = h_qidx[i];
+        exact_dist_kernel<<<db->sm_count * 4, 256, smem, st>>>(rs, dQ, q, sp.rows, d2);
+        SNK_CUDA(cudaGetLastError());
+        exact_select_kernel<<<1, 1024, 0, st>>>(d2, sp.rows, k, d_dist + q * out_stride, d_idx + q * out_stride, id_offset);
+        SNK_CUDA(cudaGetLastError());
+        db->counters[2] += 2;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k-way merge of per-shard results after the all-gather of a database-sharded search
+// (SURVEY.md section 8e): R ascending lists of k (distance, global row id) pairs per query -> the k smallest overall;
+// ties: lowest global row id.  One block per query: the R * k pairs are staged in shared memory; the output rank of a
+// pair is its own position plus, for every other list, the number of pairs that precede it there (binary search), so the
+// work per query is R k (R log k) instead of (R k)^2.
+// Layout: dist_all + r * rank_stride_d, idx_all + r * rank_stride_i are [nq, k] arrays.
+namespace {
+__device__ __forceinline__ bool mpair_lt(double v1, int64_t i1, double v2, int64_t i2) { return v1 < v2 || (v1 == v2 && i1 < i2); }
+
+__global__ void topk_merge_kernel(const double *__restrict__ dist_all, const int64_t *__restrict__ idx_all, int64_t stride_d,
+                                  int64_t stride_i, int R, int64_t nq, int k, double *__restrict__ odist,
+                                  int64_t *__restrict__ oidx) {
+    extern __shared__ double msm[];
+    double *sv = msm;                                         // [R * k]
+    int64_t *si = reinterpret_cast<int64_t *>(sv + R * k);    // [R * k]
     const int64_t q = blockIdx.x;
     const int n = R * k;
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
         const int r = t / k, j = t % k;
-        const double v = dist_all[((int64_t)r * nq + q) * k + j];
-        const int64_t i = idx_all[((int64_t)r * nq + q) * k + j];
-        int rank = 0;
-        for (int s = 0; s < n; ++s) {
-            const int rs = s / k, js = s % k;
-            const double v2 = dist_all[((int64_t)rs * nq + q) * k + js];
-            const int64_t i2 = idx_all[((int64_t)rs * nq + q) * k + js];
-            rank += (v2 < v || (v2 == v && (i2 < i || (i2 == i && s < t)))) ? 1 : 0;
+        sv[t] = dist_all[r * stride_d + q * k + j];
+        si[t] = idx_all[r * stride_i + q * k + j];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int r = t / k, j = t % k;
+        const double v = sv[t];
+        const int64_t i = si[t];
+        int rank = j;
+        for (int r2 = 0; r2 < R; ++r2) {
+            if (r2 == r) continue;
+            // pairs of list r2 that come before (v, i); equal pairs (duplicates across shards) order by shard
+            int lo = 0, hi = k;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const double v2 = sv[r2 * k + mid];
+                const int64_t i2 = si[r2 * k + mid];
+                const bool before = mpair_lt(v2, i2, v, i) || (v2 == v && i2 == i && r2 < r);
+                if (before) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
         }
         if (rank < k) {
             odist[q * k + rank] = v;
@@ -336,12 +478,22 @@ __global__ void topk_merge_kernel(const double *__restrict__ dist_all, const int
 }
 }  // namespace
 
+int snk_topk_merge_launch(const double *d_dist_all, const int64_t *d_idx_all, int64_t stride_d, int64_t stride_i, int R,
+                          int64_t nq, int k, double *d_dist, int64_t *d_idx, cudaStream_t st) {
+    if (nq == 0) return 0;
+    const size_t smem = (size_t)R * k * 16;
+    SNK_CHECK(smem <= 200 * 1024, "merge of %d lists of %d does not fit shared memory", R, k);
+    if (smem > 48 * 1024)
+        SNK_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = R * k >= 256 ? 256 : (R * k >= 64 ? 128 : 32);
+    topk_merge_kernel<<<(unsigned)nq, threads, smem, st>>>(d_dist_all, d_idx_all, stride_d, stride_i, R, nq, k, d_dist, d_idx);
+    SNK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int snk_topk_merge_dev(int device_id, const double *d_dist_all, const int64_t *d_idx_all, int R, int64_t nq,
                                   int k, double *d_dist, int64_t *d_idx, void *stream) {
     SNK_CHECK(R >= 1 && k >= 1 && nq >= 0, "bad merge shape");
-    if (nq == 0) return 0;
     SNK_CUDA(cudaSetDevice(device_id));
-    topk_merge_kernel<<<(unsigned)nq, 128, 0, (cudaStream_t)stream>>>(d_dist_all, d_idx_all, R, nq, k, d_dist, d_idx);
-    SNK_CUDA(cudaGetLastError());
-    return 0;
+    return snk_topk_merge_launch(d_dist_all, d_idx_all, nq * k, nq * k, R, nq, k, d_dist, d_idx, (cudaStream_t)stream);
 }

@@ -95,13 +95,6 @@ cvt_q16_kernel(const double *__restrict__ Q, int D, int64_t nq, int64_t nq_pad, 
     }
 }
 
-// compact the indices of uncertified queries
-__global__ void compact_fail_kernel(const int *__restrict__ cert, int64_t nq, int *__restrict__ qsel,
-                                    int *__restrict__ count) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nq; i += (int64_t)gridDim.x * blockDim.x)
-        if (!cert[i]) qsel[atomicAdd(count, 1)] = (int)i;
-}
-
 int shortlist_size(int k) {
     const int want = k + 8;
     if (want <= 32) return 32;
@@ -111,8 +104,14 @@ int shortlist_size(int k) {
     return -1;
 }
 
+// relative rounding bound of an fp32 sum of D squared differences (each term: one rounded subtraction, one fma)
+float simt_eps_rel(int D) { return 1.05f * (float)(D + 3) * 5.9604644775390625e-8f; }
+
+// fp32 direct-difference shortlist + float64 re-rank.  With d_cert the answer is certified against the fp32 rounding
+// of the keys (rerank.cu, SNK_CERT_MODE_FP32): uncertified queries clear their flag / bump the counter (sticky).
 int search_simt(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, const int *d_qsel, int k,
-                double *d_dist, int64_t *d_idx, int64_t out_stride, int64_t id_offset, cudaStream_t st) {
+                double *d_dist, int64_t *d_idx, int64_t out_stride, int64_t id_offset, int *d_cert, int *d_nfail,
+                cudaStream_t st) {
     const int KP = shortlist_size(k);
     SNK_CHECK(KP > 0, "k = %d too large (max 248)", k);
     SNK_TRY(snk_buf_reserve(&db->ws_q, (size_t)nq * sp.D * 4));
@@ -125,7 +124,8 @@ int search_simt(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, c
     db->counters[2] += 1;
     SNK_TRY(snk_shortlist_simt(db, sp, q32, sp.D, nq, KP, val, id, st));
     SNK_TRY(snk_rerank(db, sp, dQ, nq, val, id, KP, k, d_dist, d_idx, out_stride, id_offset, nullptr, nullptr,
-                       nullptr, nullptr, nullptr, nullptr, nullptr, 0, d_qsel, st));
+                       nullptr, nullptr, nullptr, d_cert, d_nfail, 1, d_qsel, simt_eps_rel(sp.D),
+                       d_cert ? SNK_CERT_MODE_FP32 : SNK_CERT_MODE_NONE, st));
     return 0;
 }
 
@@ -146,7 +146,10 @@ int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, d
     return search_dev_impl(db, space, dQ, nq, k, d_dist, d_idx, out_stride, id_offset, d_sticky, d_sticky_count, st, nullptr);
 }
 
-// gs != nullptr: dQ [nq, D] is filled here (by the assemble kernels) before it is searched
+// gs != nullptr: dQ [nq, D] is filled here (by the assemble kernels) before it is searched.
+// Certificates are always DEFERRED: d_sticky [nq] is preset to 1 by the caller and cleared for every query whose
+// answer could not be certified, d_sticky_count counts them; nothing here synchronises (the *_finish entry points
+// look at the flags and re-search).  db->engine == SNK_ENGINE_EXACT searches exhaustively in float64 (no flags needed).
 static int search_dev_impl(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist, int64_t *d_idx,
                            int64_t out_stride, int64_t id_offset, int *d_sticky, int *d_sticky_count, cudaStream_t st,
                            const greedy_src *gs) {
@@ -158,28 +161,36 @@ static int search_dev_impl(snk_db *db, int space, const double *dQ, int64_t nq, 
     db->counters[0] += nq;
     const int KP = shortlist_size(k);
     SNK_CHECK(KP > 0, "k = %d too large (max 248)", k);
+    if (db->engine == SNK_ENGINE_EXACT) {
+        if (gs) SNK_TRY(greedy_launch_assemble(db, gs, (int)nq, const_cast<double *>(dQ), st));
+        std::vector<int> all((size_t)nq);
+        for (int64_t i = 0; i < nq; ++i) all[(size_t)i] = (int)i;
+        return snk_exact_search(db, sp, dQ, all.data(), (int)nq, k, d_dist, d_idx, out_stride, id_offset, st);
+    }
     const bool use_tc = db->engine != SNK_ENGINE_SIMT && snk_tc_supported(db, sp, KP);
     SNK_CHECK(use_tc || db->engine != SNK_ENGINE_TC, "tensor-core engine requested but this search shape is not supported by it");
+    SNK_CHECK(d_sticky && d_sticky_count, "internal: a search needs certificate flags");
     const int64_t QB = 16384;
     const bool fuse = gs && use_tc && nq <= QB;          // one batch: assemble + convert in one kernel
     if (gs && !fuse) SNK_TRY(greedy_launch_assemble(db, gs, (int)nq, const_cast<double *>(dQ), st));
-    if (!use_tc) return search_simt(db, sp, dQ, nq, nullptr, k, d_dist, d_idx, out_stride, id_offset, st);
+    if (!use_tc)
+        return search_simt(db, sp, dQ, nq, nullptr, k, d_dist, d_idx, out_stride, id_offset, d_sticky, d_sticky_count, st);
 
     // ---- tensor-core shortlist + float64 re-rank + certificate, in query batches
     const int ld16 = snk_tc_query_ld(db, space);
+    const float eps_rel = snk_tc_eps_rel(db, space);
     for (int64_t qb = 0; qb < nq; qb += QB) {
         const int64_t qn_ = std::min(QB, nq - qb);
         const int64_t qpad = snk_round_up(qn_, 256);   // two query tiles: the tensor-core kernel may pair CTAs
-        // ws_q layout: Q16 [qpad, ld16] | qn [qpad] | qerr [qpad] | tau [qpad] | cert [qpad+1] | qsel [qpad] | cnt
+        // ws_io2 layout: Q16 [qpad, ld16] | qn [qpad] | qerr [qpad] | tau [qpad]
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
         const size_t o_q16 = take((size_t)qpad * ld16 * 2), o_qn = take(qpad * 4), o_qe = take(qpad * 4),
-                     o_tau = take(qpad * 4), o_cert = take((qpad + 1) * 4), o_sel = take(qpad * 4), o_cnt = take(4);
+                     o_tau = take(qpad * 4);
         SNK_TRY(snk_buf_reserve(&db->ws_io2, off));
         char *base = (char *)db->ws_io2.p;
         __half *q16 = (__half *)(base + o_q16);
         float *qn = (float *)(base + o_qn), *qerr = (float *)(base + o_qe), *tau = (float *)(base + o_tau);
-        int *cert = (int *)(base + o_cert), *qsel = (int *)(base + o_sel), *cnt = (int *)(base + o_cnt);
         SNK_TRY(snk_buf_reserve(&db->ws_list, (size_t)qn_ * KP * 8));
         float *val = (float *)db->ws_list.p;
         int *id = (int *)(val + (size_t)qn_ * KP);
@@ -197,33 +208,17 @@ static int search_dev_impl(snk_db *db, int space, const double *dQ, int64_t nq, 
         snk_tc_lists lists;
         SNK_TRY(snk_shortlist_tc(db, space, q16, ld16, qn_, k, KP, val, id, tau, &lists, st));
         const bool joint = space == SNK_SPACE_JOINT;
-        const int sticky = d_sticky != nullptr;
-        int *cert_arr = sticky ? d_sticky + qb : cert;
-        int *cert_cnt = sticky ? d_sticky_count : cert + qn_;
-        if (!sticky) SNK_CUDA(cudaMemsetAsync(cert + qn_, 0, 4, st));
         // fused merge + re-rank: 16 exact distances are plenty for k <= 2 (the certificate still guards it)
         if (lists.valid)
             SNK_TRY(snk_merge_rerank(db, sp, Qb, qn_, lists.val, lists.id, lists.nlists, lists.lsz, k <= 2 ? 16 : KP, k,
                                      d_dist + qb * out_stride, d_idx + qb * out_stride, out_stride, id_offset, qerr,
                                      joint ? db->err_j16 : db->err_t16, qn, joint ? db->maxn_j16 : db->maxn_t16,
-                                     cert_arr, cert_cnt, sticky, st));
+                                     d_sticky + qb, d_sticky_count, 1, eps_rel, st));
         else
             SNK_TRY(snk_rerank(db, sp, Qb, qn_, val, id, KP, k, d_dist + qb * out_stride, d_idx + qb * out_stride,
                                out_stride, id_offset, qerr, joint ? db->err_j16 : db->err_t16, qn,
-                               joint ? db->maxn_j16 : db->maxn_t16, tau, cert_arr, cert_cnt, sticky, nullptr, st));
-        if (sticky) continue;   // deferred: the caller inspects the flags
-        int nfail = 0;
-        SNK_CUDA(cudaMemcpyAsync(&nfail, cert + qn_, 4, cudaMemcpyDeviceToHost, st));
-        SNK_CUDA(cudaStreamSynchronize(st));
-        if (nfail > 0) {
-            db->counters[1] += nfail;
-            SNK_CUDA(cudaMemsetAsync(cnt, 0, 4, st));
-            compact_fail_kernel<<<64, 256, 0, st>>>(cert, qn_, qsel, cnt);
-            SNK_CUDA(cudaGetLastError());
-            db->counters[2] += 1;
-            SNK_TRY(search_simt(db, sp, Qb, nfail, qsel, k, d_dist + qb * out_stride, d_idx + qb * out_stride,
-                                out_stride, id_offset, st));
-        }
+                               joint ? db->maxn_j16 : db->maxn_t16, tau, d_sticky + qb, d_sticky_count, 1, nullptr,
+                               eps_rel, SNK_CERT_MODE_FP16, st));
     }
     return 0;
 }
@@ -388,9 +383,8 @@ static int greedy_launch_assemble_cvt(snk_db *db, const greedy_src *gs, int64_t 
 
 namespace {
 
-// One pass of the greedy chain over the utterances in `meta` (sorted longest first).  With deferred
-// certificates no step synchronises: flags [n] are preset to 1 and cleared by any step whose
-// tensor-core answer could not be certified.
+// One pass of the greedy chain over the utterances in `meta` (sorted longest first).  No step synchronises: the
+// certificate flags [n] are preset to 1 and cleared by any step whose answer could not be certified.
 int greedy_run(snk_db *db, const std::vector<greedy_meta> &meta, const double *d_targets, const float *d_unnorm,
                int64_t *d_paths, double *d_step_dist, int *d_flags, int *d_count, cudaStream_t st) {
     const int B = (int)meta.size();
@@ -408,8 +402,7 @@ int greedy_run(snk_db *db, const std::vector<greedy_meta> &meta, const double *d
     double *Q = (double *)(base + meta_bytes);
     int64_t *ix = (int64_t *)(base + meta_bytes + q_bytes);
     double *dist = (double *)(base + meta_bytes + q_bytes + snk_round_up((size_t)B * 8, 256));
-    SNK_CUDA(cudaMemcpyAsync(d_meta, meta.data(), sizeof(greedy_meta) * B, cudaMemcpyHostToDevice, st));
-    SNK_CUDA(cudaStreamSynchronize(st));   // meta may be a stack-lifetime host vector
+    SNK_TRY(snk_upload_async(db, d_meta, meta.data(), sizeof(greedy_meta) * B, st));   // pinned staging: no sync
     int nact_prev = 0;
     size_t next_wait = 0;
     for (int64_t t = 0; t <= maxsteps; ++t) {
@@ -434,19 +427,157 @@ __global__ void fill_int_kernel(int *p, int64_t n, int v) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+// flags [n] preset to 1 followed by one int counter preset to 0
+int launch_flag_reset(snk_db *db, int *flags, int64_t n, cudaStream_t st) {
+    fill_int_kernel<<<64, 256, 0, st>>>(flags, n, 1);
+    SNK_CUDA(cudaGetLastError());
+    SNK_CUDA(cudaMemsetAsync(flags + n, 0, 4, st));
+    db->counters[2] += 1;
+    return 0;
+}
+
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Deferred certificates.  A `_dev` search leaves one flag per query (or per utterance) and a failure counter on the
+// device and records here what it would take to repair the answer; snk_knn_finish / snk_greedy_batch_finish wait for
+// the stream, read the counter and, if it is non-zero, repeat the flagged work with the next engine of the chain
+//     tensor-core fp16 shortlist  ->  fp32 direct-difference shortlist  ->  exhaustive float64 scan,
+// each stage certified against its own rounding, the last one exact by construction.
+struct snk_pending_state {
+    struct flagbuf { int *p; size_t cap; };
+    std::vector<flagbuf> pool;          // idle flag buffers
+    struct knn_job {
+        int space, k;
+        const double *dQ;
+        int64_t nq, out_stride, id_offset;
+        double *d_dist;
+        int64_t *d_idx;
+        cudaStream_t st;
+        flagbuf fb;
+    };
+    struct greedy_job {
+        std::vector<greedy_meta> meta;
+        const double *d_targets;
+        const float *d_unnorm;
+        int64_t *d_paths;
+        double *d_step_dist;
+        cudaStream_t st;
+        flagbuf fb;
+    };
+    std::vector<knn_job> knn;
+    std::vector<greedy_job> greedy;
+};
+
+static snk_pending_state *pending_of(snk_db *db) {
+    if (!db->pending) db->pending = new snk_pending_state();
+    return db->pending;
+}
+
+void snk_pending_destroy(snk_db *db) {
+    if (!db->pending) return;
+    for (auto &f : db->pending->pool) cudaFree(f.p);
+    for (auto &j : db->pending->knn) cudaFree(j.fb.p);
+    for (auto &j : db->pending->greedy) cudaFree(j.fb.p);
+    delete db->pending;
+    db->pending = nullptr;
+}
+
+static int take_flags(snk_db *db, int64_t n, snk_pending_state::flagbuf *out) {
+    snk_pending_state *ps = pending_of(db);
+    const size_t need = (size_t)(n + 1) * 4;
+    for (size_t i = 0; i < ps->pool.size(); ++i)
+        if (ps->pool[i].cap >= need) {
+            *out = ps->pool[i];
+            ps->pool.erase(ps->pool.begin() + i);
+            return 0;
+        }
+    out->cap = need + need / 2 + 256;
+    SNK_CUDA(cudaMalloc((void **)&out->p, out->cap));
+    return 0;
+}
+
+int snk_knn_enqueue(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist, int64_t *d_idx,
+                    int64_t out_stride, int64_t id_offset, cudaStream_t st) {
+    if (nq <= 0) return 0;
+    snk_pending_state::knn_job job{space, k, dQ, nq, out_stride, id_offset, d_dist, d_idx, st, {nullptr, 0}};
+    SNK_TRY(take_flags(db, nq, &job.fb));
+    pending_of(db)->knn.push_back(job);
+    SNK_TRY(launch_flag_reset(db, job.fb.p, nq, st));
+    return search_dev_impl(db, space, dQ, nq, k, d_dist, d_idx, out_stride, id_offset, job.fb.p, job.fb.p + nq, st, nullptr);
+}
+
+// reads the failure counter of a finished job (the stream must have been synchronised)
+static int read_count(const int *d_count, int *out) {
+    SNK_CUDA(cudaMemcpy(out, d_count, 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+static int failed_indices(const int *d_flags, int64_t n, std::vector<int> *out) {
+    std::vector<int> h((size_t)n);
+    SNK_CUDA(cudaMemcpy(h.data(), d_flags, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    out->clear();
+    for (int64_t i = 0; i < n; ++i)
+        if (!h[(size_t)i]) out->push_back((int)i);
+    return 0;
+}
+
+extern "C" int snk_knn_finish(snk_db *db) {
+    SNK_CHECK(db, "db is NULL");
+    SNK_LOCK(db);
+    if (!db->pending || db->pending->knn.empty()) return 0;
+    SNK_CUDA(cudaSetDevice(db->device));
+    snk_pending_state *ps = db->pending;
+    int rc = 0;
+    for (auto &job : ps->knn) {
+        if (!rc) rc = cudaStreamSynchronize(job.st) == cudaSuccess ? 0 : 1;
+        int nfail = 0;
+        if (!rc) rc = read_count(job.fb.p + job.nq, &nfail);
+        const snk_space sp = snk_make_space(db, job.space);
+        if (!rc && nfail > 0) {
+            // stage 2: fp32 direct differences for the flagged queries, certified against fp32 rounding
+            db->counters[1] += nfail;
+            std::vector<int> idx;
+            rc = failed_indices(job.fb.p, job.nq, &idx);
+            if (!rc) rc = snk_buf_reserve(&db->ws_kflags, idx.size() * 4);
+            int *qsel = (int *)db->ws_kflags.p;
+            if (!rc) rc = snk_upload_async(db, qsel, idx.data(), idx.size() * 4, job.st);
+            if (!rc) rc = launch_flag_reset(db, job.fb.p, job.nq, job.st);
+            if (!rc) rc = search_simt(db, sp, job.dQ, (int64_t)idx.size(), qsel, job.k, job.d_dist, job.d_idx, job.out_stride,
+                                      job.id_offset, job.fb.p, job.fb.p + job.nq, job.st);
+            if (!rc) rc = cudaStreamSynchronize(job.st) == cudaSuccess ? 0 : 1;
+            int nfail2 = 0;
+            if (!rc) rc = read_count(job.fb.p + job.nq, &nfail2);
+            if (!rc && nfail2 > 0) {
+                // stage 3: exhaustive float64 scan
+                db->counters[3] += nfail2;
+                rc = failed_indices(job.fb.p, job.nq, &idx);
+                if (!rc) rc = snk_exact_search(db, sp, job.dQ, idx.data(), (int)idx.size(), job.k, job.d_dist, job.d_idx,
+                                               job.out_stride, job.id_offset, job.st);
+                if (!rc) rc = cudaStreamSynchronize(job.st) == cudaSuccess ? 0 : 1;
+            }
+        }
+        ps->pool.push_back(job.fb);
+    }
+    ps->knn.clear();
+    if (rc) snk_set_error("snk_knn_finish failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
 
 static int greedy_batch_core(snk_db *db, const double *d_targets, const float *d_unnorm, const int64_t *lens, int B,
                              const int64_t *start_state, int64_t *d_paths, double *d_step_dist, void *stream);
 
 int snk_greedy_batch_dev(snk_db *db, const double *d_targets, const int64_t *lens, int B,
                          const int64_t *start_state, int64_t *d_paths, double *d_step_dist, void *stream) {
+    SNK_CHECK(db, "db is NULL");
+    SNK_LOCK(db);
     return greedy_batch_core(db, d_targets, nullptr, lens, B, start_state, d_paths, d_step_dist, stream);
 }
 
 int snk_greedy_batch_unnorm_dev(snk_db *db, const float *d_unnorm, const int64_t *lens, int B,
                                 const int64_t *start_state, int64_t *d_paths, double *d_step_dist, void *stream) {
     SNK_CHECK(db && db->std_set, "snk_db_set_standardisation has not been called");
+    SNK_LOCK(db);
     return greedy_batch_core(db, nullptr, d_unnorm, lens, B, start_state, d_paths, d_step_dist, stream);
 }
 
@@ -472,7 +603,9 @@ static int greedy_batch_core(snk_db *db, const double *d_targets, const float *d
     if (B <= 0) return 0;
     const int m = db->m;
     // utterance order: longest first so the active set of every step is a prefix
-    std::vector<greedy_meta> meta(B);
+    snk_pending_state::greedy_job job;
+    std::vector<greedy_meta> &meta = job.meta;
+    meta.resize(B);
     int64_t toff = 0, poff = 0;
     for (int b = 0; b < B; ++b) {
         SNK_CHECK(lens[b] >= m, "utterance %d has %lld frames, fewer than multiepoch=%d "
@@ -490,30 +623,50 @@ static int greedy_batch_core(snk_db *db, const double *d_targets, const float *d
     }
     std::stable_sort(meta.begin(), meta.end(),
                      [](const greedy_meta &a, const greedy_meta &b) { return a.nsteps > b.nsteps; });
-    // deferred certificates: flags [B] preset to 1 + a failure counter, inspected once after the last step
-    SNK_TRY(snk_buf_reserve(&db->ws_flags, (size_t)(B + 1) * 4));
-    int *flags = (int *)db->ws_flags.p, *count = flags + B;
-    fill_int_kernel<<<64, 256, 0, st>>>(flags, B, 1);
-    SNK_CUDA(cudaGetLastError());
-    SNK_CUDA(cudaMemsetAsync(count, 0, 4, st));
-    SNK_TRY(greedy_run(db, meta, d_targets, d_unnorm, d_paths, d_step_dist, flags, count, st));
-    int nfail = 0;
-    SNK_CUDA(cudaMemcpyAsync(&nfail, count, 4, cudaMemcpyDeviceToHost, st));
-    SNK_CUDA(cudaStreamSynchronize(st));
-    if (nfail > 0) {
-        // some step of some utterance was not certified: redo those utterances with the exact-arithmetic
-        // engine (their later steps depend on the doubtful choice, so the whole chain is repeated)
-        std::vector<int> hflags(B);
-        SNK_CUDA(cudaMemcpy(hflags.data(), flags, (size_t)B * 4, cudaMemcpyDeviceToHost));
-        std::vector<greedy_meta> redo;
-        for (int b = 0; b < B; ++b)
-            if (!hflags[b]) redo.push_back(meta[b]);
-        db->counters[1] += (int64_t)redo.size();
-        const int saved = db->engine;
-        db->engine = SNK_ENGINE_SIMT;
-        const int rc = greedy_run(db, redo, d_targets, d_unnorm, d_paths, d_step_dist, nullptr, nullptr, st);
-        db->engine = saved;
-        SNK_TRY(rc);
+    // deferred certificates: flags [B] preset to 1 + a failure counter, inspected by snk_greedy_batch_finish
+    SNK_TRY(take_flags(db, B, &job.fb));
+    job.d_targets = d_targets; job.d_unnorm = d_unnorm; job.d_paths = d_paths; job.d_step_dist = d_step_dist; job.st = st;
+    int *flags = job.fb.p, *count = flags + B;
+    int rc = launch_flag_reset(db, flags, B, st);
+    if (!rc) rc = greedy_run(db, meta, d_targets, d_unnorm, d_paths, d_step_dist, flags, count, st);
+    pending_of(db)->greedy.push_back(std::move(job));
+    return rc;
+}
+
+extern "C" int snk_greedy_batch_finish(snk_db *db) {
+    SNK_CHECK(db, "db is NULL");
+    SNK_LOCK(db);
+    if (!db->pending || db->pending->greedy.empty()) return 0;
+    SNK_CUDA(cudaSetDevice(db->device));
+    snk_pending_state *ps = db->pending;
+    int rc = 0;
+    for (auto &job : ps->greedy) {
+        const int B = (int)job.meta.size();
+        // some step of some utterance was not certified: redo those utterances with the next engine (their later
+        // steps depend on the doubtful choice, so the whole chain is repeated)
+        const int chain[2] = {SNK_ENGINE_SIMT, SNK_ENGINE_EXACT};
+        for (int stage = 0; stage < 2 && !rc; ++stage) {
+            rc = cudaStreamSynchronize(job.st) == cudaSuccess ? 0 : 1;
+            int nfail = 0;
+            if (!rc) rc = read_count(job.fb.p + B, &nfail);
+            if (rc || nfail == 0) break;
+            std::vector<int> idx;
+            rc = failed_indices(job.fb.p, B, &idx);
+            if (rc) break;
+            std::vector<greedy_meta> redo;
+            for (int b : idx) redo.push_back(job.meta[(size_t)b]);
+            db->counters[stage == 0 ? 1 : 3] += (int64_t)redo.size();
+            rc = launch_flag_reset(db, job.fb.p, B, job.st);
+            const int saved = db->engine;
+            db->engine = chain[stage];
+            if (!rc) rc = greedy_run(db, redo, job.d_targets, job.d_unnorm, job.d_paths, job.d_step_dist, job.fb.p, job.fb.p + B,
+                                     job.st);
+            db->engine = saved;
+            job.meta.swap(redo);   // flags of the redo run index the redo list
+            if (!rc) rc = cudaStreamSynchronize(job.st) == cudaSuccess ? 0 : 1;
+        }
+        ps->pool.push_back(job.fb);
     }
-    return 0;
+    ps->greedy.clear();
+    return rc;
 }

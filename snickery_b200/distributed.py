@@ -7,7 +7,10 @@ Two shardings exist on this path:
 * k-NN over a database too large or too slow for one GPU shards the database ROWS: every rank
   searches its block with the replicated queries, the per-shard top-k (float64 distance, int64
   global row id) are all-gathered (nq*k*16 bytes per rank -- latency bound) and k-way merged on the
-  GPU by snk_topk_merge_dev with the lowest-global-id tie rule.
+  GPU with the lowest-global-id tie rule.  On GPUs the whole exchange lives INSIDE the library
+  (snk_comm_init + snk_knn_sharded_dev: ncclAllGather + merge kernel on the caller's stream);
+  torch.distributed only carries the 128-byte NCCL id to the ranks.  CPU tensors (gloo tests of the
+  host logic) take the torch all-gather + merge_topk_reference path.
 
 The reference has no distributed code at all (only multiprocessing.Pool over utterances,
 script/synth_halfphone.py:897-903), so there is no reference interface to mirror here.
@@ -71,6 +74,15 @@ def allgather_merge_topk(dist_local, idx_local, group=None):
     return out_d, out_i
 
 
+def init_comm(db, group=None):
+    """Attach an NCCL communicator to a UnitDatabase: rank 0 draws the id, torch.distributed broadcasts it."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    db.comm_init(box[0], rank, world)
+
+
 class ShardedKnn:
     """Database rows block-partitioned over the ranks of a process group; `.query` returns the same
     (dist, idx) on every rank as a single-GPU search of the whole matrix would."""
@@ -83,6 +95,8 @@ class ShardedKnn:
         self.db = engine.UnitDatabase(F, np.zeros((F.shape[0] + 1, 1), np.float32), multiepoch=1, device=device)
         self.db.set_weights(np.asarray(weights, dtype=np.float64), np.ones(1))
         self.device = device
+        if world > 1:
+            init_comm(self.db, group)
 
     @classmethod
     def from_epoch_db(cls, F, Jc, multiepoch, wt, wj, rank, world, device, group=None):
@@ -97,27 +111,35 @@ class ShardedKnn:
         self.db = engine.UnitDatabase(Fs, Js, multiepoch=multiepoch, device=device)
         self.db.set_weights(np.asarray(wt, dtype=np.float64), np.asarray(wj, dtype=np.float64))
         self.space = engine.SPACE_JOINT
+        if world > 1:
+            init_comm(self.db, group)
         return self
 
     def query_local_dev(self, q_dev, k):
-        """q_dev: torch float64 CUDA tensor [nq, D]; returns local top-k with GLOBAL row ids."""
+        """q_dev: torch float64 CUDA tensor [nq, D]; returns this shard's certified top-k with GLOBAL row ids."""
         import torch
         nq = q_dev.shape[0]
         d = torch.empty((nq, k), dtype=torch.float64, device=q_dev.device)
         i = torch.empty((nq, k), dtype=torch.int64, device=q_dev.device)
-        lib = engine.load_library()
-        stream = torch.cuda.current_stream(q_dev.device)
-        rc = lib.snk_knn_dev(self.db.handle, getattr(self, "space", engine.SPACE_TARGET), C.c_void_p(q_dev.data_ptr()), nq, k,
-                             C.c_void_p(d.data_ptr()), C.c_void_p(i.data_ptr()), self.lo, C.c_void_p(stream.cuda_stream))
-        if rc:
-            raise engine.EngineError(lib.snk_last_error().decode())
+        stream = torch.cuda.current_stream(q_dev.device).cuda_stream
+        self.db.knn_dev(q_dev.data_ptr(), nq, k, d.data_ptr(), i.data_ptr(), getattr(self, "space", engine.SPACE_TARGET),
+                        self.lo, stream)
+        self.db.knn_finish()
         return d, i
 
     def query(self, q_dev, k):
-        d, i = self.query_local_dev(q_dev, k)
+        """Global top-k on every rank: local search + ncclAllGather + merge, all enqueued by the library."""
+        import torch
         if self.world == 1:
-            return d, i
-        return allgather_merge_topk(d, i, self.group)
+            return self.query_local_dev(q_dev, k)
+        nq = q_dev.shape[0]
+        d = torch.empty((nq, k), dtype=torch.float64, device=q_dev.device)
+        i = torch.empty((nq, k), dtype=torch.int64, device=q_dev.device)
+        stream = torch.cuda.current_stream(q_dev.device).cuda_stream
+        self.db.knn_sharded_dev(q_dev.data_ptr(), nq, k, d.data_ptr(), i.data_ptr(), getattr(self, "space", engine.SPACE_TARGET),
+                                self.lo, stream)
+        self.db.knn_sharded_finish()
+        return d, i
 
 
 class ShardedGreedy:

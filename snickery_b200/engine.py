@@ -20,7 +20,7 @@ SPACE_TARGET = 0
 SPACE_JOINT = 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 VITERBI_BEAM1 = 1
-PROF_KNN, PROF_JOIN, PROF_VITERBI = 0, 1, 2
+PROF_KNN, PROF_JOIN, PROF_VITERBI, PROF_ALLGATHER, PROF_MERGE, PROF_JOIN_VITERBI, PROF_RERANK = 0, 1, 2, 3, 4, 5, 6
 
 _lib = None
 
@@ -60,6 +60,13 @@ def load_library(path=None):
         "snk_knn": [vp, i32, P(dbl), i64, i32, P(dbl), P(i64)],
         "snk_knn_dev": [vp, i32, vp, i64, i32, vp, vp, i64, vp],
         "snk_topk_merge_dev": [i32, vp, vp, i32, i64, i32, vp, vp, vp],
+        "snk_knn_finish": [vp],
+        "snk_greedy_batch_finish": [vp],
+        "snk_comm_unique_id": [vp, i32],
+        "snk_comm_init": [vp, vp, i32, i32],
+        "snk_comm_info": [vp, P(i32), P(i32), P(i32)],
+        "snk_knn_sharded_dev": [vp, i32, vp, i64, i32, vp, vp, i64, vp],
+        "snk_knn_sharded_finish": [vp],
         "snk_greedy_batch": [vp, P(dbl), P(i64), i32, P(i64), P(i64), P(dbl)],
         "snk_greedy_batch_dev": [vp, vp, P(i64), i32, P(i64), vp, vp, vp],
         "snk_db_set_standardisation": [vp, P(dbl), P(dbl), dbl, dbl, C.c_uint],
@@ -70,6 +77,9 @@ def load_library(path=None):
         "snk_join_tiles": [vp, P(i64), P(i64), i32, i32, P(flt)],
         "snk_join_viterbi_batch": [vp, P(i64), P(dbl), P(i64), i32, i32, C.c_uint, P(i64), P(i64), P(dbl), P(dbl), P(dbl)],
         "snk_join_viterbi_batch_dev": [vp, vp, vp, P(i64), i32, i32, C.c_uint, vp, vp, vp, vp, vp, vp],
+        "snk_acoustic_viterbi_batch": [vp, P(dbl), P(i64), i32, i32, C.c_uint, P(i64), P(i64), P(dbl), P(dbl), P(dbl)],
+        "snk_acoustic_viterbi_batch_dev": [vp, vp, P(i64), i32, i32, C.c_uint, vp, vp, vp, vp, vp, vp],
+        "snk_acoustic_viterbi_finish": [vp],
         "snk_greedy_path_scores": [vp, P(dbl), i64, P(i64), i64, P(i32), i32, P(i32), i32, P(dbl), P(dbl)],
         "snk_frames_create": [P(vp), i32, i64, i32, P(flt), P(flt), P(flt), P(dbl), P(dbl), i64, P(i64), P(i64), P(i64)],
         "snk_frames_destroy": [vp],
@@ -88,11 +98,14 @@ STD_FLOAT32 = 1
 EXPORTED_SYMBOLS = ["snk_last_error", "snk_version", "snk_device_count", "snk_db_create", "snk_db_destroy",
                     "snk_db_info", "snk_db_set_weights", "snk_db_set_engine", "snk_db_counters", "snk_db_profile_enable",
                     "snk_db_profile_read", "snk_knn",
-                    "snk_knn_dev", "snk_topk_merge_dev", "snk_greedy_batch", "snk_greedy_batch_dev",
+                    "snk_knn_dev", "snk_knn_finish", "snk_topk_merge_dev", "snk_comm_unique_id", "snk_comm_init",
+                    "snk_comm_info", "snk_knn_sharded_dev", "snk_knn_sharded_finish", "snk_greedy_batch",
+                    "snk_greedy_batch_dev", "snk_greedy_batch_finish",
                     "snk_db_set_standardisation", "snk_prepare_targets", "snk_greedy_batch_unnorm",
                     "snk_greedy_batch_unnorm_dev",
                     "snk_candidate_distances", "snk_join_tiles", "snk_join_viterbi_batch",
-                    "snk_join_viterbi_batch_dev", "snk_greedy_path_scores", "snk_frames_create", "snk_frames_destroy",
+                    "snk_join_viterbi_batch_dev", "snk_acoustic_viterbi_batch", "snk_acoustic_viterbi_batch_dev",
+                    "snk_acoustic_viterbi_finish", "snk_greedy_path_scores", "snk_frames_create", "snk_frames_destroy",
                     "snk_concat_magphase_epoch"]
 
 
@@ -103,6 +116,16 @@ def _check(rc):
 
 def device_count():
     return load_library().snk_device_count()
+
+
+UNIQUE_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """The NCCL unique id (bytes) rank 0 hands to the other ranks before UnitDatabase.comm_init."""
+    buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+    _check(load_library().snk_comm_unique_id(buf, UNIQUE_ID_BYTES))
+    return buf.raw
 
 
 class UnitDatabase:
@@ -156,7 +179,7 @@ class UnitDatabase:
     def counters(self, reset=False):
         out = np.zeros(4, dtype=np.int64)
         _check(load_library().snk_db_counters(self._h, _ptr(out, C.c_int64), int(reset)))
-        return {"queries": int(out[0]), "recertified": int(out[1]), "launches": int(out[2])}
+        return {"queries": int(out[0]), "recertified": int(out[1]), "launches": int(out[2]), "exhaustive": int(out[3])}
 
     def profile_enable(self, on=True):
         _check(load_library().snk_db_profile_enable(self._h, int(on)))
@@ -165,6 +188,51 @@ class UnitDatabase:
         ms, n, w = C.c_double(), C.c_int64(), C.c_double()
         _check(load_library().snk_db_profile_read(self._h, int(which), C.byref(ms), C.byref(n), C.byref(w), int(reset)))
         return {"ms": ms.value, "launches": n.value, "work": w.value}
+
+    # -- device-pointer entry points (used by distributed.py / bench.py with torch tensors: only raw addresses cross)
+    def knn_dev(self, q_ptr, nq, k, dist_ptr, idx_ptr, space=SPACE_TARGET, id_offset=0, stream=0):
+        _check(load_library().snk_knn_dev(self._h, space, C.c_void_p(q_ptr), int(nq), int(k), C.c_void_p(dist_ptr),
+                                          C.c_void_p(idx_ptr), int(id_offset), C.c_void_p(stream)))
+
+    def knn_finish(self):
+        _check(load_library().snk_knn_finish(self._h))
+
+    def greedy_batch_dev(self, targets_ptr, lens, paths_ptr, dists_ptr=0, start_states=None, stream=0, unnorm=False):
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        ss = None if start_states is None else np.ascontiguousarray(start_states, dtype=np.int64)
+        lib = load_library()
+        fn = lib.snk_greedy_batch_unnorm_dev if unnorm else lib.snk_greedy_batch_dev
+        _check(fn(self._h, C.c_void_p(targets_ptr), _ptr(lens, C.c_int64), lens.size, _ptr(ss, C.c_int64),
+                  C.c_void_p(paths_ptr), C.c_void_p(dists_ptr) if dists_ptr else None, C.c_void_p(stream)))
+
+    def greedy_batch_finish(self):
+        _check(load_library().snk_greedy_batch_finish(self._h))
+
+    def join_viterbi_batch_dev(self, cand_ptr, tdist_ptr, lens, K, paths_ptr, plen_ptr, pcost_ptr, tcost_ptr=0, jcost_ptr=0,
+                               flags=0, stream=0):
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        _check(load_library().snk_join_viterbi_batch_dev(
+            self._h, C.c_void_p(cand_ptr), C.c_void_p(tdist_ptr), _ptr(lens, C.c_int64), lens.size, int(K), int(flags),
+            C.c_void_p(paths_ptr), C.c_void_p(plen_ptr), C.c_void_p(pcost_ptr), C.c_void_p(tcost_ptr) if tcost_ptr else None,
+            C.c_void_p(jcost_ptr) if jcost_ptr else None, C.c_void_p(stream)))
+
+    # -- database sharded over the GPUs of one box: NCCL communicator inside the library
+    def comm_init(self, unique_id, rank, nranks):
+        buf = C.create_string_buffer(bytes(unique_id), UNIQUE_ID_BYTES)
+        _check(load_library().snk_comm_init(self._h, buf, int(rank), int(nranks)))
+        self.comm_rank, self.comm_nranks = int(rank), int(nranks)
+
+    def comm_info(self):
+        r, n, v = C.c_int(), C.c_int(), C.c_int()
+        _check(load_library().snk_comm_info(self._h, C.byref(r), C.byref(n), C.byref(v)))
+        return {"rank": r.value, "nranks": n.value, "nccl_version": v.value}
+
+    def knn_sharded_dev(self, q_ptr, nq, k, dist_ptr, idx_ptr, space=SPACE_TARGET, id_offset=0, stream=0):
+        _check(load_library().snk_knn_sharded_dev(self._h, space, C.c_void_p(q_ptr), int(nq), int(k), C.c_void_p(dist_ptr),
+                                                  C.c_void_p(idx_ptr), int(id_offset), C.c_void_p(stream)))
+
+    def knn_sharded_finish(self):
+        _check(load_library().snk_knn_sharded_finish(self._h))
 
     # -- searches (host arrays in, host arrays out)
     def knn(self, Q, k, space=SPACE_TARGET):
@@ -278,6 +346,27 @@ class UnitDatabase:
                                                      _ptr(lens, C.c_int64), B, K, flags, _ptr(paths, C.c_int64),
                                                      _ptr(plen, C.c_int64), _ptr(pcost, C.c_double),
                                                      _ptr(tcost, C.c_double), _ptr(jcost, C.c_double)))
+        out, off = [], 0
+        for b in range(B):
+            out.append(paths[off:off + plen[b]].tolist() if plen[b] > 0 else [])
+            off += lens[b]
+        return out, pcost, tcost, jcost
+
+    def acoustic_viterbi_batch_cat(self, cat, lens, K, flags=0):
+        """preselect_units_acoustic + viterbi_search for a batch given as one concatenated float64 array [sum T_b, Dt]
+        (may be pinned) + lengths; the candidate lists stay on the device."""
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        B = lens.size
+        cat = np.ascontiguousarray(cat, dtype=np.float64)
+        if cat.ndim != 2 or cat.shape[1] != self.Dt or cat.shape[0] != int(lens.sum()):
+            raise ValueError("targets must be [sum(lens), %d]" % self.Dt)
+        paths = np.empty(max(int(lens.sum()), 1), dtype=np.int64)
+        plen = np.empty(B, dtype=np.int64)
+        pcost, tcost, jcost = (np.empty(B, dtype=np.float64) for _ in range(3))
+        _check(load_library().snk_acoustic_viterbi_batch(self._h, _ptr(cat, C.c_double), _ptr(lens, C.c_int64), B, int(K),
+                                                         flags, _ptr(paths, C.c_int64), _ptr(plen, C.c_int64),
+                                                         _ptr(pcost, C.c_double), _ptr(tcost, C.c_double),
+                                                         _ptr(jcost, C.c_double)))
         out, off = [], 0
         for b in range(B):
             out.append(paths[off:off + plen[b]].tolist() if plen[b] > 0 else [])

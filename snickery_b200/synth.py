@@ -365,6 +365,18 @@ class Synthesiser:
             return paths, pcost, tcost, jcost
         return paths
 
+    def synthesise_paths_acoustic_batch(self, unit_features_list, return_costs=False):
+        """preselect_units_acoustic -> viterbi_search of synth_utt (synth_halfphone.py:1611-1625) for a batch of
+        utterances in ONE engine call: the candidate lists never leave the device, only the paths come back."""
+        self._push_weights()
+        feats = [np.asarray(u, dtype=np.float64) for u in unit_features_list]
+        lens = np.array([u.shape[0] for u in feats], dtype=np.int64)
+        paths, pcost, tcost, jcost = self.db.acoustic_viterbi_batch_cat(np.concatenate(feats, axis=0), lens,
+                                                                        self.config["n_candidates"])
+        if return_costs:
+            return paths, pcost, tcost, jcost
+        return paths
+
     # ---- cost report (synth_halfphone.py:1964-1981)
     def get_scores_per_stream(self, unit_features, best_path):
         self._push_weights()

@@ -21,6 +21,16 @@ def test_reference_arm_json_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
 
 
+def test_reference_arm_halfphone_workload_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "halfphone",
+                          "--steps", "1", "--warmup", "0", "--hp-units", "3000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "target_frames_per_sec" and line["value"] > 0
+    assert line["config"]["workload"].startswith("hybrid_halfphone_default") and line["config"]["n_candidates"] == 50
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["value"] == line["value"]
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], env=env,
