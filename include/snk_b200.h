@@ -92,6 +92,15 @@ int snk_db_counters(const snk_db *db, int64_t counters[4], int reset);
 int snk_db_profile_enable(snk_db *db, int enable);
 int snk_db_profile_read(snk_db *db, int which, double *total_ms, int64_t *launches, double *work, int reset);
 
+/* ---- test instrumentation of the exactness certificate -----------------------------------------
+ * The tensor-core kernel's raw keys ||y~||^2 - 2 x~.y~ (fp32) for queries Q [nq, D] (float64, host)
+ * against rows [row0, row0 + nrows) -> keys [nq, nrows]; qnorm [nq] = the fp32 ||x~||^2 the
+ * certificate adds; *eps_rel = the relative slack it allows, *maxnorm = max_u ||y~_u||^2.
+ * tests/test_gpu_certificate.py compares key + qnorm with the float64 distance of the rounded
+ * operands and checks the measured error against eps_rel (||x~||^2 + 2 maxnorm).           */
+int snk_debug_tc_keys(snk_db *db, int space, const double *Q, int64_t nq, int64_t row0, int64_t nrows,
+                      float *keys, float *qnorm, float *eps_rel, float *maxnorm);
+
 /* ---- k-NN: tree.query(X, k) ------------------------------------------------------------
  * Replaces cKDTree.query / sklearn KDTree.query (synth_halfphone.py:1364,1384;
  * synth_simple.py:490; StashableKDTree.py).  Q is float64 [nq, D] already weighted like

@@ -203,6 +203,8 @@ int snk_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, co
 #define SNK_CERT_MODE_FP32 2
 // relative fp32-accumulation slack of the tensor-core key for a D-column operand row (knn_tc.cu)
 float snk_tc_eps_rel(const snk_db *db, int space);
+int snk_tc_debug_keys(snk_db *db, int space, const __half *dQ16, int ldq16, int64_t nq, int64_t row0, int64_t nrows,
+                      float *d_keys, int64_t ld, cudaStream_t st);
 
 // exhaustive float64 search of the n queries h_qidx (host array of query indices): certificate of last resort
 int snk_exact_search(snk_db *db, const snk_space &sp, const double *dQ, const int *h_qidx, int n, int k, double *d_dist,

@@ -1033,6 +1033,37 @@ float snk_tc_eps_rel(const snk_db *db, int space) {
     return (float)(1.02 * (g_acc + g_norm));
 }
 
+// Raw tensor-core keys (||y~||^2 - 2 x~.y~, fp32) of every query against rows [row0, row0 + nrows): the store epilogue
+// without any selection.  Test instrumentation for the certificate's error bound (snk_debug_tc_keys).
+int snk_tc_debug_keys(snk_db *db, int space, const __half *dQ16, int ldq16, int64_t nq, int64_t row0, int64_t nrows,
+                      float *d_keys, int64_t ld, cudaStream_t st) {
+    tc_state *s = (tc_state *)db->tc_state;
+    const tc_space_host &h = s->sp[space];
+    SNK_CHECK(h.ok, "tensor-core engine does not support this search space");
+    SNK_CHECK(ld % BN == 0 && ld >= snk_round_up(nrows, BN), "key matrix leading dimension must be a multiple of %d", BN);
+    const int64_t nq_pad = snk_round_up(nq, 2 * BM);
+    const int nqt = (int)snk_cdiv(nq, BM);
+    CUtensorMap mapQ;
+    SNK_TRY(make_map(s->encode, &mapQ, dQ16, (uint64_t)ldq16, (uint64_t)nq_pad, (uint64_t)ldq16, BM));
+    tc_params p;
+    memset(&p, 0, sizeof(p));
+    p.nkb = h.nkb; p.nload = h.nload; p.nsub = h.nsub; p.stages = h.stages;
+    p.embed = h.embed ? 1 : 0; p.b_bytes = h.b_bytes; p.cluster = 1;
+    memcpy(p.load, h.load, sizeof(h.load));
+    memcpy(p.sub, h.sub, sizeof(h.sub));
+    p.nq = nq; p.q16 = dQ16; p.ldq16 = ldq16; p.tile_stride = 1;
+    p.nrm = space == SNK_SPACE_JOINT ? db->nrm_j16 : db->nrm_t16;
+    const int64_t tiles = snk_cdiv(nrows, BN);
+    const tc_split ws = make_split(db, h, nqt, tiles);
+    p.row_lo = row0; p.row_hi = row0 + nrows; p.nchunks = ws.nchunks;
+    p.chunk_rows = snk_cdiv(tiles, ws.nchunks) * BN;
+    p.odist = d_keys; p.ldo = ld;
+    SNK_TRY(launch_tc(pick_kernel(MODE_STORE, 4, h.sched), ws.nqt_pad * ws.nchunks, num_threads_of(h.sched), s->smem[space], st,
+                      mapQ, s, p));
+    SNK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int snk_tc_query_ld(const snk_db *db, int space) { return ((const tc_state *)db->tc_state)->sp[space].ldq; }
 const short *snk_tc_qmap(const snk_db *db, int space) { return ((const tc_state *)db->tc_state)->sp[space].d_qmap; }
 

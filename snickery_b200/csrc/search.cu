@@ -223,6 +223,40 @@ static int search_dev_impl(snk_db *db, int space, const double *dQ, int64_t nq, 
     return 0;
 }
 
+// Test instrumentation (include/snk_b200.h: snk_debug_tc_keys): the tensor-core kernel's raw keys, the fp32 squared norm
+// of the rounded query the certificate adds to them, and the slack the certificate allows.
+extern "C" int snk_debug_tc_keys(snk_db *db, int space, const double *Q, int64_t nq, int64_t row0, int64_t nrows, float *keys,
+                                 float *qnorm, float *eps_rel, float *maxnorm) {
+    SNK_CHECK(db && Q && keys && db->weights_set, "NULL argument / weights not set");
+    SNK_LOCK(db);
+    SNK_CHECK(space == SNK_SPACE_TARGET || space == SNK_SPACE_JOINT, "unknown search space %d", space);
+    SNK_CUDA(cudaSetDevice(db->device));
+    const snk_space sp = snk_make_space(db, space);
+    SNK_CHECK(snk_tc_supported(db, sp, 32), "tensor-core engine does not support this search space");
+    SNK_CHECK(nq >= 1 && nq <= 4096 && row0 >= 0 && nrows >= 1 && row0 + nrows <= sp.rows, "bad query / row range");
+    const int ld16 = snk_tc_query_ld(db, space);
+    const int64_t qpad = snk_round_up(nq, 256), ld = snk_round_up(nrows, 128);
+    SNK_TRY(snk_buf_reserve(&db->ws_h0, (size_t)nq * sp.D * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_io2, (size_t)qpad * ld16 * 2 + (size_t)qpad * 8 + 512));
+    SNK_TRY(snk_buf_reserve(&db->ws_dist, (size_t)qpad * ld * 4));
+    __half *q16 = (__half *)db->ws_io2.p;
+    float *qn = (float *)((char *)db->ws_io2.p + snk_round_up((size_t)qpad * ld16 * 2, 256)), *qerr = qn + qpad;
+    cudaStream_t st = db->stream;
+    SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, Q, (size_t)nq * sp.D * 8, cudaMemcpyHostToDevice, st));
+    cvt_q16_kernel<<<(unsigned)std::min<int64_t>(qpad, (int64_t)db->sm_count * 16), CVT_THREADS, 0, st>>>(
+        (const double *)db->ws_h0.p, sp.D, nq, qpad, snk_tc_qmap(db, space), ld16, q16, qn, qerr);
+    SNK_CUDA(cudaGetLastError());
+    SNK_TRY(snk_tc_debug_keys(db, space, q16, ld16, nq, row0, nrows, (float *)db->ws_dist.p, ld, st));
+    SNK_CUDA(cudaMemcpy2DAsync(keys, (size_t)nrows * 4, db->ws_dist.p, (size_t)ld * 4, (size_t)nrows * 4, (size_t)nq,
+                               cudaMemcpyDeviceToHost, st));
+    if (qnorm) SNK_CUDA(cudaMemcpyAsync(qnorm, qn, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (maxnorm)
+        SNK_CUDA(cudaMemcpyAsync(maxnorm, space == SNK_SPACE_JOINT ? db->maxn_j16 : db->maxn_t16, 4, cudaMemcpyDeviceToHost, st));
+    SNK_CUDA(cudaStreamSynchronize(st));
+    if (eps_rel) *eps_rel = snk_tc_eps_rel(db, space);
+    return 0;
+}
+
 // =====================================================================================
 // greedy joint search
 namespace {

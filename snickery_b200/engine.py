@@ -61,6 +61,7 @@ def load_library(path=None):
         "snk_knn_dev": [vp, i32, vp, i64, i32, vp, vp, i64, vp],
         "snk_topk_merge_dev": [i32, vp, vp, i32, i64, i32, vp, vp, vp],
         "snk_knn_finish": [vp],
+        "snk_debug_tc_keys": [vp, i32, P(dbl), i64, i64, i64, P(flt), P(flt), P(flt), P(flt)],
         "snk_greedy_batch_finish": [vp],
         "snk_comm_unique_id": [vp, i32],
         "snk_comm_init": [vp, vp, i32, i32],
@@ -98,7 +99,7 @@ STD_FLOAT32 = 1
 EXPORTED_SYMBOLS = ["snk_last_error", "snk_version", "snk_device_count", "snk_db_create", "snk_db_destroy",
                     "snk_db_info", "snk_db_set_weights", "snk_db_set_engine", "snk_db_counters", "snk_db_profile_enable",
                     "snk_db_profile_read", "snk_knn",
-                    "snk_knn_dev", "snk_knn_finish", "snk_topk_merge_dev", "snk_comm_unique_id", "snk_comm_init",
+                    "snk_knn_dev", "snk_knn_finish", "snk_debug_tc_keys", "snk_topk_merge_dev", "snk_comm_unique_id", "snk_comm_init",
                     "snk_comm_info", "snk_knn_sharded_dev", "snk_knn_sharded_finish", "snk_greedy_batch",
                     "snk_greedy_batch_dev", "snk_greedy_batch_finish",
                     "snk_db_set_standardisation", "snk_prepare_targets", "snk_greedy_batch_unnorm",
@@ -233,6 +234,16 @@ class UnitDatabase:
 
     def knn_sharded_finish(self):
         _check(load_library().snk_knn_sharded_finish(self._h))
+
+    def debug_tc_keys(self, Q, row0, nrows, space=SPACE_TARGET):
+        """Raw tensor-core keys [nq, nrows] + the certificate's query norms, slack and max row norm (test instrumentation)."""
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        keys = np.empty((Q.shape[0], nrows), dtype=np.float32)
+        qn = np.empty(Q.shape[0], dtype=np.float32)
+        eps, mx = C.c_float(), C.c_float()
+        _check(load_library().snk_debug_tc_keys(self._h, space, _ptr(Q, C.c_double), Q.shape[0], int(row0), int(nrows),
+                                                _ptr(keys, C.c_float), _ptr(qn, C.c_float), C.byref(eps), C.byref(mx)))
+        return keys, qn, eps.value, mx.value
 
     # -- searches (host arrays in, host arrays out)
     def knn(self, Q, k, space=SPACE_TARGET):
