@@ -68,11 +68,13 @@ def build(force=False, verbose=True):
 
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(todo)))) as pool:
         list(pool.map(compile_one, todo))
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + [_obj(s) for s in _sources()] + \
+    tmp = LIB + ".tmp%d" % os.getpid()      # link beside the target, then rename: a reader never sees a half-written .so
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + [_obj(s) for s in _sources()] + \
           ["-lcudart_static", "-ldl", "-lrt", "-lpthread"]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB)
     return LIB
 
 
