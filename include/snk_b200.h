@@ -194,6 +194,10 @@ int snk_candidate_distances(snk_db *db, const int64_t *cand, const double *targe
  * with +inf where either unit is inadmissible (-1, < 1, >= N-1: :3238-3268).
  * tiles: float32 [sum_b (T_b - 1), K, K].                                               */
 int snk_join_tiles(snk_db *db, const int64_t *cand, const int64_t *lens, int B, int K, float *tiles);
+/* statistics of the last snk_join_tiles call when the tensor-core path took it (n_candidates <= 64):
+ * stats[0] = finite tile entries, stats[1] = entries whose rows nearly coincide and were therefore recomputed by direct
+ * float64 differences instead of the norm expansion (csrc/join_tc.cu).                                               */
+int snk_join_stats(const snk_db *db, int64_t stats[2]);
 
 /* ---- join + Viterbi --------------------------------------------------------------------------
  * Replaces Synthesiser.viterbi_search (synth_halfphone.py:1399-1436) =

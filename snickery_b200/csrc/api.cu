@@ -132,7 +132,8 @@ int snk_db_create(snk_db **out, int device_id, int64_t N, int Dt, int Dj, int mu
     ALLOC(db->wt, (size_t)Dt * 8);
     ALLOC(db->wj, (size_t)Dj * 8);
     ALLOC(db->Fw32, (size_t)N * Dt * 4);
-    ALLOC(db->Jw32, (size_t)(N + 1) * db->ldJ32 * 4);
+    ALLOC(db->Jw32, (size_t)(N + 2) * db->ldJ32 * 4);      // row N + 1 stays zero: the row join_tc.cu loads for absent candidates
+    cudaMemset(db->Jw32 + (size_t)(N + 1) * db->ldJ32, 0, (size_t)db->ldJ32 * 4);
     ALLOC(db->G16, (size_t)N * db->ldG16 * 2);
     ALLOC(db->S16, (size_t)(N + 1) * db->ldS16 * 2);
     ALLOC(db->nrm_t16, (size_t)N * 4);
@@ -172,6 +173,7 @@ int snk_db_destroy(snk_db *db) {
     snk_pending_destroy(db);
     delete db->acoustic;
     snk_tc_destroy(db);
+    snk_join_tc_free(db);
     for (snk_stage_slot &sl : db->stage) {
         if (sl.ev) cudaEventDestroy(sl.ev);
         if (sl.host) cudaFreeHost(sl.host);
@@ -218,6 +220,7 @@ int snk_db_set_weights(snk_db *db, const double *wt, const double *wj) {
     // fp16 range guard: weighted values (or their squared norms) beyond fp16 disable the tensor-core engine
     db->tc_ok = stats[2] < 6.0e4f && stats[3] < 6.0e4f && stats[0] == stats[0] && stats[1] == stats[1];
     db->weights_set = true;
+    db->jsplit_valid = false;   // the operand scale of join_tc.cu follows the weights; refreshed by the next Viterbi search
     return 0;
 }
 
@@ -471,6 +474,13 @@ int snk_join_tiles(snk_db *db, const int64_t *cand, const int64_t *lens, int B, 
     SNK_TRY(snk_join_tiles_dev(db, (const int64_t *)db->ws_h0.p, lens, B, K, (float *)db->ws_tiles.p, db->stream));
     SNK_CUDA(cudaMemcpyAsync(tiles, db->ws_tiles.p, (size_t)ntiles * K * K * 4, cudaMemcpyDeviceToHost, db->stream));
     SNK_CUDA(cudaStreamSynchronize(db->stream));
+    return 0;
+}
+
+int snk_join_stats(const snk_db *db, int64_t stats[2]) {
+    SNK_CHECK(db && stats, "NULL argument");
+    stats[0] = (int64_t)db->jv_stats[0];
+    stats[1] = (int64_t)db->jv_stats[1];
     return 0;
 }
 

@@ -109,6 +109,10 @@ struct snk_db {
     float *err_j16 = nullptr;   // [1]   max_u ||joint row - fp16(joint row)||
     float *maxn_t16 = nullptr;  // [1]   max_u nrm_t16
     float *maxn_j16 = nullptr;  // [1]
+    // power-of-two operand scale of the fused join-cost + Viterbi kernel (join_tc.cu), refreshed on first use after a re-weighting
+    float *split_sc = nullptr;  // {s, 1/s, max |weighted join value|}
+    bool jsplit_valid = false;
+    unsigned long long jv_stats[2] = {0, 0};   // last snk_join_tiles: finite entries, entries recomputed by direct differences
     void *tc_state = nullptr;   // tensor maps etc. (knn_tc.cu)
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host entry points: uploads that overlap the first search steps
@@ -160,6 +164,17 @@ void snk_comm_free(snk_db *db);
 
 // ---- weights.cu
 int snk_apply_weights(snk_db *db, cudaStream_t st);
+
+// ---- join_viterbi.cu / join_tc.cu
+struct snk_vit_meta {
+    int64_t frame_off;   // first frame of the utterance in cand / tdist / paths
+    int64_t tile_off;    // first lattice step (join tile) of the utterance
+    int64_t T;
+};
+bool snk_join_tc_supported(const snk_db *db, int K);
+void snk_join_tc_free(snk_db *db);
+int snk_join_tc_launch(snk_db *db, const int64_t *d_cand, int K, const int *d_tile2frame, int64_t ntiles, float *d_tiles,
+                       unsigned long long *d_stats, cudaStream_t st);
 
 // ---- knn_simt.cu : fp32 direct-difference shortlist
 // Q32 [nq, ldq] f32 queries.  Writes the KP smallest (dist^2 f32, row id i32) per query, unsorted.

@@ -168,11 +168,7 @@ __global__ void join_tile_kernel(const float *__restrict__ Jw, int ldJ, int64_t 
 }
 
 // ---------------------------------------------------------------------------------------------
-struct vit_meta {
-    int64_t frame_off;   // first frame of the utterance in cand / tdist / paths
-    int64_t tile_off;    // first tile of the utterance
-    int64_t T;
-};
+using vit_meta = snk_vit_meta;
 
 // cp.async helpers (LDGSTS): tiles are prefetched into a shared-memory ring ahead of the DP front
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
@@ -419,8 +415,10 @@ size_t tile_smem_bytes(int K, int ldJ) {
 }
 
 int launch_tiles(snk_db *db, const int64_t *d_cand, int K, const int *d_tile2frame, int64_t ntiles, float *d_tiles,
-                 cudaStream_t st) {
+                 cudaStream_t st, unsigned long long *d_stats = nullptr) {
     if (ntiles <= 0) return 0;
+    if (snk_join_tc_supported(db, K))   // n_candidates <= 64: centred norm expansion on the tensor cores (join_tc.cu)
+        return snk_join_tc_launch(db, d_cand, K, d_tile2frame, ntiles, d_tiles, d_stats, st);
     const int nb = (K + SUB - 1) / SUB;
     const int threads = (int)snk_round_up(nb * nb, 32);
     SNK_CHECK(threads <= 1024, "n_candidates = %d too large for the join-tile kernel (max 160)", K);
@@ -456,13 +454,13 @@ int snk_join_viterbi_batch_dev(snk_db *db, const int64_t *d_cand, const double *
     const size_t meta_bytes = snk_round_up(sizeof(vit_meta) * B, 256);
     const size_t t2f_bytes = snk_round_up(sizeof(int) * (size_t)std::max<int64_t>(ntiles, 1), 256);
     SNK_TRY(snk_buf_reserve(&db->ws_io, meta_bytes + t2f_bytes));
-    SNK_TRY(snk_buf_reserve(&db->ws_tiles, (size_t)std::max<int64_t>(ntiles, 1) * K * K * 4));
     SNK_TRY(snk_buf_reserve(&db->ws_bp, (size_t)std::max<int64_t>(nframes, 1) * K * 2));
     vit_meta *d_meta = (vit_meta *)db->ws_io.p;
     int *d_t2f = (int *)((char *)db->ws_io.p + meta_bytes);
     // launch metadata goes through the pinned staging ring: nothing here waits for the GPU
     SNK_TRY(snk_upload_async(db, d_meta, meta.data(), sizeof(vit_meta) * B, st));
     if (ntiles) SNK_TRY(snk_upload_async(db, d_t2f, t2f.data(), sizeof(int) * ntiles, st));
+    SNK_TRY(snk_buf_reserve(&db->ws_tiles, (size_t)std::max<int64_t>(ntiles, 1) * K * K * 4));
     SNK_TRY(launch_tiles(db, d_cand, K, d_t2f, ntiles, (float *)db->ws_tiles.p, st));
     const int threads = (int)snk_round_up(K, 32);
     {   // per (utt, t): K*K*4 tile read + K*8 target costs + K*2 backpointers
@@ -514,9 +512,14 @@ int snk_join_tiles_dev(snk_db *db, const int64_t *d_cand, const int64_t *lens, i
     SNK_TRY(build_meta(lens, B, meta, t2f));
     const int64_t ntiles = (int64_t)t2f.size();
     if (!ntiles) return 0;
-    SNK_TRY(snk_buf_reserve(&db->ws_io, sizeof(int) * ntiles));
+    const size_t t2f_bytes = snk_round_up(sizeof(int) * ntiles, 16);
+    SNK_TRY(snk_buf_reserve(&db->ws_io, t2f_bytes + 16));
     SNK_TRY(snk_upload_async(db, db->ws_io.p, t2f.data(), sizeof(int) * ntiles, st));
-    return launch_tiles(db, d_cand, K, (const int *)db->ws_io.p, ntiles, d_tiles, st);
+    unsigned long long *d_stats = (unsigned long long *)((char *)db->ws_io.p + t2f_bytes);
+    SNK_CUDA(cudaMemsetAsync(d_stats, 0, 16, st));
+    SNK_TRY(launch_tiles(db, d_cand, K, (const int *)db->ws_io.p, ntiles, d_tiles, st, d_stats));
+    SNK_CUDA(cudaMemcpyAsync(db->jv_stats, d_stats, 16, cudaMemcpyDeviceToHost, st));   // read by snk_join_stats after the caller's sync
+    return 0;
 }
 
 int snk_candidate_distances_dev(snk_db *db, const int64_t *d_cand, const double *d_targets, int64_t T, int K,

@@ -76,6 +76,7 @@ def load_library(path=None):
         "snk_greedy_batch_unnorm_dev": [vp, vp, P(i64), i32, P(i64), vp, vp, vp],
         "snk_candidate_distances": [vp, P(i64), P(dbl), i64, i32, P(dbl)],
         "snk_join_tiles": [vp, P(i64), P(i64), i32, i32, P(flt)],
+        "snk_join_stats": [vp, P(i64)],
         "snk_join_viterbi_batch": [vp, P(i64), P(dbl), P(i64), i32, i32, C.c_uint, P(i64), P(i64), P(dbl), P(dbl), P(dbl)],
         "snk_join_viterbi_batch_dev": [vp, vp, vp, P(i64), i32, i32, C.c_uint, vp, vp, vp, vp, vp, vp],
         "snk_acoustic_viterbi_batch": [vp, P(dbl), P(i64), i32, i32, C.c_uint, P(i64), P(i64), P(dbl), P(dbl), P(dbl)],
@@ -104,7 +105,7 @@ EXPORTED_SYMBOLS = ["snk_last_error", "snk_version", "snk_device_count", "snk_db
                     "snk_greedy_batch_dev", "snk_greedy_batch_finish",
                     "snk_db_set_standardisation", "snk_prepare_targets", "snk_greedy_batch_unnorm",
                     "snk_greedy_batch_unnorm_dev",
-                    "snk_candidate_distances", "snk_join_tiles", "snk_join_viterbi_batch",
+                    "snk_candidate_distances", "snk_join_tiles", "snk_join_stats", "snk_join_viterbi_batch",
                     "snk_join_viterbi_batch_dev", "snk_acoustic_viterbi_batch", "snk_acoustic_viterbi_batch_dev",
                     "snk_acoustic_viterbi_finish", "snk_greedy_path_scores", "snk_frames_create", "snk_frames_destroy",
                     "snk_concat_magphase_epoch"]
@@ -339,6 +340,12 @@ class UnitDatabase:
         _check(load_library().snk_join_tiles(self._h, _ptr(cat, C.c_int64), _ptr(lens, C.c_int64), len(cand_list), K,
                                              _ptr(tiles, C.c_float)))
         return tiles
+
+    def join_stats(self):
+        """(finite entries, entries recomputed by direct differences) of the last join_tiles call (tensor-core path)."""
+        out = np.zeros(2, dtype=np.int64)
+        _check(load_library().snk_join_stats(self._h, _ptr(out, C.c_int64)))
+        return int(out[0]), int(out[1])
 
     def join_viterbi_batch(self, cand_list, dist_list, flags=0):
         B = len(cand_list)
