@@ -22,10 +22,9 @@
 //    schedules (sched_traits); other shapes run a table-driven variant of the same kernel.
 //  * multiepoch 6 keeps the query operand in TENSOR memory (written once per CTA with tcgen05.st): the UTCHMMAs then
 //    read only the database operand from shared memory, whose bandwidth is what two smem operands saturate.
-//  * epilogues: MODE_LIST (register lists of the 4 / 8 best per query, k <= 4; MODE_PARTS hands the lists out
-//    several times per chunk for the sampling pass of larger k), MODE_STORE
-//    (keys to HBM, small databases and the sampling pass of larger k), MODE_EMIT (append every row
-//    at or below a per-query bound; larger k).
+//  * epilogues: MODE_LIST (register lists of the 4 / 8 best per query, k <= 4), MODE_STORE (keys to HBM, small
+//    databases), MODE_MINS (the smallest key of every 32-row group: sampling pass of larger k), MODE_EMIT (append every
+//    row at or below a per-query bound; larger k).
 //  * each CTA scans one (query tile, database chunk) pair; per-chunk results are merged by
 //    rerank.cu (in-block) or snk_topk_scan.  Optionally two CTAs form a cluster and share every
 //    database tile by TMA multicast (SNK_TC_CLUSTER=1).
@@ -83,8 +82,7 @@ struct tc_params {
     float *odist;           // store : [nq, ldo] keys of the scanned tiles, compacted (tile_stride > 1 = sample)
     int64_t ldo;
     int tile_stride;        // scan every tile_stride-th tile of a chunk (1 = all)
-    int flush_tiles, nparts;   // list mode: hand the lists out and start afresh every flush_tiles tiles (nparts per chunk;
-                               // 0 / 1 = one list set per chunk).  Output [nq_pad, nchunks * nparts * split, LSZ]
+    int mins_group, mins_per_chunk;   // MINS: tiles per minimum group, groups per chunk; odist [nq, nchunks * mins_per_chunk * split * 32]
     // emit mode: every row whose key is <= thr[q] is appended to the (query, chunk, half) buffer
     const float *thr;       // [nq]
     float *bufv;            // [nq_pad, nchunks * split, cap]
@@ -93,7 +91,7 @@ struct tc_params {
     int cap;
     float *tau;             // [nq] preset to thr; a buffer overflow writes -inf (certificate must fail)
 };
-constexpr int MODE_LIST = 0, MODE_STORE = 1, MODE_EMIT = 2, MODE_PARTS = 3;   // PARTS: LIST with several list sets per chunk
+constexpr int MODE_LIST = 0, MODE_STORE = 1, MODE_EMIT = 2, MODE_MINS = 3;   // MINS: the smallest key of every 32-column group
 // half-box tensor maps of the multicast path: each CTA of a pair fetches half of every database tile
 struct tc_maps_mc { CUtensorMap S_h, G_h, Gslab72; };
 constexpr int MC_ROWS0 = 72;   // rows of a frame slab fetched by rank 0 (9 swizzle atoms); rank 1 takes the other 64
@@ -458,20 +456,19 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         // emit mode state
         const float thr = (MODE == MODE_EMIT && q < p.nq) ? p.thr[q] * (HALFKEY ? 0.5f : 1.f) : -INFINITY;
         int ecnt = 0;
+        float rmin[MODE == MODE_MINS ? 32 : 1];          // MINS: running per-column extremum of the current tile group
+#pragma unroll
+        for (int j = 0; j < (MODE == MODE_MINS ? 32 : 1); ++j) rmin[j] = HALFKEY ? -INFINITY : INFINITY;
         float *ebv = MODE == MODE_EMIT ? p.bufv + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * p.cap : nullptr;
         int *ebi = MODE == MODE_EMIT ? p.bufi + (((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half) * p.cap : nullptr;
-        // list mode: lists may be handed out several times per chunk (sampling pass of the larger-k path)
-        const int NP = (MODE == MODE_PARTS && p.nparts > 1) ? p.nparts : 1;
-        int part = 0;
-        auto flush_lists = [&](int r) {
-            const size_t slot = (((size_t)q * p.nchunks + chunk) * NP + r) * EPI_SPLIT + half;
+        auto flush_lists = [&]() {
+            const size_t slot = ((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half;
             float *ov = p.oval + slot * LSZ;
             int *oi = p.oid + slot * LSZ;
 #pragma unroll
             for (int i = 0; i < LSZ; ++i) { ov[i] = OSCALE * lv[i]; oi[i] = li[i]; lv[i] = INFINITY; li[i] = -1; }
         };
         for (int t = 0; t < ntiles; ++t) {
-            if (MODE == MODE_PARTS && NP > 1 && t > 0 && t % p.flush_tiles == 0 && part + 1 < NP) flush_lists(part++);
             const int acc = t & 1;
             const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
             const int64_t r0 = row_beg + (int64_t)t * tstep;
@@ -520,12 +517,57 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     }
                 }
                 if (MODE == MODE_EMIT) {
+                    // a few rows per thousand pass the bound: maxima of 8-column groups first (three-input max tree), so
+                    // that the per-column test and its predicated stores run for the rare group that holds a hit
+                    float g[4];
+#pragma unroll
+                    for (int gi = 0; gi < 4; ++gi) {
+                        if constexpr (HALFKEY) {
+                            const float *a8 = v + 8 * gi;
+                            g[gi] = -max3(max3(a8[0], a8[1], a8[2]), max3(a8[3], a8[4], a8[5]), fmaxf(a8[6], a8[7]));
+                        } else {
+                            const float *k8 = key + 8 * gi;
+                            g[gi] = min3(min3(k8[0], k8[1], k8[2]), min3(k8[3], k8[4], k8[5]), fminf(k8[6], k8[7]));
+                        }
+                    }
+                    if (fminf(fminf(g[0], g[1]), fminf(g[2], g[3])) <= thr) {
+#pragma unroll
+                        for (int gi = 0; gi < 4; ++gi) {
+                            if (g[gi] <= thr) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    if (key[gi * 8 + e] <= thr) {
+                                        if (ecnt < p.cap) { ebv[ecnt] = OSCALE * key[gi * 8 + e]; ebi[ecnt] = (int)(r0 + c0 + gi * 8 + e); }
+                                        ++ecnt;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                } else if (MODE == MODE_MINS) {
+                    // sampling pass of the larger-k search: running minimum per column over mins_group sampled tiles.  The
+                    // 32 rows behind one minimum are whole tiles apart, so neighbouring (similar) rows of a recording do not
+                    // share a group and the k-th smallest minimum stays close to the k-th smallest key of the sample.
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        if (key[j] <= thr) {
-                            if (ecnt < p.cap) { ebv[ecnt] = OSCALE * key[j]; ebi[ecnt] = (int)(r0 + c0 + j); }
-                            ++ecnt;
+                        if constexpr (HALFKEY) rmin[j] = fmaxf(rmin[j], v[j]);     // half key = -accumulator
+                        else rmin[j] = fminf(rmin[j], key[j]);
+                    }
+                    if (c0 + 32 == (half + 1) * COLS && ((t + 1) % p.mins_group == 0 || t + 1 == ntiles)) {
+                        if (q < p.nq) {
+                            float *dst = p.odist + q * p.ldo +
+                                         (((size_t)chunk * p.mins_per_chunk + t / p.mins_group) * EPI_SPLIT + half) * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                if constexpr (HALFKEY)
+                                    *reinterpret_cast<float4 *>(dst + j) = make_float4(-OSCALE * rmin[j], -OSCALE * rmin[j + 1],
+                                                                                       -OSCALE * rmin[j + 2], -OSCALE * rmin[j + 3]);
+                                else
+                                    *reinterpret_cast<float4 *>(dst + j) = make_float4(rmin[j], rmin[j + 1], rmin[j + 2], rmin[j + 3]);
+                            }
                         }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) rmin[j] = HALFKEY ? -INFINITY : INFINITY;
                     }
                 } else if (MODE == MODE_STORE) {
                     if (q < p.nq) {
@@ -589,10 +631,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             p.bufn[((size_t)q * p.nchunks + chunk) * EPI_SPLIT + half] = min(ecnt, p.cap);
             if (ecnt > p.cap && q < p.nq) p.tau[q] = -INFINITY;   // rows were lost: never certify
         }
-        if (MODE == MODE_LIST || MODE == MODE_PARTS) {
-            flush_lists(part);
-            for (int r = part + 1; r < NP; ++r) flush_lists(r);     // parts this chunk had no tiles for: empty lists
-        }
+        if (MODE == MODE_LIST) flush_lists();
     }
     tc_fence_before();
     __syncthreads();
@@ -609,25 +648,142 @@ __global__ void chunk_tau_kernel(const float *__restrict__ oval, int64_t nq, int
         tau[q] = t;
     }
 }
-// thr[q] = k-th smallest of the KP sampled keys (+inf if the sample held fewer than k rows); tau starts equal
-__global__ void kth_select_kernel(const float *__restrict__ val, const int *__restrict__ id, int64_t nq, int KP, int k,
-                                  float *__restrict__ thr, float *__restrict__ tau) {
-    const int lane = threadIdx.x & 31;
-    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (q >= nq) return;
-    float kth = INFINITY;
-    for (int t = lane; t < KP; t += 32) {
-        const float v = id[q * KP + t] >= 0 ? val[q * KP + t] : INFINITY;
-        int rank = 0;
-        for (int j = 0; j < KP; ++j) {
-            const float w = id[q * KP + j] >= 0 ? val[q * KP + j] : INFINITY;
-            rank += (w < v || (w == v && j < t)) ? 1 : 0;
-        }
-        if (rank == k - 1) kth = v;
+// ---- order statistics by bisection on the key bits: one warp per query, no lists, no sorting
+// monotone map float -> uint32 (negative keys are possible: a key is ||y||^2 - 2 x.y)
+__device__ __forceinline__ uint32_t key_bits(float v) {
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_value(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+// smallest t with #{u <= t} >= K over the n staged keys (n >= K >= 1)
+__device__ __forceinline__ uint32_t warp_kth(const uint32_t *keys, int n, int K, int lane) {
+    uint32_t lo = 0u, hi = 0xffffffffu;
+#pragma unroll 1
+    for (int it = 0; it < 32; ++it) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        int cnt = 0;
+        for (int i = lane; i < n; i += 32) cnt += keys[i] <= mid;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt >= K) hi = mid; else lo = mid + 1u;
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) kth = fminf(kth, __shfl_xor_sync(0xffffffffu, kth, off));
-    if (lane == 0) { thr[q] = kth; tau[q] = kth; }
+    return lo;
+}
+constexpr int SEL_WARPS = 4;
+constexpr int SEL_CAP = 1024;      // keys staged in shared memory per query; longer rows bisect over global memory
+
+// thr[q] = tau[q] = k-th smallest of row q of vals [nq, ld] (n <= ld values; +inf if fewer than k are finite)
+__global__ void __launch_bounds__(SEL_WARPS * 32) kth_of_rows_kernel(const float *__restrict__ vals, int64_t nq, int n,
+                                                                     int64_t ld, int k, float *__restrict__ thr,
+                                                                     float *__restrict__ tau) {
+    __shared__ uint32_t sk[SEL_WARPS][SEL_CAP];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * SEL_WARPS + w;
+    if (q >= nq) return;
+    const float *row = vals + q * ld;
+    float out = INFINITY;
+    if (n >= k) {
+        uint32_t t;
+        if (n <= SEL_CAP) {
+            for (int i = lane; i < n; i += 32) sk[w][i] = key_bits(__ldg(row + i));
+            __syncwarp();
+            t = warp_kth(sk[w], n, k, lane);
+        } else {
+            uint32_t lo = 0u, hi = 0xffffffffu;
+#pragma unroll 1
+            for (int it = 0; it < 32; ++it) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                int cnt = 0;
+                for (int i = lane; i < n; i += 32) cnt += key_bits(__ldg(row + i)) <= mid;
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                if (cnt >= k) hi = mid; else lo = mid + 1u;
+            }
+            t = lo;
+        }
+        out = key_value(t);
+        if (out != out) out = INFINITY;
+    }
+    if (lane == 0) { thr[q] = out; tau[q] = out; }
+}
+
+// The KP smallest (key, id) pairs of the emit buffers of query q (nseg buffers of cap slots, cnt[q, seg] filled), unsorted;
+// missing entries: key +inf, id -1.  Ties at the KP-th key: first come.
+__global__ void __launch_bounds__(SEL_WARPS * 32) select_segments_kernel(const float *__restrict__ bufv, const int *__restrict__ bufi,
+                                                                         const int *__restrict__ bufn, int64_t nq, int nseg,
+                                                                         int cap, int KP, float *__restrict__ oval,
+                                                                         int *__restrict__ oid) {
+    __shared__ uint32_t sk[SEL_WARPS][SEL_CAP];
+    __shared__ int si[SEL_WARPS][SEL_CAP];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * SEL_WARPS + w;
+    if (q >= nq) return;
+    float *ov = oval + q * KP;
+    int *oi = oid + q * KP;
+    int tot = 0;
+    for (int sg = 0; sg < nseg; ++sg) tot += min(cap, bufn[q * nseg + sg]);
+    int nout = 0;
+    if (tot <= SEL_CAP) {
+        int base = 0;
+        for (int sg = 0; sg < nseg; ++sg) {
+            const int c = min(cap, bufn[q * nseg + sg]);
+            const size_t off = ((size_t)q * nseg + sg) * cap;
+            for (int i = lane; i < c; i += 32) {
+                sk[w][base + i] = key_bits(__ldg(bufv + off + i));
+                si[w][base + i] = __ldg(bufi + off + i);
+            }
+            base += c;
+        }
+        __syncwarp();
+        if (tot <= KP) {
+            for (int i = lane; i < tot; i += 32) { ov[i] = key_value(sk[w][i]); oi[i] = si[w][i]; }
+            nout = tot;
+        } else {
+            const uint32_t t = warp_kth(sk[w], tot, KP, lane);
+            // everything below t, then keys equal to t until KP entries are out
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int i0 = 0; i0 < tot && nout < KP; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool take = i < tot && (pass == 0 ? sk[w][i] < t : sk[w][i] == t);
+                    const unsigned m = __ballot_sync(0xffffffffu, take);
+                    const int pos = nout + __popc(m & ((1u << lane) - 1u));
+                    if (take && pos < KP) { ov[pos] = key_value(sk[w][i]); oi[pos] = si[w][i]; }
+                    nout = min(KP, nout + __popc(m));
+                }
+            }
+        }
+    } else {
+        // rare: more rows at or below the bound than fit in shared memory -- bisect over the buffers in global memory
+        uint32_t lo = 0u, hi = 0xffffffffu;
+#pragma unroll 1
+        for (int it = 0; it < 32; ++it) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            int cnt = 0;
+            for (int sg = 0; sg < nseg; ++sg) {
+                const int c = min(cap, bufn[q * nseg + sg]);
+                const size_t off = ((size_t)q * nseg + sg) * cap;
+                for (int i = lane; i < c; i += 32) cnt += key_bits(__ldg(bufv + off + i)) <= mid;
+            }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (cnt >= KP) hi = mid; else lo = mid + 1u;
+        }
+        const uint32_t t = lo;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int sg = 0; sg < nseg; ++sg) {
+                const int c = min(cap, bufn[q * nseg + sg]);
+                const size_t off = ((size_t)q * nseg + sg) * cap;
+                for (int i0 = 0; i0 < c && nout < KP; i0 += 32) {
+                    const int i = i0 + lane;
+                    const uint32_t u = i < c ? key_bits(__ldg(bufv + off + i)) : 0xffffffffu;
+                    const bool take = i < c && (pass == 0 ? u < t : u == t);
+                    const unsigned m = __ballot_sync(0xffffffffu, take);
+                    const int pos = nout + __popc(m & ((1u << lane) - 1u));
+                    if (take && pos < KP) { ov[pos] = key_value(u); oi[pos] = __ldg(bufi + off + i); }
+                    nout = min(KP, nout + __popc(m));
+                }
+            }
+    }
+    for (int i = nout + lane; i < KP; i += 32) { ov[i] = INFINITY; oi[i] = -1; }
 }
 __global__ void fill_kernel(float *p, int64_t n, float v) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
@@ -797,7 +953,7 @@ tc_kernel_fn pick_sched(int sched) {
 tc_kernel_fn pick_kernel(int mode, int lsz, int sched) {
     if (mode == MODE_STORE) return pick_sched<MODE_STORE, 4>(sched);
     if (mode == MODE_EMIT) return pick_sched<MODE_EMIT, 4>(sched);
-    if (mode == MODE_PARTS) return pick_sched<MODE_PARTS, 8>(sched);
+    if (mode == MODE_MINS) return pick_sched<MODE_MINS, 4>(sched);
     return lsz == 4 ? pick_sched<MODE_LIST, 4>(sched) : pick_sched<MODE_LIST, 8>(sched);
 }
 
@@ -867,7 +1023,7 @@ int snk_tc_prepare(snk_db *db) {
     }
     for (int sched : {0, 2, 11, 13, 14, 16, 12, 21, 23, 24, 26})
         for (int v = 0; v < 5; ++v)
-            SNK_CUDA(cudaFuncSetAttribute((const void *)pick_kernel(v == 2 ? MODE_STORE : v == 3 ? MODE_EMIT : v == 4 ? MODE_PARTS : MODE_LIST,
+            SNK_CUDA(cudaFuncSetAttribute((const void *)pick_kernel(v == 2 ? MODE_STORE : v == 3 ? MODE_EMIT : v == 4 ? MODE_MINS : MODE_LIST,
                                                                     v == 1 ? 8 : 4, sched),
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return 0;
@@ -1038,58 +1194,62 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         return 0;
     };
 
-    // Sampled threshold + emit: the k-th smallest key of every 8th tile bounds the k-th smallest key overall
+    // Sampled threshold + emit: the k-th smallest key of a sample of rows bounds the k-th smallest key overall
     // from above; a second pass over the whole database appends every row at or below that bound to
-    // per-(query, chunk, half) buffers (about 8k rows per query), and only those are scanned and re-ranked.
+    // per-(query, chunk, half) buffers (a few k rows per query), and only those are scanned and re-ranked.
     // Rows above the bound cannot be among the k nearest, so the bound itself is the certificate's tau.
-    constexpr int SAMPLE = 8;
-    if (!getenv("SNK_TC_NOEMIT") && sp.rows / SAMPLE >= (int64_t)16 * k && row_tiles >= 4 * SAMPLE) {
+    // The sampling pass is a max tree per 32 keys, so it runs at the speed of the contraction: every 4th tile costs a
+    // quarter of a pass and halves the emitted rows against every 8th (SNK_TC_SAMPLE overrides).
+    // never every tile: a bound that hugs the k-th key leaves the certificate no room for the fp16 rounding of the keys
+    int SAMPLE = getenv("SNK_TC_SAMPLE") ? std::max(2, atoi(getenv("SNK_TC_SAMPLE"))) : 4;
+    while (SAMPLE > 2 && snk_cdiv(row_tiles, SAMPLE) * BN < 4 * (2 * k + 16)) SAMPLE /= 2;
+    if (!getenv("SNK_TC_NOEMIT") && snk_cdiv(row_tiles, SAMPLE) * BN >= 2 * (2 * k + 16) && sp.rows >= (int64_t)64 * k) {
         {
-            // Sampling pass in list mode: every SAMPLE-th tile, the 8 smallest keys per (query, chunk part, column
-            // range), lists handed out `parts` times per chunk so that their union holds >= 2k + 16 actual rows.
-            // The k-th smallest of ANY set of actual rows bounds the k-th smallest overall from above, so the
-            // k-th of that union is a valid (and, with 2k+ entries, tight) threshold -- and no key goes to HBM.
-            const int lsz = 8;
+            // Sampling pass: column-wise minima over groups of sampled tiles (every SAMPLE-th).  Each of them is the key of an
+            // actual row, and the k-th smallest of ANY set of actual rows bounds the k-th smallest overall from above.
             const int64_t stiles = snk_cdiv(row_tiles, SAMPLE);
             const tc_split ss = make_split(db, h, nqt, stiles);
-            const int per_chunk = ss.nchunks * epi_split_of(h.sched) * lsz;
-            int parts = 1;
-            while (per_chunk * parts < 2 * k + 16 && parts < 32) parts *= 2;
             const int64_t chunk_tiles = snk_cdiv(stiles, ss.nchunks);
+            const int split = epi_split_of(h.sched);
+            // tiles per group so that a query ends up with about 768 minima (at least 2k + 16)
+            int group = (int)std::max<int64_t>(1, std::min<int64_t>(64, stiles * split * 32 / 768));
+            while (group > 1 && snk_cdiv(chunk_tiles, group) * ss.nchunks * split * 32 < 2 * k + 16) --group;
+            p.mins_group = group;
+            p.mins_per_chunk = (int)snk_cdiv(chunk_tiles, group);
+            const int64_t nmin = (int64_t)ss.nchunks * p.mins_per_chunk * split * 32;   // minima per query (groups no tile reaches: +inf)
             p.cluster = ss.cluster;
             p.tile_stride = SAMPLE;
             p.row_lo = 0; p.row_hi = sp.rows; p.nchunks = ss.nchunks;
             p.chunk_rows = chunk_tiles * BN * SAMPLE;
-            p.nparts = parts;
-            p.flush_tiles = (int)std::max<int64_t>(1, snk_cdiv(chunk_tiles, parts));
-            const int nl = ss.nchunks * parts * epi_split_of(h.sched);
-            const size_t nlist = (size_t)nq_pad * nl * lsz;
-            SNK_TRY(snk_buf_reserve(&db->ws_dist, nlist * 8));
-            p.oval = (float *)db->ws_dist.p;
-            p.oid = (int *)(p.oval + nlist);
+            SNK_TRY(snk_buf_reserve(&db->ws_dist, (size_t)nq_pad * nmin * 4));
+            p.odist = (float *)db->ws_dist.p; p.ldo = nmin;
+            fill_kernel<<<db->sm_count * 4, 256, 0, st>>>(p.odist, nq * nmin, INFINITY);   // groups no tile covers
+            SNK_CUDA(cudaGetLastError());
             {
                 snk_prof_scope prof(db, SNK_PROF_KNN, 2.0 * (double)nq * (double)stiles * BN * sp.D, st);
-                SNK_TRY(launch_tc(pick_kernel(MODE_PARTS, lsz, h.sched), ss.nqt_pad * ss.nchunks, num_threads_of(h.sched), smem,
+                SNK_TRY(launch_tc(pick_kernel(MODE_MINS, 4, h.sched), ss.nqt_pad * ss.nchunks, num_threads_of(h.sched), smem,
                                   st, mapQ, s, p));
             }
             SNK_CUDA(cudaGetLastError());
+            db->counters[2] += 2;
+            SNK_TRY(snk_buf_reserve(&db->ws_misc, (size_t)nq_pad * 4));
+            // The bound is the (2k)-th smallest minimum, not the k-th: the certificate needs the k-th exact distance to stay
+            // below the bound by the fp16 rounding of the keys, and a bound that hugs the k-th key fails it for a few
+            // queries in 10^5 (measured; each failure costs a re-search).  SNK_TC_KMARGIN overrides the factor.
+            const int margin = getenv("SNK_TC_KMARGIN") ? std::max(1, atoi(getenv("SNK_TC_KMARGIN"))) : 2;
+            const int kth = (int)std::min<int64_t>(nmin, (int64_t)k * margin);
+            kth_of_rows_kernel<<<(unsigned)snk_cdiv(nq, SEL_WARPS), SEL_WARPS * 32, 0, st>>>(p.odist, nq, (int)nmin, nmin, kth,
+                                                                                          (float *)db->ws_misc.p, d_tau);
+            SNK_CUDA(cudaGetLastError());
             db->counters[2] += 1;
-            for (int64_t q0 = 0; q0 < nq; q0 += 32768) {
-                const int64_t n = std::min<int64_t>(32768, nq - q0);
-                SNK_TRY(snk_topk_scan(db, p.oval + (size_t)q0 * nl * lsz, p.oid + (size_t)q0 * nl * lsz, n, (int64_t)nl * lsz,
-                                      (int64_t)nl * lsz, 0, KP, true, d_val + q0 * KP, d_id + q0 * KP, st));
-            }
-            p.tile_stride = 1; p.nparts = 0; p.flush_tiles = 0; p.oval = nullptr; p.oid = nullptr;
+            p.tile_stride = 1; p.odist = nullptr; p.ldo = 0;
         }
-        SNK_TRY(snk_buf_reserve(&db->ws_misc, (size_t)nq_pad * 4));
         float *thr = (float *)db->ws_misc.p;
-        kth_select_kernel<<<(unsigned)snk_cdiv(nq * 32, 256), 256, 0, st>>>(d_val, d_id, nq, KP, k, thr, d_tau);
-        SNK_CUDA(cudaGetLastError());
         const tc_split ws = make_split(db, h, nqt, row_tiles);
         const int nchunks = ws.nchunks;
         p.cluster = ws.cluster;
         const int nlists = nchunks * epi_split_of(h.sched);
-        // neighbours cluster on a few consecutive rows (trajectories), so one list may take most of the ~8k
+        // neighbours cluster on a few consecutive rows (trajectories), so one list may take most of the
         // expected rows and an unsampled tile may hide a whole cluster: size every list for 20k rows (measured:
         // 10k overflowed for 0.17 % of the queries, 20k for 0.001 %)
         const int cap = getenv("SNK_TC_EMIT_CAP") ? atoi(getenv("SNK_TC_EMIT_CAP")) :
@@ -1111,12 +1271,10 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
         }
         SNK_CUDA(cudaGetLastError());
         db->counters[2] += 3;
-        for (int64_t q0 = 0; q0 < nq; q0 += 32768) {
-            const int64_t n = std::min<int64_t>(32768, nq - q0);
-            SNK_TRY(snk_topk_scan(db, p.bufv + (size_t)q0 * nlists * cap, p.bufi + (size_t)q0 * nlists * cap, n,
-                                  (int64_t)nlists * cap, (int64_t)nlists * cap, 0, KP, true, d_val + q0 * KP, d_id + q0 * KP,
-                                  st, p.bufn + (size_t)q0 * nlists, cap));
-        }
+        select_segments_kernel<<<(unsigned)snk_cdiv(nq, SEL_WARPS), SEL_WARPS * 32, 0, st>>>(p.bufv, p.bufi, p.bufn, nq, nlists, cap,
+                                                                                           KP, d_val, d_id);
+        SNK_CUDA(cudaGetLastError());
+        db->counters[2] += 1;
         return 0;
     }
     // small databases: plain store + scan of every key

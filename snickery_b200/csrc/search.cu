@@ -170,7 +170,7 @@ static int search_dev_impl(snk_db *db, int space, const double *dQ, int64_t nq, 
     const bool use_tc = db->engine != SNK_ENGINE_SIMT && snk_tc_supported(db, sp, KP);
     SNK_CHECK(use_tc || db->engine != SNK_ENGINE_TC, "tensor-core engine requested but this search shape is not supported by it");
     SNK_CHECK(d_sticky && d_sticky_count, "internal: a search needs certificate flags");
-    const int64_t QB = 16384;
+    const int64_t QB = std::max<int64_t>(4096, (int64_t)db->sm_count * 128 / 256 * 256);   // one 128-query tile per SM and batch (148 SMs: 18944)
     const bool fuse = gs && use_tc && nq <= QB;          // one batch: assemble + convert in one kernel
     if (gs && !fuse) SNK_TRY(greedy_launch_assemble(db, gs, (int)nq, const_cast<double *>(dQ), st));
     if (!use_tc)
