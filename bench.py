@@ -460,10 +460,12 @@ def run_ours(args):
     if not args.no_secondary:
         hp = block_halfphone(D, args, headline=False)
         sk = block_sharded_knn(D, args)
+        sg = block_sharded_greedy(D, db, wt, syn.join_weight_vector, cfg)
         if rank == 0:
             out["halfphone"] = hp["halfphone"]
             out["viterbi_sharded"] = hp["viterbi_sharded"]
             out["sharded_knn"] = sk
+            out["sharded_greedy"] = sg
     # ---- CPU baseline + parity of the GPU path against it (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu:
         run, frames, info = cpu_reference_rate(db, cfg, wt, 1, budget_s=12.0, seed=99)
@@ -544,6 +546,52 @@ def block_single_utterance(D, syn, db, wt):
             "us_per_step": ms * 1e3 / steps, "hbm_floor_us_per_step": floor_us, "frac_of_hbm_floor": floor_us / (ms * 1e3 / steps),
             "operand_bytes_per_step": operand_bytes, "peak_kind": kind,
             "host_call_ms": host_ms, "host_call_frames_per_s": UTT_FRAMES / (host_ms / 1e3)}
+
+
+def block_sharded_greedy(D, db, wt, wj, cfg):
+    """greedy chain over a row-sharded joint database, one exchange per time step inside the
+    library (snk_greedy_sharded_batch_dev).  configs[1] database split over the ranks; step latency at B = 1024 and B = 1;
+    the paths of a few utterances are compared with the replicated single-GPU search on rank 0's own database."""
+    import torch
+    from snickery_b200 import Synthesiser, distributed as dd, engine
+    rank, world, dev = D.rank, D.world, D.dev
+    F, Jc = db["F"], db["Jc"]
+    sg = dd.ShardedGreedy(F, Jc, MULTIEPOCH, wt, wj, rank, world, D.local)
+    steps = 12
+    res = {"what": "configs[1] joint rows sharded by row block over the ranks, join contexts replicated; one grouped "
+                   "ncclAllGather (distance, global row, bound: B x 24 bytes per rank) + arg-min / certificate kernel per "
+                   "time step, enqueued by the library; device time, max over ranks",
+           "n_gpus": world, "rows_per_gpu": int(sg.knn.hi - sg.knn.lo), "steps": steps, "cases": []}
+    for B in (1024, 1):
+        tg = torch.from_numpy(make_batch(F, wt, B, steps * MULTIEPOCH, seed=31 + B).reshape(B, steps * MULTIEPOCH, -1)).to(dev)
+        paths = [None]
+
+        def run():
+            paths[0] = sg.search(tg)
+
+        run()                                  # NCCL connects lazily on the first collective: keep that out of the numbers
+        sg.knn.db.profile_enable(True)
+        ms = D.timed(run, reps=3, warm=0)
+        ag = sg.knn.db.profile_read(engine.PROF_ALLGATHER)
+        sg.knn.db.profile_enable(False)
+        case = {"utterances": B, "us_per_step": ms * 1e3 / steps,
+                # event time around the grouped collective on this rank: includes waiting for the slowest rank to arrive
+                "us_per_step_in_allgather": (ag["ms"] * 1e3 / ag["launches"]) if ag["launches"] else 0.0,
+                "nvlink_bytes_received_per_rank_per_step": B * 24 * (world - 1)}
+        if B == 1024:       # parity sample against the replicated database
+            case["paths_hash"] = int(paths[0].sum().item() % 1000003)
+        res["cases"].append(case)
+        keep = paths[0][:4].cpu().numpy() if B == 1024 else None
+        if B == 1024 and rank == 0:
+            ref = Synthesiser(cfg, F, Jc, device=D.local)
+            utts = [tg[b].cpu().numpy() for b in range(4)]
+            want = ref.greedy_joint_search_batch(utts)
+            res["first_4_paths_equal_replicated_search"] = bool(all(keep[b].tolist() == want[b] for b in range(4)))
+            ref.db.close()
+    c = sg.knn.db.counters()
+    res["exactness"] = {"utterances_recertified": int(c["recertified"]), "exhaustive_f64": int(c["exhaustive"])}
+    sg.knn.db.close()
+    return res
 
 
 def block_halfphone(D, args, headline):

@@ -151,6 +151,21 @@ int snk_greedy_batch_dev(snk_db *db, const double *d_targets, const int64_t *len
                          void *stream);
 /* completes every snk_greedy_batch_dev / snk_greedy_batch_unnorm_dev enqueued since the last call */
 int snk_greedy_batch_finish(snk_db *db);
+/* Greedy search over a database whose joint rows are sharded by row block across the ranks of the communicator
+ * (snk_comm_init; SURVEY.md section 8e, row "greedy chain with sharded DB" -- the reference has no counterpart, its chain
+ * is script/synth_simple.py:487-501 in one process).  This handle holds joint rows [id_offset, id_offset + rows) of the
+ * rows_full searchable rows, i.e. frames F[id_offset : id_offset + rows + m - 1] and join contexts
+ * Jc[id_offset : id_offset + rows + m]; d_Jc_full is the replicated un-weighted float32 join matrix [rows_full + m, Dj] on
+ * this device, from which every rank reads the previous join vector (current_join_rep[u] = Jw[u + m]).  After every time
+ * step the ranks exchange their best (distance, global row) per utterance and the distance below which no row outside
+ * their shortlist can lie -- one grouped ncclAllGather of B * 24 bytes plus an arg-min kernel, enqueued by the library --
+ * so the paths (GLOBAL row ids) are identical on every rank, and an answer is certified when it is not above any rank's
+ * bound (a shard that holds no close row cannot certify its own best, and does not need to).
+ * Collective: every rank calls it with the same targets, then snk_greedy_batch_finish (which also agrees, with one
+ * all-reduce, on the utterances whose certificates failed on any rank and repeats them in lockstep).               */
+int snk_greedy_sharded_batch_dev(snk_db *db, const double *d_targets, const int64_t *lens, int B, const int64_t *start_state,
+                                 const float *d_Jc_full, int64_t rows_full, int64_t id_offset, int64_t *d_paths,
+                                 double *d_step_dist, void *stream);
 
 /* ---- target preparation -----------------------------------------------------
  * Replaces the per-utterance host numpy between compose_speech and the search

@@ -19,8 +19,8 @@ extern "C" {
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef enum { ncclSuccess = 0 } ncclResult_t;
-typedef enum { ncclInt8 = 0, ncclInt32 = 2, ncclInt64 = 4 } ncclDataType_t;
-typedef enum { ncclSum = 0, ncclMax = 2 } ncclRedOp_t;
+typedef enum { ncclInt8 = 0, ncclInt32 = 2, ncclInt64 = 4, ncclFloat64 = 8 } ncclDataType_t;
+typedef enum { ncclSum = 0, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
 }
 
 namespace {
@@ -34,6 +34,8 @@ struct nccl_api {
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     ncclResult_t (*GetVersion)(int *) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
 };
 nccl_api g_nccl;
 
@@ -53,6 +55,8 @@ int load_nccl() {
     SYM(AllReduce, "ncclAllReduce");
     SYM(GetErrorString, "ncclGetErrorString");
     SYM(GetVersion, "ncclGetVersion");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
 #undef SYM
     g_nccl.lib = h;
     return 0;
@@ -112,6 +116,75 @@ int exchange_and_merge(snk_db *db, cudaStream_t st) {
 }
 
 }  // namespace
+
+namespace {
+
+// per query the best (distance, global row) pair over the R ranks' answers (ties: lowest global row), judged against every
+// rank's bound on the rows it did not look at exactly: the answer stands iff it is not above any of them
+__global__ void best_of_ranks_kernel(const double *__restrict__ dist_all, const int64_t *__restrict__ ix_all,
+                                     const double *__restrict__ bound_all, int R, int n, double *__restrict__ dist,
+                                     int64_t *__restrict__ ix, int *__restrict__ flags, int *__restrict__ count) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    double bd = dist_all[b], lb = bound_all ? bound_all[b] : INFINITY;
+    int64_t bi = ix_all[b];
+    for (int r = 1; r < R; ++r) {
+        const double d = dist_all[(size_t)r * n + b];
+        const int64_t i = ix_all[(size_t)r * n + b];
+        if (d < bd || (d == bd && i < bi)) { bd = d; bi = i; }
+        if (bound_all) lb = fmin(lb, bound_all[(size_t)r * n + b]);
+    }
+    dist[b] = bd;
+    ix[b] = bi;
+    if (!(bd <= lb)) {           // some shard may hide a closer row: every rank clears the same flag
+        if (flags[b]) atomicAdd(count, 1);
+        flags[b] = 0;
+    }
+}
+
+}  // namespace
+
+// One exchange step of the database-sharded greedy search: every rank's best
+// (distance, global row) per utterance and its bound on the rows outside its shortlist -> one grouped ncclAllGather
+// (n * 24 bytes per rank) -> arg-min over the ranks, written back in place, certificate flags cleared where the global
+// best is not below every bound.  Collective: every rank calls it with the same n.
+int snk_comm_exchange_best(snk_db *db, double *d_dist, int64_t *d_ix, double *d_bound, int n, int *d_flags, int *d_count,
+                           cudaStream_t st) {
+    snk_comm_state *c = db->comm;
+    SNK_CHECK(c, "snk_comm_init has not been called");
+    if (n <= 0) return 0;
+    const size_t one = snk_round_up((size_t)n * 8 * c->nranks, 256);
+    SNK_TRY(snk_buf_reserve(&db->ws_ag, 3 * one));
+    double *rd = (double *)db->ws_ag.p;
+    int64_t *ri = (int64_t *)((char *)db->ws_ag.p + one);
+    double *rb = (double *)((char *)db->ws_ag.p + 2 * one);
+    if (c->nranks > 1) {
+        snk_prof_scope prof(db, SNK_PROF_ALLGATHER, (double)n * 24 * (c->nranks - 1), st);
+        SNK_NCCL(g_nccl.GroupStart());
+        SNK_NCCL(g_nccl.AllGather(d_dist, rd, (size_t)n, ncclFloat64, c->comm, st));
+        SNK_NCCL(g_nccl.AllGather(d_ix, ri, (size_t)n, ncclInt64, c->comm, st));
+        if (d_bound) SNK_NCCL(g_nccl.AllGather(d_bound, rb, (size_t)n, ncclFloat64, c->comm, st));
+        SNK_NCCL(g_nccl.GroupEnd());
+    } else {
+        rd = d_dist; ri = d_ix; rb = d_bound;      // a communicator of one: judge the local answer against the local bound
+    }
+    if (!d_bound) rb = nullptr;          // exhaustive float64 stage: exact by construction, nothing to judge
+    best_of_ranks_kernel<<<(n + 127) / 128, 128, 0, st>>>(rd, ri, rb, c->nranks, n, d_dist, d_ix, d_flags, d_count);
+    SNK_CUDA(cudaGetLastError());
+    db->counters[2] += 2;
+    return 0;
+}
+
+// element-wise minimum of an int array over the ranks, in place (certificate flags: 0 = some rank could not certify)
+int snk_comm_allreduce_min(snk_db *db, int *d_buf, int n, cudaStream_t st) {
+    snk_comm_state *c = db->comm;
+    SNK_CHECK(c, "snk_comm_init has not been called");
+    if (n <= 0 || c->nranks == 1) return 0;
+    SNK_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, ncclInt32, ncclMin, c->comm, st));
+    return 0;
+}
+
+int snk_comm_nranks(const snk_db *db) { return db->comm ? db->comm->nranks : 1; }
 
 extern "C" {
 

@@ -86,6 +86,9 @@ struct snk_db {
     int debug_fail_mod = 0;      // SNK_DEBUG_CERT_FAIL=n: pretend every n-th query failed its tensor-core certificate (tests)
     int debug_fail_mod2 = 0;     // SNK_DEBUG_CERT_FAIL2=n: ... its fp32 certificate too (exercises the exhaustive scan)
     bool tc_ok = false;          // fp16 operands of the current weighting are finite (no overflow)
+    // database-sharded greedy search: the re-rank writes, per query, the distance below which no row outside its shortlist
+    // can lie (instead of clearing certificate flags); the ranks judge the exchanged answer against all bounds (comm.cu)
+    double *cert_bound_out = nullptr;
     // resident arrays
     float *F_raw = nullptr;   // [N, Dt]
     float *Jc_raw = nullptr;  // [N+1, Dj]
@@ -161,6 +164,11 @@ int snk_upload_async(snk_db *db, void *d_dst, const void *h_src, size_t bytes, c
 // search.cu / comm.cu: lifetime hooks called by snk_db_destroy
 void snk_pending_destroy(snk_db *db);
 void snk_comm_free(snk_db *db);
+// comm.cu: exchange step of the database-sharded greedy search, flag agreement, communicator size (1 without one)
+int snk_comm_exchange_best(snk_db *db, double *d_dist, int64_t *d_ix, double *d_bound, int n, int *d_flags, int *d_count,
+                           cudaStream_t st);
+int snk_comm_allreduce_min(snk_db *db, int *d_buf, int n, cudaStream_t st);
+int snk_comm_nranks(const snk_db *db);
 
 // ---- weights.cu
 int snk_apply_weights(snk_db *db, cudaStream_t st);

@@ -103,7 +103,8 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
               int64_t ostride, int64_t id_offset, int64_t nrows, const float *__restrict__ qerr,
               const float *__restrict__ dberr, const float *__restrict__ qn, const float *__restrict__ maxn,
               const float *__restrict__ tau_extra, int *__restrict__ cert, int *__restrict__ nfail, int sticky,
-              const int *__restrict__ qsel, int debug_fail_mod, float eps_rel, int cert_mode) {
+              const int *__restrict__ qsel, int debug_fail_mod, float eps_rel, int cert_mode,
+              double *__restrict__ bound_out) {
     extern __shared__ double sm[];
     double *q_s = sm;                       // [D]
     double *wA_s = q_s + sp.D;              // [dA]
@@ -234,6 +235,7 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
                 if (kMerge)
                     for (int w = 0; w < THREADS / 32; ++w) mx = fminf(mx, s_wtau[w]);
                 int good = 1;
+                double bound = INFINITY;     // every row outside the shortlist is at least this far from the query
                 const double dk = ok ? sqrt(v) : INFINITY;
                 if (mx < INFINITY && cert_mode == SNK_CERT_FP32) {
                     // fp32 direct-difference keys (knn_simt.cu) of float32-rounded operands.  A dropped row y that truly
@@ -245,6 +247,9 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
                     for (int w = 0; w < THREADS / 32; ++w) xn2 += s_qn2[w];
                     const double U = dk + 5.9604644775390625e-8 * (2.0 * sqrt(xn2) + dk);
                     good = (U * U * (1.0 + (double)eps_rel) < (double)mx) ? 1 : 0;
+                    // the same inequality solved for dk: any dk below this value would have been certified
+                    bound = (sqrt(fmax((double)mx, 0.0) / (1.0 + (double)eps_rel)) - 1.1920928955078125e-7 * sqrt(xn2)) /
+                            (1.0 + 5.9604644775390625e-8) * (1.0 - 1e-12);
                 } else if (mx < INFINITY) {
                     // fp16 tensor-core keys: key + ||x~||^2 is the squared distance between the ROUNDED vectors up to
                     // eps = eps_rel (||x~||^2 + 2 max||y~||^2), the fp32 accumulation bound derived in DESIGN.md section 2
@@ -255,8 +260,16 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
                     const double tau = tau2 > 0.0 ? sqrt(tau2) : 0.0;
                     const double delta = (double)(qerr ? qerr[q] : 0.f) + (double)(dberr ? *dberr : 0.f);
                     good = (dk + delta <= tau) ? 1 : 0;
+                    bound = tau - delta;
                 }
-                if (debug_fail_mod > 0 && q % debug_fail_mod == 0) good = 0;   // test hook: exercise the re-search paths
+                if (debug_fail_mod > 0 && q % debug_fail_mod == 0) { good = 0; bound = -INFINITY; }   // test hook: exercise the re-search paths
+                if (bound_out) {
+                    // database-sharded search: this shard's answer is only one candidate for the global one.  Export the
+                    // bound instead of judging here: after the exchange the global best d* is certified iff d* <= bound
+                    // on every rank (a rank whose own best is certified has d* <= its best <= its bound).
+                    bound_out[q] = bound;
+                    good = 1;
+                }
                 // sticky: the flag array is preset to 1 by the caller and only ever cleared (a greedy batch
                 // inspects it once, after the last step, instead of synchronising every step)
                 if (!sticky) cert[q] = good;
@@ -298,11 +311,11 @@ int snk_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, co
     if (rr_small_blocks(db, nq))
         rerank_kernel<false, RR_THREADS_SMALL><<<(unsigned)nq, RR_THREADS_SMALL, smem, st>>>(
             rs, dQ, d_val, d_id, KP, 0, 0, k, d_dist, d_idx, out_stride, id_offset, sp.rows, d_qerr, d_dberr, d_qn,
-            d_maxn, d_tau_extra, d_cert, d_nfail, sticky, d_qsel, dbg, eps_rel, cert_mode);
+            d_maxn, d_tau_extra, d_cert, d_nfail, sticky, d_qsel, dbg, eps_rel, cert_mode, d_cert ? db->cert_bound_out : nullptr);
     else
         rerank_kernel<false, RR_THREADS><<<(unsigned)nq, RR_THREADS, smem, st>>>(
             rs, dQ, d_val, d_id, KP, 0, 0, k, d_dist, d_idx, out_stride, id_offset, sp.rows, d_qerr, d_dberr, d_qn,
-            d_maxn, d_tau_extra, d_cert, d_nfail, sticky, d_qsel, dbg, eps_rel, cert_mode);
+            d_maxn, d_tau_extra, d_cert, d_nfail, sticky, d_qsel, dbg, eps_rel, cert_mode, d_cert ? db->cert_bound_out : nullptr);
     SNK_CUDA(cudaGetLastError());
     db->counters[2] += 1;
     return 0;
@@ -324,11 +337,11 @@ int snk_merge_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t 
     if (rr_small_blocks(db, nq))
         rerank_kernel<true, RR_THREADS_SMALL><<<(unsigned)nq, RR_THREADS_SMALL, smem, st>>>(
             rs, dQ, d_lval, d_lid, KP, nlists, lsz, k, d_dist, d_idx, out_stride, id_offset, sp.rows, d_qerr, d_dberr,
-            d_qn, d_maxn, nullptr, d_cert, d_nfail, sticky, nullptr, dbg, eps_rel, SNK_CERT_FP16);
+            d_qn, d_maxn, nullptr, d_cert, d_nfail, sticky, nullptr, dbg, eps_rel, SNK_CERT_FP16, d_cert ? db->cert_bound_out : nullptr);
     else
         rerank_kernel<true, RR_THREADS><<<(unsigned)nq, RR_THREADS, smem, st>>>(
             rs, dQ, d_lval, d_lid, KP, nlists, lsz, k, d_dist, d_idx, out_stride, id_offset, sp.rows, d_qerr, d_dberr,
-            d_qn, d_maxn, nullptr, d_cert, d_nfail, sticky, nullptr, dbg, eps_rel, SNK_CERT_FP16);
+            d_qn, d_maxn, nullptr, d_cert, d_nfail, sticky, nullptr, dbg, eps_rel, SNK_CERT_FP16, d_cert ? db->cert_bound_out : nullptr);
     SNK_CUDA(cudaGetLastError());
     db->counters[2] += 1;
     return 0;

@@ -419,23 +419,30 @@ namespace {
 
 // One pass of the greedy chain over the utterances in `meta` (sorted longest first).  No step synchronises: the
 // certificate flags [n] are preset to 1 and cleared by any step whose answer could not be certified.
+// sh (database-sharded search): this handle holds a block of the joint rows; row ids become global
+// by sh->id_offset, after every step the ranks exchange their best (distance, row) pairs, and the previous join vector is
+// read from the replicated join contexts sh->Jc_full (current_join_rep[u] = Jw[u + m], synth_simple.py:213-214,501).
+struct greedy_shard { const float *Jc_full; int64_t id_offset; };
+
 int greedy_run(snk_db *db, const std::vector<greedy_meta> &meta, const double *d_targets, const float *d_unnorm,
-               int64_t *d_paths, double *d_step_dist, int *d_flags, int *d_count, cudaStream_t st) {
+               int64_t *d_paths, double *d_step_dist, int *d_flags, int *d_count, cudaStream_t st,
+               const greedy_shard *sh = nullptr) {
     const int B = (int)meta.size();
     const std_params stp{db->std_mean, db->std_sd, db->wt, db->uv_special, db->uv_scale, db->std_f32};
     const int m = db->m;
     const snk_space sp = snk_make_space(db, SNK_SPACE_JOINT);
     int64_t maxsteps = 0;
     for (const greedy_meta &g : meta) maxsteps = std::max(maxsteps, g.nsteps);
-    // ws_io: meta | Q [B, D] | ix [B] | dist [B]
+    // ws_io: meta | Q [B, D] | ix [B] | dist [B] | bound [B]
     const size_t meta_bytes = snk_round_up(sizeof(greedy_meta) * B, 256);
     const size_t q_bytes = snk_round_up((size_t)B * sp.D * 8, 256);
-    SNK_TRY(snk_buf_reserve(&db->ws_io, meta_bytes + q_bytes + (size_t)B * 16 + 512));
+    SNK_TRY(snk_buf_reserve(&db->ws_io, meta_bytes + q_bytes + (size_t)B * 24 + 1024));
     char *base = (char *)db->ws_io.p;
     greedy_meta *d_meta = (greedy_meta *)base;
     double *Q = (double *)(base + meta_bytes);
     int64_t *ix = (int64_t *)(base + meta_bytes + q_bytes);
     double *dist = (double *)(base + meta_bytes + q_bytes + snk_round_up((size_t)B * 8, 256));
+    double *bound = (double *)(base + meta_bytes + q_bytes + 2 * snk_round_up((size_t)B * 8, 256));   // sharded search only
     SNK_TRY(snk_upload_async(db, d_meta, meta.data(), sizeof(greedy_meta) * B, st));   // pinned staging: no sync
     int nact_prev = 0;
     size_t next_wait = 0;
@@ -446,12 +453,17 @@ int greedy_run(snk_db *db, const std::vector<greedy_meta> &meta, const double *d
         // chunked uploads (host entry point): step t may start once its target frames have landed
         while (next_wait < db->step_waits.size() && db->step_waits[next_wait].first <= t)
             SNK_CUDA(cudaStreamWaitEvent(st, db->step_waits[next_wait++].second, 0));
-        const greedy_src gs{d_meta, nact_prev, t, d_targets, d_unnorm, stp, db->Dt, m, db->Jc_raw, db->wj, db->Dj, db->Djq,
+        const greedy_src gs{d_meta, nact_prev, t, d_targets, d_unnorm, stp, db->Dt, m, sh ? sh->Jc_full : db->Jc_raw, db->wj, db->Dj, db->Djq,
                             db->prev_row_off, db->prev_col, db->cur_row_off, db->cur_col, ix, dist, d_paths, d_step_dist};
-        if (nact > 0)   // the search builds its queries from the recipe (one fused kernel on the tensor-core path)
-            SNK_TRY(search_dev_impl(db, SNK_SPACE_JOINT, Q, nact, 1, dist, ix, 1, 0, d_flags, d_count, st, &gs));
-        else            // every utterance has finished: only the last choices remain to be written out
+        if (nact > 0) {   // the search builds its queries from the recipe (one fused kernel on the tensor-core path)
+            db->cert_bound_out = sh ? bound : nullptr;
+            const int rcs = search_dev_impl(db, SNK_SPACE_JOINT, Q, nact, 1, dist, ix, 1, sh ? sh->id_offset : 0, d_flags, d_count, st, &gs);
+            db->cert_bound_out = nullptr;
+            SNK_TRY(rcs);
+            if (sh) SNK_TRY(snk_comm_exchange_best(db, dist, ix, db->engine == SNK_ENGINE_EXACT ? nullptr : bound, nact, d_flags, d_count, st));
+        } else {          // every utterance has finished: only the last choices remain to be written out
             SNK_TRY(greedy_launch_assemble(db, &gs, 0, Q, st));
+        }
         nact_prev = nact;
     }
     return 0;
@@ -498,6 +510,9 @@ struct snk_pending_state {
         double *d_step_dist;
         cudaStream_t st;
         flagbuf fb;
+        bool sharded = false;
+        const float *Jc_full = nullptr;
+        int64_t id_offset = 0;
     };
     std::vector<knn_job> knn;
     std::vector<greedy_job> greedy;
@@ -599,7 +614,8 @@ extern "C" int snk_knn_finish(snk_db *db) {
 }
 
 static int greedy_batch_core(snk_db *db, const double *d_targets, const float *d_unnorm, const int64_t *lens, int B,
-                             const int64_t *start_state, int64_t *d_paths, double *d_step_dist, void *stream);
+                             const int64_t *start_state, int64_t *d_paths, double *d_step_dist, void *stream,
+                             const float *d_Jc_full = nullptr, int64_t rows_full = 0, int64_t id_offset = 0);
 
 int snk_greedy_batch_dev(snk_db *db, const double *d_targets, const int64_t *lens, int B,
                          const int64_t *start_state, int64_t *d_paths, double *d_step_dist, void *stream) {
@@ -613,6 +629,24 @@ int snk_greedy_batch_unnorm_dev(snk_db *db, const float *d_unnorm, const int64_t
     SNK_CHECK(db && db->std_set, "snk_db_set_standardisation has not been called");
     SNK_LOCK(db);
     return greedy_batch_core(db, nullptr, d_unnorm, lens, B, start_state, d_paths, d_step_dist, stream);
+}
+
+// Greedy search over a database whose joint rows are sharded by row block across the ranks of the communicator
+// (snk_comm_init): this handle holds joint rows [id_offset, id_offset + Np) -- frames F[id_offset : id_offset + Np + m - 1],
+// join contexts Jc[id_offset : id_offset + Np + m] -- and d_Jc_full is the replicated un-weighted join matrix
+// [rows_full + m, Dj] every rank reads the previous join vector from.  One exchange per time step inside the library
+// (grouped ncclAllGather of B * 24 bytes + arg-min / certificate kernel); paths hold GLOBAL row ids, identical on every rank.
+// Collective: every rank calls it with the same targets, and snk_greedy_batch_finish afterwards.
+int snk_greedy_sharded_batch_dev(snk_db *db, const double *d_targets, const int64_t *lens, int B, const int64_t *start_state,
+                                 const float *d_Jc_full, int64_t rows_full, int64_t id_offset, int64_t *d_paths,
+                                 double *d_step_dist, void *stream) {
+    SNK_CHECK(db && d_Jc_full, "NULL argument");
+    SNK_LOCK(db);
+    SNK_CHECK(db->comm, "snk_comm_init has not been called");
+    SNK_CHECK(id_offset >= 0 && id_offset + db->Np <= rows_full, "shard [%lld, %lld) outside the %lld joint rows",
+              (long long)id_offset, (long long)(id_offset + db->Np), (long long)rows_full);
+    return greedy_batch_core(db, d_targets, nullptr, lens, B, start_state, d_paths, d_step_dist, stream, d_Jc_full, rows_full,
+                             id_offset);
 }
 
 int snk_prepare_targets_dev(snk_db *db, const float *d_unnorm, int64_t rows, double *d_out, void *stream) {
@@ -630,8 +664,11 @@ int snk_prepare_targets_dev(snk_db *db, const float *d_unnorm, int64_t rows, dou
 }
 
 static int greedy_batch_core(snk_db *db, const double *d_targets, const float *d_unnorm, const int64_t *lens, int B,
-                             const int64_t *start_state, int64_t *d_paths, double *d_step_dist, void *stream) {
+                             const int64_t *start_state, int64_t *d_paths, double *d_step_dist, void *stream,
+                             const float *d_Jc_full, int64_t rows_full, int64_t id_offset) {
     SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    const bool sharded = d_Jc_full != nullptr;
+    const int64_t rows_all = sharded ? rows_full : db->Np;
     SNK_CUDA(cudaSetDevice(db->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (B <= 0) return 0;
@@ -648,7 +685,7 @@ static int greedy_batch_core(snk_db *db, const double *d_targets, const float *d
         meta[b].path_off = poff;
         meta[b].nsteps = lens[b] / m;
         meta[b].start_state = start_state ? start_state[b] : -1;
-        if (meta[b].start_state >= db->Np) {
+        if (meta[b].start_state >= rows_all) {
             snk_set_error("start_state %lld out of range", (long long)meta[b].start_state);
             return 1;
         }
@@ -660,9 +697,11 @@ static int greedy_batch_core(snk_db *db, const double *d_targets, const float *d
     // deferred certificates: flags [B] preset to 1 + a failure counter, inspected by snk_greedy_batch_finish
     SNK_TRY(take_flags(db, B, &job.fb));
     job.d_targets = d_targets; job.d_unnorm = d_unnorm; job.d_paths = d_paths; job.d_step_dist = d_step_dist; job.st = st;
+    job.sharded = sharded; job.Jc_full = d_Jc_full; job.id_offset = id_offset;
+    const greedy_shard sh{d_Jc_full, id_offset};
     int *flags = job.fb.p, *count = flags + B;
     int rc = launch_flag_reset(db, flags, B, st);
-    if (!rc) rc = greedy_run(db, meta, d_targets, d_unnorm, d_paths, d_step_dist, flags, count, st);
+    if (!rc) rc = greedy_run(db, meta, d_targets, d_unnorm, d_paths, d_step_dist, flags, count, st, sharded ? &sh : nullptr);
     pending_of(db)->greedy.push_back(std::move(job));
     return rc;
 }
@@ -680,21 +719,23 @@ extern "C" int snk_greedy_batch_finish(snk_db *db) {
         // steps depend on the doubtful choice, so the whole chain is repeated)
         const int chain[2] = {SNK_ENGINE_SIMT, SNK_ENGINE_EXACT};
         for (int stage = 0; stage < 2 && !rc; ++stage) {
-            rc = cudaStreamSynchronize(job.st) == cudaSuccess ? 0 : 1;
-            int nfail = 0;
-            if (!rc) rc = read_count(job.fb.p + B, &nfail);
-            if (rc || nfail == 0) break;
+            const int nflags = (int)job.meta.size();     // flags index the list of the run they belong to
+            // sharded: an utterance is doubtful if ANY rank could not certify one of its steps -- all ranks agree on the
+            // union of the cleared flags (element-wise minimum) and redo the same utterances in lockstep
+            if (job.sharded) rc = snk_comm_allreduce_min(db, job.fb.p, nflags, job.st);
+            if (!rc) rc = cudaStreamSynchronize(job.st) == cudaSuccess ? 0 : 1;
             std::vector<int> idx;
-            rc = failed_indices(job.fb.p, B, &idx);
-            if (rc) break;
+            if (!rc) rc = failed_indices(job.fb.p, nflags, &idx);
+            if (rc || idx.empty()) break;
             std::vector<greedy_meta> redo;
             for (int b : idx) redo.push_back(job.meta[(size_t)b]);
             db->counters[stage == 0 ? 1 : 3] += (int64_t)redo.size();
             rc = launch_flag_reset(db, job.fb.p, B, job.st);
             const int saved = db->engine;
             db->engine = chain[stage];
+            const greedy_shard sh{job.Jc_full, job.id_offset};
             if (!rc) rc = greedy_run(db, redo, job.d_targets, job.d_unnorm, job.d_paths, job.d_step_dist, job.fb.p, job.fb.p + B,
-                                     job.st);
+                                     job.st, job.sharded ? &sh : nullptr);
             db->engine = saved;
             job.meta.swap(redo);   // flags of the redo run index the redo list
             if (!rc) rc = cudaStreamSynchronize(job.st) == cudaSuccess ? 0 : 1;

@@ -144,42 +144,40 @@ class ShardedKnn:
 
 class ShardedGreedy:
     """Greedy joint search over a database whose joint rows are sharded by row block (SURVEY.md section 8e,
-    row "greedy chain with sharded DB"): one exchange PER TIME STEP.  Every rank searches its shard with the
-    replicated step queries, the per-shard best (distance, global row) pairs are all-gathered and merged,
-    and the next step's previous-join vector is read from the replicated weighted join contexts
-    (current_join_rep[u] = Jw[u + m], reference script/synth_simple.py:213-214,501), so no second exchange is
-    needed.  Messages are B * 16 bytes per rank and step: latency bound."""
+    row "greedy chain with sharded DB"): one exchange PER TIME STEP, enqueued by the library
+    (snk_greedy_sharded_batch_dev: grouped ncclAllGather of the per-shard best (distance, global row, bound) triples, B * 24
+    bytes per rank, and an arg-min kernel).  The next step's previous-join vector is read from the replicated join
+    contexts (current_join_rep[u] = Jw[u + m], reference script/synth_simple.py:213-214,501), so no second exchange
+    is needed.  Latency bound: the step is the shard's search plus one small collective."""
 
     def __init__(self, F, Jc, multiepoch, wt, wj, rank, world, device, group=None):
         import torch
         self.m = int(multiepoch)
         self.knn = ShardedKnn.from_epoch_db(F, Jc, multiepoch, wt, wj, rank, world, device, group)
-        dev = torch.device("cuda", device)
-        # replicated float64 weighted join contexts, the reference's own values (f32 data * f64 weights)
-        self.Jw = torch.from_numpy(np.ascontiguousarray(Jc, dtype=np.float32)).to(dev).double() * \
-            torch.from_numpy(np.asarray(wj, dtype=np.float64)).to(dev)
-        self.Dj = self.Jw.shape[1]
+        if world == 1:                             # a communicator of one: the same entry point on a single GPU
+            self.knn.db.comm_init(engine.comm_unique_id(), 0, 1)
+        self.rows_full = F.shape[0] - (self.m - 1)
+        # replicated un-weighted float32 join contexts, as the voice file holds them
+        self.Jc_full = torch.from_numpy(np.ascontiguousarray(Jc, dtype=np.float32)).to(torch.device("cuda", device))
         self.Dt = F.shape[1]
 
-    def search(self, targets, start_states=None):
-        """targets: torch float64 CUDA tensor [B, T, Dt] (weighted, equal lengths); returns int64 [B, T // m]."""
+    def search(self, targets, start_states=None, return_dists=False):
+        """targets: torch float64 CUDA tensor [B, T, Dt] (weighted, equal lengths); returns int64 [B, T // m] of GLOBAL
+        row ids, identical on every rank."""
         import torch
         B, T, Dt = targets.shape
         steps = T // self.m
         if steps == 0:
             raise ValueError("Not enough data points to segment array in 'cut' mode")
+        targets = targets.contiguous()
         paths = torch.empty((B, steps), dtype=torch.int64, device=targets.device)
-        prev = torch.zeros((B, self.Dj), dtype=torch.float64, device=targets.device)
-        if start_states is not None:
-            ss = torch.as_tensor(start_states, device=targets.device)
-            prev = torch.where((ss >= 0)[:, None], self.Jw[ss.clamp(min=0)], prev)   # prev_join_rep[u] = Jw[u]
-        for t in range(steps):
-            q = torch.cat([prev, targets[:, t * self.m:(t + 1) * self.m, :].reshape(B, self.m * Dt)], dim=1).contiguous()
-            _, idx = self.knn.query(q, 1)
-            ix = idx[:, 0]
-            paths[:, t] = ix
-            prev = self.Jw[ix + self.m]
-        return paths
+        dists = torch.empty((B, steps), dtype=torch.float64, device=targets.device)
+        stream = torch.cuda.current_stream(targets.device).cuda_stream
+        db = self.knn.db
+        db.greedy_sharded_batch_dev(targets.data_ptr(), np.full(B, T, dtype=np.int64), self.Jc_full.data_ptr(), self.rows_full,
+                                    self.knn.lo, paths.data_ptr(), dists.data_ptr(), start_states, stream)
+        db.greedy_batch_finish()
+        return (paths, dists) if return_dists else paths
 
 
 def gather_paths(paths_local, utt_ids_local, n_utts, group=None):

@@ -70,6 +70,7 @@ def load_library(path=None):
         "snk_knn_sharded_finish": [vp],
         "snk_greedy_batch": [vp, P(dbl), P(i64), i32, P(i64), P(i64), P(dbl)],
         "snk_greedy_batch_dev": [vp, vp, P(i64), i32, P(i64), vp, vp, vp],
+        "snk_greedy_sharded_batch_dev": [vp, vp, P(i64), i32, P(i64), vp, i64, i64, vp, vp, vp],
         "snk_db_set_standardisation": [vp, P(dbl), P(dbl), dbl, dbl, C.c_uint],
         "snk_prepare_targets": [vp, P(flt), i64, P(dbl)],
         "snk_greedy_batch_unnorm": [vp, P(flt), P(i64), i32, P(i64), P(i64), P(dbl)],
@@ -102,7 +103,7 @@ EXPORTED_SYMBOLS = ["snk_last_error", "snk_version", "snk_device_count", "snk_db
                     "snk_db_profile_read", "snk_knn",
                     "snk_knn_dev", "snk_knn_finish", "snk_debug_tc_keys", "snk_topk_merge_dev", "snk_comm_unique_id", "snk_comm_init",
                     "snk_comm_info", "snk_knn_sharded_dev", "snk_knn_sharded_finish", "snk_greedy_batch",
-                    "snk_greedy_batch_dev", "snk_greedy_batch_finish",
+                    "snk_greedy_batch_dev", "snk_greedy_batch_finish", "snk_greedy_sharded_batch_dev",
                     "snk_db_set_standardisation", "snk_prepare_targets", "snk_greedy_batch_unnorm",
                     "snk_greedy_batch_unnorm_dev",
                     "snk_candidate_distances", "snk_join_tiles", "snk_join_stats", "snk_join_viterbi_batch",
@@ -209,6 +210,17 @@ class UnitDatabase:
 
     def greedy_batch_finish(self):
         _check(load_library().snk_greedy_batch_finish(self._h))
+
+    def greedy_sharded_batch_dev(self, targets_ptr, lens, jc_full_ptr, rows_full, id_offset, paths_ptr, dists_ptr=0,
+                                 start_states=None, stream=0):
+        """Collective: this handle holds joint rows [id_offset, id_offset + rows); jc_full_ptr is the replicated
+        float32 join matrix on this device.  Follow with greedy_batch_finish() on every rank."""
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        ss = None if start_states is None else np.ascontiguousarray(start_states, dtype=np.int64)
+        _check(load_library().snk_greedy_sharded_batch_dev(
+            self._h, C.c_void_p(targets_ptr), _ptr(lens, C.c_int64), lens.size, _ptr(ss, C.c_int64), C.c_void_p(jc_full_ptr),
+            int(rows_full), int(id_offset), C.c_void_p(paths_ptr), C.c_void_p(dists_ptr) if dists_ptr else None,
+            C.c_void_p(stream)))
 
     def join_viterbi_batch_dev(self, cand_ptr, tdist_ptr, lens, K, paths_ptr, plen_ptr, pcost_ptr, tcost_ptr=0, jcost_ptr=0,
                                flags=0, stream=0):

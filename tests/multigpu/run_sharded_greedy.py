@@ -30,6 +30,13 @@ def main():
     paths = sg.search(tg, starts).cpu().numpy()
     want = ref.greedy_joint_search_batch(utts, starts)
     ok = all(paths[b].tolist() == want[b] for b in range(B))
+    # the same with the fp16 certificate forced to fail for every 3rd query: all ranks must agree on the utterances to
+    # repeat (one all-reduce in snk_greedy_batch_finish) and repeat them in lockstep with the fp32 engine
+    os.environ["SNK_DEBUG_CERT_FAIL"] = "3"
+    sg2 = D.ShardedGreedy(db["F"], db["Jc"], 6, wt, wj, rank, world, local)
+    del os.environ["SNK_DEBUG_CERT_FAIL"]
+    paths2 = sg2.search(tg, starts).cpu().numpy()
+    ok = ok and all(paths2[b].tolist() == want[b] for b in range(B)) and sg2.knn.db.counters()["recertified"] > 0
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
