@@ -193,7 +193,9 @@ class Hdf5File:
                     dims = tuple(self._u(q + 4 * i, 4) for i in range(nd))
                     q += 4 * nd
                     if cls == 2:
-                        d.layout, d.chunk = "chunked", dims + (self._u(q, 4),)
+                        # as in version 3, the dimensionality of a chunked layout counts the trailing element-size
+                        # dimension: the nd values just read are the whole chunk shape, nothing follows them
+                        d.layout, d.chunk = "chunked", dims
                     elif cls == 1:
                         d.layout = "contiguous"
                     else:

@@ -14,6 +14,8 @@ satisfies every (1+eps) guarantee.
 """
 from __future__ import annotations
 
+import warnings
+
 import numpy as np
 
 from . import engine
@@ -38,6 +40,14 @@ class GpuKDTree:
         # speech_manip.py:209-213); a generic float64 matrix is held as float32 x 1.0
         f32 = np.ascontiguousarray(data, dtype=np.float32)
         self.exact_storage = bool(np.array_equal(f32.astype(np.float64), np.asarray(data, dtype=np.float64)))
+        if not self.exact_storage:
+            # e.g. a stash of already weighted float64 rows (float32 voice * float64 weights): the products are not
+            # float32 numbers.  Distances are then taken to the float32-rounded rows (each coordinate off by at most
+            # 6e-8 relative), so neighbours tied to within that may come back in another order than scipy / sklearn
+            # return them.  GpuKDTree.from_weighted(raw_f32, weights) keeps the exact values.
+            warnings.warn("GpuKDTree: the data matrix is not exactly representable in float32; searching its float32 "
+                          "rounding (use GpuKDTree.from_weighted(raw_float32, weight_vector) for exact float64 rows)",
+                          RuntimeWarning, stacklevel=2)
         self.data = data
         self._db = engine.UnitDatabase(f32, np.zeros((self.n + 1, 1), np.float32), multiepoch=1, device=device)
         self._db.set_weights(np.ones(self.m), np.ones(1))
