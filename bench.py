@@ -206,7 +206,7 @@ def run_reference(args):
                 "pinned against the reference's own code by tests/test_reference_exec.py, driving the reference's own "
                 "scipy cKDTree engine) on the host cores",
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
@@ -271,7 +271,7 @@ def run_reference_halfphone(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "oracle/ restatement (pinned by tests/test_reference_exec.py) driving the reference's own scipy cKDTree; "
                     "OpenFst replaced by the min-plus DP"}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
@@ -347,7 +347,7 @@ def run_ours(args):
         if rank == 0:
             out.update(hp)
             out["clocks"] = clocks
-            print(json.dumps(out), flush=True)
+            emit_line(out)
         D.close()
         return 0
 
@@ -476,7 +476,7 @@ def run_ours(args):
                                          (info["steps_per_utt"], info["tree_build_s"])}
         out["parity"] = greedy_parity(syn, run)
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit_line(out)
     D.close()
     return 0
 
@@ -875,7 +875,32 @@ def block_sharded_knn(D, args):
             "exactness": {"queries": cnt["queries"], "recertified_by_simt": cnt["recertified"], "exhaustive_f64": cnt["exhaustive"]}}
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+    communicator when NCCL_DEBUG asks for it), so file descriptor 1 is pointed at stderr for the whole run and the line
+    goes out through a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -21,6 +21,9 @@
  *    certificate flags and repairs the (rare) uncertified answers; results are final
  *    only after it.  Input and output buffers must stay alive until then.  All _dev
  *    calls on one handle share its workspaces: issue them on ONE stream at a time.
+ *    The one exception to "never": the handle's grow-only device workspaces are
+ *    (re)allocated when a call needs more than any call before it (cudaFree /
+ *    cudaMalloc wait for the device), i.e. during the first calls of a given size.
  *  - there is NO CPU fallback: without a CUDA device every compute entry point
  *    fails with an error.
  *  - thread-safe per handle: calls on one handle are serialised by an internal lock,

@@ -7,18 +7,22 @@ search).  It exists so the CUDA path can be checked; nothing in the product
 `bench.py`'s cpu_baseline / `--impl reference` leg may execute it.
 
 PARITY PINNING.  The reference (Python 2.7, needs h5py / pywrapfst / magphase)
-cannot be imported or run in this image and ships NO tests, golden vectors or
-known-answer fixtures for this path.  The oracle is
-therefore pinned by:
-  (1) the reference's own third-party engines where they exist here:
-      `scipy.spatial.cKDTree` with the reference's constructor/query kwargs
-      (script/synth_simple.py:229,490; script/synth_halfphone.py:379,1364);
-  (2) the reference's only in-code known answers: the natural-path identity
-      assertion (script/synth_simple.py:909-928, script/synth_halfphone.py:1455-1474)
-      and zero join cost between adjacent units (script/synth_simple.py:250-251);
-  (3) exhaustive path enumeration on small lattices for the Viterbi restatement,
-      because OpenFst 1.5.4 / pywrapfst (pinned in README_FULL.md:45-53) is absent.
-The Viterbi part is "parity unpinned" against OpenFst itself; DESIGN.md says so.
+cannot be imported in this image and ships NO tests, golden vectors or
+known-answer fixtures for this path.  The oracle is pinned by
+  (1) OUTPUTS OF THE REFERENCE'S OWN CODE: oracle/ref_exec.py executes the reference's
+      functions for this path (mechanical Python 2 -> 3 transform of the files where they
+      lie) on seeded inputs; the results are committed as tests/golden/reference_exec.npz and
+      tests/test_reference_exec.py requires this module to reproduce every one of them;
+  (2) the reference's third-party engines where they exist here: `scipy.spatial.cKDTree`
+      with the reference's constructor/query kwargs (script/synth_simple.py:229,490;
+      script/synth_halfphone.py:379,1364) and `sklearn.neighbors.KDTree`;
+  (3) the reference's only in-code known answers: the natural-path identity assertion
+      (script/synth_simple.py:909-928, script/synth_halfphone.py:1455-1474) and zero join
+      cost between adjacent units (script/synth_simple.py:250-251);
+  (4) exhaustive path enumeration on small lattices for the Viterbi restatement.
+OpenFst 1.5.4 / pywrapfst (pinned in README_FULL.md:45-53) is absent: the reference's calls
+into it land in oracle/minifst.py, a restatement of the published algorithms.  What stays
+"parity unpinned" is OpenFst's own tie order between equal-cost paths; DESIGN.md says so.
 
 Every function cites the reference file:line it follows (paths under
 /root/reference/script/).

@@ -56,3 +56,46 @@ def test_fails_loudly_without_gpu():
 def test_argument_validation_happens_before_device_work():
     with pytest.raises(ValueError):
         snickery_b200.UnitDatabase(np.zeros((10, 3), np.float32), np.zeros((10, 2), np.float32))  # Jc needs N+1 rows
+
+
+def _function_bodies(src):
+    """name -> body of every top-level C function definition in src (brace matching; strings in this code base hold no braces)."""
+    import re
+    out = {}
+    for m in re.finditer(r"^(?:static\s+|extern\s+\"C\"\s+)?(?:int|bool|void|float)\s+(\w+)\s*\([^;{]*\)\s*\{", src, re.M):
+        depth, i = 1, m.end()
+        while depth and i < len(src):
+            depth += {"{": 1, "}": -1}.get(src[i], 0)
+            i += 1
+        out[m.group(1)] = src[m.end():i]
+    return out
+
+
+def test_dev_entry_points_do_not_synchronise():
+    """include/snk_b200.h promises that `_dev` entry points only enqueue on the caller's stream.  Walk the call graph of every
+    `_dev` function through the engine's own functions (everything but the `*_finish` calls, which are where waiting belongs)
+    and make sure no blocking CUDA call is reachable."""
+    import glob
+    import re
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "snickery_b200", "csrc")
+    bodies = {}
+    for path in glob.glob(os.path.join(csrc, "*.cu")):
+        bodies.update(_function_bodies(open(path).read()))
+    roots = [n for n in bodies if n.endswith("_dev")]
+    assert {"snk_knn_dev", "snk_greedy_batch_dev", "snk_join_viterbi_batch_dev", "snk_acoustic_viterbi_batch_dev",
+            "snk_knn_sharded_dev", "snk_greedy_sharded_batch_dev"} <= set(roots)
+    blocking = re.compile(r"cudaStreamSynchronize|cudaDeviceSynchronize|cudaEventSynchronize|cudaMemcpy\s*\(|cudaMemcpy2D\s*\(|cudaFree\s*\(")
+    seen, todo = set(), list(roots)
+    while todo:
+        name = todo.pop()
+        if name in seen or name.endswith("_finish"):
+            continue
+        seen.add(name)
+        body = bodies[name]
+        hit = blocking.search(body)
+        # two documented exceptions (include/snk_b200.h): the staging ring waits on an event only when it wraps around an
+        # upload that is still pending eight uploads later, and a grow-only workspace is reallocated the first time a call
+        # needs more than any call before it
+        assert hit is None or name in ("snk_upload_async", "snk_buf_reserve", "take_flags"), "%s reaches %s" % (name, hit.group(0))
+        todo += [c for c in set(re.findall(r"\b(\w+)\s*\(", body)) if c in bodies]
+    assert len(seen) > 25
