@@ -591,9 +591,58 @@ int snk_acoustic_viterbi_batch(snk_db *db, const double *targets, const int64_t 
     SNK_TRY(snk_buf_reserve(&db->ws_h3, (size_t)B * 8 * 4));
     int64_t *d_plen = (int64_t *)db->ws_h3.p;
     double *d_pc = (double *)db->ws_h3.p + B, *d_tc = d_pc + B, *d_jc = d_tc + B;
-    if (frames) SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, targets, (size_t)frames * db->Dt * 8, cudaMemcpyHostToDevice, db->stream));
-    SNK_TRY(snk_acoustic_viterbi_batch_dev(db, (const double *)db->ws_h0.p, lens, B, K, flags, (int64_t *)db->ws_h2.p, d_plen,
-                                           d_pc, d_tc, d_jc, db->stream));
+    // Upload in slices of one search batch on the copy stream: the k-NN of slice i runs while slice i + 1 crosses PCIe
+    // (the targets are 8 * Dt bytes per frame -- 120 MB for 1024 x 80 half-phone targets -- and every target is an
+    // independent query), then the lattice search runs over all candidate lists.
+    const int64_t slice = std::max<int64_t>(4096, (int64_t)db->sm_count * 128 / 256 * 256);
+    if (frames > slice) {
+        snk_acoustic_job *job = acoustic_job(db);
+        SNK_CHECK(!job->active, "the previous snk_acoustic_viterbi_batch_dev has not been finished");
+        const size_t fK = (size_t)frames * K;
+        SNK_TRY(snk_buf_reserve(&db->ws_jv, fK * 16));
+        double *d_dist = (double *)db->ws_jv.p;
+        int64_t *d_cand = (int64_t *)(d_dist + fK);
+        const int nsl = (int)snk_cdiv(frames, slice);
+        while ((int)db->upload_events.size() < nsl) {
+            cudaEvent_t e;
+            SNK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            db->upload_events.push_back(e);
+        }
+        auto upload = [&](int c) -> int {
+            const int64_t q0 = c * slice, qn = std::min<int64_t>(slice, frames - q0);
+            const size_t off = (size_t)q0 * db->Dt * 8;
+            SNK_CUDA(cudaMemcpyAsync((char *)db->ws_h0.p + off, (const char *)targets + off, (size_t)qn * db->Dt * 8,
+                                     cudaMemcpyHostToDevice, db->copy_stream));
+            SNK_CUDA(cudaEventRecord(db->upload_events[c], db->copy_stream));
+            return 0;
+        };
+        int rc = upload(0);
+        for (int c = 0; c < nsl && !rc; ++c) {
+            // the next slice is queued before this slice's search: with pageable host memory the copy call itself waits
+            // for the staging, and it should do so while the GPU is busy
+            if (c + 1 < nsl) rc = upload(c + 1);
+            if (rc) break;
+            const int64_t q0 = c * slice, qn = std::min<int64_t>(slice, frames - q0);
+            rc = cudaStreamWaitEvent(db->stream, db->upload_events[c], 0) == cudaSuccess ? 0 : 1;
+            if (!rc) rc = snk_knn_enqueue(db, SNK_SPACE_TARGET, (const double *)db->ws_h0.p + q0 * db->Dt, qn, K, d_dist + q0 * K,
+                                          d_cand + q0 * K, K, 0, db->stream);
+        }
+        if (!rc) rc = snk_join_viterbi_batch_dev(db, d_cand, d_dist, lens, B, K, flags, (int64_t *)db->ws_h2.p, d_plen, d_pc, d_tc,
+                                                 d_jc, db->stream);
+        if (rc) {
+            cudaStreamSynchronize(db->copy_stream);
+            cudaStreamSynchronize(db->stream);
+            return 1;
+        }
+        job->active = true;
+        job->lens.assign(lens, lens + B);
+        job->K = K; job->flags = flags; job->d_paths = (int64_t *)db->ws_h2.p; job->d_plen = d_plen; job->d_pcost = d_pc;
+        job->d_tcost = d_tc; job->d_jcost = d_jc; job->st = db->stream;
+    } else {
+        if (frames) SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, targets, (size_t)frames * db->Dt * 8, cudaMemcpyHostToDevice, db->stream));
+        SNK_TRY(snk_acoustic_viterbi_batch_dev(db, (const double *)db->ws_h0.p, lens, B, K, flags, (int64_t *)db->ws_h2.p, d_plen,
+                                               d_pc, d_tc, d_jc, db->stream));
+    }
     SNK_TRY(snk_acoustic_viterbi_finish(db));
     if (frames) SNK_CUDA(cudaMemcpyAsync(paths, db->ws_h2.p, (size_t)frames * 8, cudaMemcpyDeviceToHost, db->stream));
     SNK_CUDA(cudaMemcpyAsync(path_len, d_plen, (size_t)B * 8, cudaMemcpyDeviceToHost, db->stream));
