@@ -55,7 +55,6 @@ __host__ __device__ constexpr int epi_split_of(int sched) { return (sched == 2 |
 constexpr int TILE_BYTES = BM * BK * 2;                    // 16 KiB query K-block
 constexpr int SLOT_BYTES = (BN + SLAB_EXTRA) * BK * 2;     // 17 KiB ring slot (plain tile or frame slab)
 __host__ __device__ constexpr int num_threads_of(int sched) { return 64 + 128 * epi_split_of(sched); }
-constexpr uint32_t TMEM_COLS = 256;       // two 128-column fp32 accumulators
 
 // One TMA load per ring slot; it feeds nsub MMA K-blocks.  A frame slab (BN + 8 rows of G16) feeds the
 // m window offsets of the multiepoch row: K-block j reads the slab from row j on, so the sliding
@@ -183,7 +182,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     constexpr bool ATM = sched_traits<SCHED>::ATM;
     constexpr int AS = sched_traits<SCHED>::AS;                       // join-part blocks of the query held in tensor memory
     const int NKB = ATM ? sched_traits<SCHED>::NS - AS : p.nkb;       // query K-blocks resident in shared memory
-    constexpr uint32_t TCOLS = ATM ? 512u : TMEM_COLS;
+    // accumulators in flight: four for the static schedules that keep the query in shared memory (all 512 tensor-memory
+    // columns; the issuing thread runs up to three tiles ahead of the epilogue, which otherwise waits a barrier and a
+    // tcgen05.ld round trip per tile: the K = 192 tile is only 768 tensor-pipe cycles), two when the query operand takes
+    // 256 columns and for the table-driven path (its norm staging is double-buffered)
+    constexpr int NACC = (SCHED != 0 && !ATM) ? 4 : 2;
+    constexpr uint32_t TCOLS = ATM ? 512u : (uint32_t)(NACC * BN);
     constexpr uint32_t ATM_COL = 2 * BN;                              // tensor-memory columns of A: [AS join blocks][frame blocks], 32 each
     const uint32_t sA = sbase;
     const uint32_t sB = sA + (uint32_t)NKB * TILE_BYTES;
@@ -191,10 +195,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     const uint32_t sBar = sB + (uint32_t)p.b_bytes;
     // barriers: full[MAX_STAGES] empty[MAX_STAGES] a_full tmem_full[2] tmem_empty[2]
     const uint32_t bar_full = sBar, bar_empty = sBar + 8 * MAX_STAGES, bar_a = sBar + 16 * MAX_STAGES;
-    const uint32_t bar_tfull = bar_a + 8, bar_tempty = bar_tfull + 16;
-    const uint32_t s_tmem_ptr = bar_tempty + 16;
+    const uint32_t bar_tfull = bar_a + 8, bar_tempty = bar_tfull + 32;      // room for four accumulators each
+    const uint32_t s_tmem_ptr = bar_tempty + 32;
     const uint32_t bar_atm = s_tmem_ptr + 8;                          // A frames have been written to tensor memory
-    uint8_t *g_after = gbase + (size_t)NKB * TILE_BYTES + (size_t)p.b_bytes + 16 * MAX_STAGES + 8 + 32;
+    uint8_t *g_after = gbase + (size_t)NKB * TILE_BYTES + (size_t)p.b_bytes + 16 * MAX_STAGES + 8 + 64;
     volatile uint32_t *tmem_ptr_g = reinterpret_cast<volatile uint32_t *>(g_after);
     float *nrm_s = reinterpret_cast<float *>(g_after + 24);           // [2][BN], 16-byte aligned (table-driven path only)
     uint4 *sub_s = reinterpret_cast<uint4 *>(g_after + 24 + 2 * BN * 4);   // [MAXSUB] {a start addr >> 4, b byte offset, ksteps, -}
@@ -220,7 +224,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         }
         mbar_init(bar_a, 1);
         if (ATM) mbar_init(bar_atm, 128 * epi_split_of(SCHED));
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < NACC; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
             mbar_init(bar_tempty + 8 * a, NUM_EPI_THREADS);
         }
@@ -329,8 +333,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             if (elect_one()) {
                 const uint32_t a0 = sA >> 4, b0 = sB >> 4;       // start-address fields; every offset below is an immediate
                 for (int t = 0; t < ntiles; ++t) {
-                    const int acc = t & 1;
-                    const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
+                    const int acc = t % NACC;
+                    const uint32_t acc_phase = (uint32_t)(t / NACC) & 1;
                     mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
@@ -385,8 +389,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < ntiles; ++t) {
-            const int acc = t & 1;
-            const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
+            const int acc = t % NACC;
+            const uint32_t acc_phase = (uint32_t)(t / NACC) & 1;
             mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);       // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
@@ -469,8 +473,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             for (int i = 0; i < LSZ; ++i) { ov[i] = OSCALE * lv[i]; oi[i] = li[i]; lv[i] = INFINITY; li[i] = -1; }
         };
         for (int t = 0; t < ntiles; ++t) {
-            const int acc = t & 1;
-            const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
+            const int acc = t % NACC;
+            const uint32_t acc_phase = (uint32_t)(t / NACC) & 1;
             const int64_t r0 = row_beg + (int64_t)t * tstep;
             if (!embed) {
                 if (et < BN) {
@@ -826,7 +830,7 @@ int make_map(encode_fn enc, CUtensorMap *map, const void *base, uint64_t cols, u
 }
 
 size_t aux_bytes(int sched) {   // barriers + tmem pointer (+ norm staging and descriptor table of the table-driven path)
-    return 16 * MAX_STAGES + 8 + 32 + 24 + (sched == 0 ? 2 * BN * 4 + MAXSUB * 16 : 0) + 16;
+    return 16 * MAX_STAGES + 8 + 64 + 24 + (sched == 0 ? 2 * BN * 4 + MAXSUB * 16 : 0) + 16;
 }
 
 int build_space(snk_db *db, int space, tc_space_host *h) {
