@@ -188,6 +188,19 @@ int snk_db_set_standardisation(snk_db *db, const double *mean, const double *std
                                unsigned flags);
 /* unnorm float32 [rows, Dt] (compose_speech output) -> out float64 [rows, Dt], host buffers */
 int snk_prepare_targets(snk_db *db, const float *unnorm, int64_t rows, double *out);
+/* Half-phone target preparation: what get_halfphone_stats + standardise + weight produce
+ * between compose_speech and the search (reference script/train_halfphone.py:959-1070 as called from
+ * script/synth_halfphone.py:1510-1548).  unnorm: float32 [frames, dim] un-normalised speech of one utterance;
+ * points: int64 [n, P], P = 1 / 2 / 3 frame indices per half-phone (onepoint: middle; twopoint: first, last; threepoint:
+ * first, middle, last -- taken from the 5-state alignment, see snickery_b200/synth.py::halfphone_unit_points);
+ * durations: float64 [n] normalised durations appended as the last column, or NULL.  P * dim (+ 1) must equal Dt.
+ * out float64 [n, Dt] = weight(hstack(standardise(unnorm)[points], durations)): the statistics of
+ * snk_db_set_standardisation are Dt wide, i.e. the frame statistics repeated per point (any value for the duration
+ * column, which is only weighted).  Bit-identical to the numpy expression in both arithmetic modes.                  */
+int snk_halfphone_targets(snk_db *db, const float *unnorm, int64_t frames, int dim, const int64_t *points, int64_t n, int P,
+                          const double *durations, double *out);
+int snk_halfphone_targets_dev(snk_db *db, const float *d_unnorm, int64_t frames, int dim, const int64_t *d_points, int64_t n,
+                              int P, const double *d_durations, double *d_out, void *stream);
 /* snk_greedy_batch on un-normalised float32 speech: the standardise+weight step is fused
  * into the query assembly, half the host->device bytes of the float64 form.  Results are
  * identical to snk_greedy_batch(snk_prepare_targets(unnorm)).                              */

@@ -46,6 +46,40 @@ def weight(speech, weight_vec):
     return speech * weight_vec
 
 
+def halfphone_stats(speech, labels, representation_type="twopoint"):
+    """train_halfphone.py:959-1070 -- (names, features, timings) of the half-phones of one utterance.  labels: list of
+    ((start, end), [ll, l, c, r, rr, state]), five states '2'..'6' per phone; states 2-3 are the left half-phone, 4-6
+    the right one; a unit is described by its first frame (start of state 2 / 4), its middle frame (end of state 2 / 5)
+    and its last frame (end of state 3 / 6), ends clipped to the utterance."""
+    m = speech.shape[0]
+    assert len(labels) % 5 == 0
+    names, starts, middles, ends = [], [], [], []
+    for (s, e), lab in labels:
+        e = min(e, m - 1)
+        quin, state = list(lab[:5]), lab[-1]
+        if state == "2":
+            quin[2] += "_L"
+            names.append("/".join(quin)); starts.append(s); middles.append(e)
+        elif state == "3":
+            ends.append(e)
+        elif state == "4":
+            quin[2] += "_R"
+            names.append("/".join(quin)); starts.append(s)
+        elif state == "5":
+            middles.append(e)
+        elif state == "6":
+            ends.append(e)
+        else:
+            raise SystemExit("bad state number")
+    if representation_type == "onepoint":
+        feats = speech[middles, :]
+    elif representation_type == "twopoint":
+        feats = np.hstack([speech[starts, :], speech[ends, :]])
+    else:
+        feats = np.hstack([speech[starts, :], speech[middles, :], speech[ends, :]])
+    return np.array(names), feats, list(zip(starts, ends))
+
+
 SPECIAL_UV_VALUE = -1000.0   # const.py:12
 UV_SCALING_FACTOR = 20.0     # const.py:14
 

@@ -348,6 +348,33 @@ int snk_prepare_targets(snk_db *db, const float *unnorm, int64_t rows, double *o
     return 0;
 }
 
+int snk_halfphone_targets(snk_db *db, const float *unnorm, int64_t frames, int dim, const int64_t *points, int64_t n, int P,
+                          const double *durations, double *out) {
+    SNK_CHECK(db && db->std_set, "snk_db_set_standardisation has not been called");
+    SNK_LOCK(db);
+    SNK_CHECK(n >= 0 && frames >= 1 && dim >= 1 && P >= 1, "bad shape");
+    if (n == 0) return 0;
+    SNK_CHECK(unnorm && points && out, "NULL argument");
+    for (int64_t i = 0; i < n * P; ++i)      // numpy raises IndexError for these
+        SNK_CHECK(points[i] >= -frames && points[i] < frames, "frame index %lld out of bounds for %lld frames",
+                  (long long)points[i], (long long)frames);
+    SNK_CUDA(cudaSetDevice(db->device));
+    const size_t xb = (size_t)frames * dim * 4, pb = (size_t)n * P * 8, db_ = durations ? (size_t)n * 8 : 0;
+    SNK_TRY(snk_buf_reserve(&db->ws_h0, xb));
+    SNK_TRY(snk_buf_reserve(&db->ws_h1, (size_t)n * db->Dt * 8));
+    SNK_TRY(snk_buf_reserve(&db->ws_h2, pb + db_ + 16));
+    int64_t *d_pts = (int64_t *)db->ws_h2.p;
+    double *d_dur = durations ? (double *)((char *)db->ws_h2.p + pb) : nullptr;
+    SNK_CUDA(cudaMemcpyAsync(db->ws_h0.p, unnorm, xb, cudaMemcpyHostToDevice, db->stream));
+    SNK_CUDA(cudaMemcpyAsync(d_pts, points, pb, cudaMemcpyHostToDevice, db->stream));
+    if (durations) SNK_CUDA(cudaMemcpyAsync(d_dur, durations, db_, cudaMemcpyHostToDevice, db->stream));
+    SNK_TRY(snk_halfphone_targets_dev(db, (const float *)db->ws_h0.p, frames, dim, d_pts, n, P, d_dur, (double *)db->ws_h1.p,
+                                      db->stream));
+    SNK_CUDA(cudaMemcpyAsync(out, db->ws_h1.p, (size_t)n * db->Dt * 8, cudaMemcpyDeviceToHost, db->stream));
+    SNK_CUDA(cudaStreamSynchronize(db->stream));
+    return 0;
+}
+
 // host entry point shared by the weighted-float64 and the un-normalised-float32 forms (elem = 8 / 4)
 static int greedy_batch_host(snk_db *db, const void *targets, size_t elem, const int64_t *lens, int B,
                              const int64_t *start_state, int64_t *paths, double *step_dist) {

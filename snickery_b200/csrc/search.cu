@@ -298,6 +298,25 @@ __global__ void prepare_targets_kernel(const float *__restrict__ x, int64_t tota
         out[i] = standardise_weight(x[i], (int)(i % Dt), sp);
 }
 
+// Half-phone targets (train_halfphone.py:959-1070, synth_halfphone.py:1510-1548): unit i is described by P frames of the
+// utterance (first / middle / last frame of the half-phone, chosen from the state alignment), optionally followed by its
+// normalised duration; the frames are standardised, the row is weighted.  Column p * dim + c of the row takes the
+// statistics and the weight of target column p * dim + c, so the Dt-wide vectors of snk_db_set_standardisation hold the
+// frame statistics repeated per point.  The duration column is not standardised here (get_norm_durations did that).
+__global__ void halfphone_targets_kernel(const float *__restrict__ x, int64_t frames, int dim, const int64_t *__restrict__ pts,
+                                         int64_t n, int P, const double *__restrict__ dur, int Dt, std_params sp,
+                                         double *__restrict__ out) {
+    const int64_t total = n * Dt;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t u = i / Dt;
+        const int col = (int)(i - u * Dt);
+        if (col >= P * dim) { out[i] = __dmul_rn(dur[u], sp.w[col]); continue; }
+        int64_t f = pts[u * P + col / dim];
+        if (f < 0) f += frames;                      // numpy's negative indexing
+        out[i] = (f >= 0 && f < frames) ? standardise_weight(x[f * dim + col % dim], col, sp) : NAN;
+    }
+}
+
 // Query b of step t = [ prev_join_vector || m consecutive target frames ]   (synth_simple.py:467-470,488,501).
 // The recipe: where the previous choices and the target frames are, and where finished steps go.
 // targets: weighted float64 frames, or (targets32 != nullptr) un-normalised float32 frames that are
@@ -658,6 +677,24 @@ int snk_prepare_targets_dev(snk_db *db, const float *d_unnorm, int64_t rows, dou
     const int64_t total = rows * db->Dt;
     const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)db->sm_count * 8);
     prepare_targets_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_unnorm, total, db->Dt, stp, d_out);
+    SNK_CUDA(cudaGetLastError());
+    db->counters[2] += 1;
+    return 0;
+}
+
+int snk_halfphone_targets_dev(snk_db *db, const float *d_unnorm, int64_t frames, int dim, const int64_t *d_points, int64_t n,
+                              int P, const double *d_dur, double *d_out, void *stream) {
+    SNK_CHECK(db && db->weights_set, "snk_db_set_weights has not been called");
+    SNK_CHECK(db->std_set, "snk_db_set_standardisation has not been called");
+    SNK_CHECK(P >= 1 && P <= 3 && dim >= 1 && frames >= 1, "bad shape");
+    SNK_CHECK(P * dim + (d_dur ? 1 : 0) == db->Dt, "%d points x %d dims%s do not make the %d target columns of this voice", P,
+              dim, d_dur ? " + duration" : "", db->Dt);
+    if (n <= 0) return 0;
+    SNK_CUDA(cudaSetDevice(db->device));
+    const std_params stp{db->std_mean, db->std_sd, db->wt, db->uv_special, db->uv_scale, db->std_f32};
+    const int64_t total = n * db->Dt;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)db->sm_count * 8);
+    halfphone_targets_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_unnorm, frames, dim, d_points, n, P, d_dur, db->Dt, stp, d_out);
     SNK_CUDA(cudaGetLastError());
     db->counters[2] += 1;
     return 0;

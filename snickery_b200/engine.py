@@ -73,6 +73,8 @@ def load_library(path=None):
         "snk_greedy_sharded_batch_dev": [vp, vp, P(i64), i32, P(i64), vp, i64, i64, vp, vp, vp],
         "snk_db_set_standardisation": [vp, P(dbl), P(dbl), dbl, dbl, C.c_uint],
         "snk_prepare_targets": [vp, P(flt), i64, P(dbl)],
+        "snk_halfphone_targets": [vp, P(flt), i64, i32, P(i64), i64, i32, P(dbl), P(dbl)],
+        "snk_halfphone_targets_dev": [vp, vp, i64, i32, vp, i64, i32, vp, vp, vp],
         "snk_greedy_batch_unnorm": [vp, P(flt), P(i64), i32, P(i64), P(i64), P(dbl)],
         "snk_greedy_batch_unnorm_dev": [vp, vp, P(i64), i32, P(i64), vp, vp, vp],
         "snk_candidate_distances": [vp, P(i64), P(dbl), i64, i32, P(dbl)],
@@ -104,7 +106,8 @@ EXPORTED_SYMBOLS = ["snk_last_error", "snk_version", "snk_device_count", "snk_db
                     "snk_knn_dev", "snk_knn_finish", "snk_debug_tc_keys", "snk_topk_merge_dev", "snk_comm_unique_id", "snk_comm_init",
                     "snk_comm_info", "snk_knn_sharded_dev", "snk_knn_sharded_finish", "snk_greedy_batch",
                     "snk_greedy_batch_dev", "snk_greedy_batch_finish", "snk_greedy_sharded_batch_dev",
-                    "snk_db_set_standardisation", "snk_prepare_targets", "snk_greedy_batch_unnorm",
+                    "snk_db_set_standardisation", "snk_prepare_targets", "snk_halfphone_targets",
+                    "snk_halfphone_targets_dev", "snk_greedy_batch_unnorm",
                     "snk_greedy_batch_unnorm_dev",
                     "snk_candidate_distances", "snk_join_tiles", "snk_join_stats", "snk_join_viterbi_batch",
                     "snk_join_viterbi_batch_dev", "snk_acoustic_viterbi_batch", "snk_acoustic_viterbi_batch_dev",
@@ -291,6 +294,22 @@ class UnitDatabase:
         out = np.empty(unnorm.shape, dtype=np.float64)
         _check(load_library().snk_prepare_targets(self._h, _ptr(unnorm, C.c_float), unnorm.shape[0],
                                                   _ptr(out, C.c_double)))
+        return out
+
+    def halfphone_targets(self, unnorm, points, durations=None):
+        """weight(hstack(standardise(unnorm)[points], durations)) on the device: float32 [frames, dim], int [n, P]
+        (+ float64 [n]) -> float64 [n, Dt]."""
+        unnorm = np.ascontiguousarray(unnorm, dtype=np.float32)
+        points = np.ascontiguousarray(points, dtype=np.int64)
+        if unnorm.ndim != 2 or points.ndim != 2:
+            raise ValueError("unnorm must be [frames, dim] and points [n, P]")
+        dur = None if durations is None else np.ascontiguousarray(np.asarray(durations, dtype=np.float64).reshape(-1))
+        if dur is not None and dur.shape[0] != points.shape[0]:
+            raise ValueError("one duration per unit")
+        out = np.empty((points.shape[0], self.Dt), dtype=np.float64)
+        _check(load_library().snk_halfphone_targets(self._h, _ptr(unnorm, C.c_float), unnorm.shape[0], unnorm.shape[1],
+                                                    _ptr(points, C.c_int64), points.shape[0], points.shape[1],
+                                                    _ptr(dur, C.c_double), _ptr(out, C.c_double)))
         return out
 
     def greedy_batch_cat(self, cat, lens, start_states=None, return_dists=False, unnorm=False):

@@ -63,6 +63,41 @@ def segment_axis_cut(a, length):
     return a[: n * length].reshape(n, length * a.shape[1])
 
 
+def halfphone_unit_points(labels, n_frames):
+    """Frame indices that describe every half-phone of an utterance (train_halfphone.py:959-1070).  labels: the
+    reference's 5-state alignment, a list of ((start, end), lab) with lab = [ll, l, c, r, rr, state] and states '2'..'6'
+    per phone.  States 2-3 make the left half-phone (first frame: start of 2, middle: end of 2, last: end of 3), states
+    4-6 the right one (start of 4, end of 5, end of 6); ends past the utterance are clipped to its last frame.
+    Returns (names, starts, middles, ends): names 'll/l/c_L/r/rr' style, int64 arrays of equal length."""
+    if len(labels) % 5 != 0:
+        raise AssertionError("There must be 5 states for each phone in label")
+    names, starts, middles, ends = [], [], [], []
+    for (s, e), lab in labels:
+        e = min(e, n_frames - 1)
+        if len(lab) != 6:
+            raise AssertionError("label must be a quinphone plus state")
+        state = lab[-1]
+        if state in ("2", "4"):
+            quin = list(lab[:5])
+            quin[2] += "_L" if state == "2" else "_R"
+            if any(LABEL_DELIMITER in part for part in quin):
+                raise AssertionError("delimiter %s occurs in one or more name element (%s)" % (LABEL_DELIMITER, quin))
+            names.append(LABEL_DELIMITER.join(quin))
+            starts.append(s)
+            if state == "2":
+                middles.append(e)
+        elif state == "5":
+            middles.append(e)
+        elif state in ("3", "6"):
+            ends.append(e)
+        else:
+            raise ValueError("bad state number")
+    if not (len(names) == len(starts) == len(middles) == len(ends) == 2 * (len(labels) // 5)):
+        raise AssertionError("state alignment does not describe two half-phones per phone")
+    as_int = lambda v: np.asarray(v, dtype=np.int64)
+    return np.array(names), as_int(starts), as_int(middles), as_int(ends)
+
+
 class Synthesiser:
     def __init__(self, config, train_unit_features_unweighted, join_contexts_unweighted, device=0, verbose=False,
                  train_unit_names=None):
@@ -263,7 +298,10 @@ class Synthesiser:
         """The voice's mean_vec_target / std_vec_target (synth_simple.py:96-97) and const.py:12-14."""
         self.mean_vec_target = np.asarray(mean_vec_target)      # dtype kept: float32 statistics -> float32 arithmetic
         self.std_vec_target = np.asarray(std_vec_target)
-        self.db.set_standardisation(self.mean_vec_target, self.std_vec_target, special_uv_value, uv_scaling_factor)
+        # a half-phone voice standardises FRAMES (dim columns) before it samples them into Dt-wide units: those
+        # statistics reach the device per point in halfphone_targets()
+        if self.mean_vec_target.size == self.db.Dt:
+            self.db.set_standardisation(self.mean_vec_target, self.std_vec_target, special_uv_value, uv_scaling_factor)
 
     def prepare_targets(self, unnorm_speech):
         """weight(standardise(unnorm_speech), target_weight_vector): compose_speech's float32 output in,
@@ -271,6 +309,31 @@ class Synthesiser:
         With REPLICATE_IS2018_EXP the first and the last frame are dropped (synth_simple.py:384-387)."""
         self._push_weights()
         return self.db.prepare_targets(self._trim_speech(unnorm_speech))
+
+    def halfphone_targets(self, unnorm_speech, labels, durations=None):
+        """The half-phone unit_features of synth_utt (synth_halfphone.py:1510-1548): standardise the utterance, sample
+        every half-phone at the frames its state alignment names (get_halfphone_stats, train_halfphone.py:959-1070),
+        append the normalised durations (config add_duration_as_target) and weight -- the frame picking on the host
+        (labels are Python objects), everything else in one device kernel on float32 input.  Needs set_standardisation
+        with the FRAME statistics (synth_halfphone.py mean_vec_target / std_vec_target); returns
+        (unit_names, unit_features float64 [n, Dt], unit_timings)."""
+        u = np.asarray(unnorm_speech, dtype=np.float32)
+        names, starts, middles, ends = halfphone_unit_points(labels, u.shape[0])
+        rep = self.target_representation
+        points = {"onepoint": [middles], "twopoint": [starts, ends], "threepoint": [starts, middles, ends]}[rep]
+        points = np.stack(points, axis=1)
+        npts, dim = points.shape[1], u.shape[1]
+        extra = 1 if durations is not None else 0
+        if npts * dim + extra != self.db.Dt:
+            raise ValueError("%s targets of %d-dim frames%s are %d wide, the voice's are %d" %
+                             (rep, dim, " + duration" if extra else "", npts * dim + extra, self.db.Dt))
+        # the device applies column-wise statistics: the frame statistics once per point (the duration is only weighted)
+        mean = np.concatenate([np.ravel(self.mean_vec_target)] * npts + [np.zeros(extra, self.mean_vec_target.dtype)])
+        std = np.concatenate([np.ravel(self.std_vec_target)] * npts + [np.ones(extra, self.std_vec_target.dtype)])
+        self._push_weights()
+        self.db.set_standardisation(mean, std, -1000.0, 20.0)
+        feats = self.db.halfphone_targets(u, points, durations)
+        return names, feats, list(zip(starts.tolist(), ends.tolist()))
 
     def _trim_speech(self, unnorm_speech):
         u = np.asarray(unnorm_speech, dtype=np.float32)

@@ -82,7 +82,25 @@ def input_arrays(ge, gh):
     inp["std_std"] = rng.uniform(0.5, 2.0, size=(1, 61))
     inp["taper_frag"] = rng.standard_normal((10, 7)).astype(np.float32)
     inp["seg_a"] = rng.standard_normal((23, 3))
+    # half-phone target preparation (train_halfphone.py:959-1070): 6 phones x 5 states over a 70-frame utterance whose last
+    # state runs past the end (clipped), un-normalised speech with unvoiced markers, normalised durations
+    bounds = np.sort(rng.choice(np.arange(1, 72), size=29, replace=False))
+    inp["hp3_state_ends"] = np.concatenate([bounds, [74]]).astype(np.int64)          # end frame of each of the 30 states
+    inp["hp3_speech"] = rng.standard_normal((70, 61)).astype(np.float32) * 2 + 0.5
+    inp["hp3_speech"][rng.random((70, 61)) < 0.05] = -1000.0
+    inp["hp3_speech"][:, 60][::4] = -1000.0
+    inp["hp3_dur"] = rng.standard_normal((12, 1))
     return inp
+
+
+def hp3_labels(state_ends):
+    """The reference's label structure: [((start, end), [ll, l, c, r, rr, state]), ...] (label_manip.py / read_label)."""
+    labs, s = [], 0
+    for i, e in enumerate(state_ends.tolist()):
+        ph = i // 5
+        labs.append(((s, int(e)), ["p%d" % (ph - 2), "p%d" % (ph - 1), "p%d" % ph, "p%d" % (ph + 1), "p%d" % (ph + 2), str(2 + i % 5)]))
+        s = int(e) + 1
+    return labs
 
 
 def generate(ge, gh, inp):
@@ -164,6 +182,17 @@ def generate(ge, gh, inp):
         st = dm_.standardise(sp, inp["std_mean"].astype(cast), inp["std_std"].astype(cast))
         out["std_out_" + nm] = st
         out["std_weighted_" + nm] = weight(st, np.linspace(0.1, 1.0, 61))
+    # half-phone targets: standardise -> get_halfphone_stats -> hstack(durations) -> weight (synth_halfphone.py:1510-1548)
+    th = R.load_module("train_halfphone")
+    labs = hp3_labels(inp["hp3_state_ends"])
+    for nm, cast in (("f64", np.float64), ("f32", np.float32)):
+        st = dm_.standardise(np.array(inp["hp3_speech"]), inp["std_mean"].astype(cast), inp["std_std"].astype(cast))
+        for rep, npts in (("onepoint", 1), ("twopoint", 2), ("threepoint", 3)):
+            names, feats, timings = th.get_halfphone_stats(st, labs, representation_type=rep)
+            out["hp3_%s_%s" % (rep, nm)] = weight(feats, np.linspace(0.2, 1.1, 61 * npts))
+        out["hp3_names"] = np.array([str(n) for n in names])
+        out["hp3_timings"] = np.array(timings, dtype=np.int64)
+        out["hp3_threepoint_dur_" + nm] = weight(np.hstack([feats, inp["hp3_dur"]]), np.linspace(0.2, 1.1, 184))
     mo = R.load_module("matrix_operations")
     out["taper_out"] = mo.taper_matrix(mo.zero_pad_matrix(np.array(inp["taper_frag"]), 2, 0), 4)
     out["taper_out_f32"] = mo.taper_matrix(np.array(inp["taper_frag"]), 4)

@@ -201,3 +201,23 @@ def test_stashable_tree_vs_sklearn_kdtree():
     assert np.array_equal(tree.query(data[:50], k=1)[1][:, 0], np.arange(50))        # a stored point finds itself
     ii = tree.query(X, k=3, return_distance=False)
     assert np.array_equal(ii, ref.query(X, k=3, return_distance=False))
+
+
+def test_halfphone_target_preparation_equals_reference_run(fx, inputs, golden_halfphone):
+    """Row N4, half-phone part: standardise -> get_halfphone_stats (three-point sampling from the state alignment) ->
+    hstack(durations) -> weight (synth_halfphone.py:1510-1548, train_halfphone.py:959-1070), bit for bit in both of
+    numpy's arithmetic modes, from un-normalised float32 speech in one device kernel."""
+    gh = golden_halfphone
+    labs = MF.hp3_labels(inputs["hp3_state_ends"])
+    g = Synthesiser(halfphone_config(n_candidates=4), gh["F"], gh["Jc"])
+    assert g.db.Dt == 184 and g.target_representation == "threepoint"
+    g.db.set_weights(np.linspace(0.2, 1.1, 184), g.join_weight_vector)
+    g._dirty = False
+    for nm, cast in (("f64", np.float64), ("f32", np.float32)):
+        g.set_standardisation(inputs["std_mean"].astype(cast), inputs["std_std"].astype(cast).reshape(-1))
+        names, feats, timings = g.halfphone_targets(inputs["hp3_speech"], labs, durations=inputs["hp3_dur"])
+        assert names.tolist() == fx["hp3_names"].tolist()
+        assert np.array_equal(np.asarray(timings), fx["hp3_timings"])
+        assert np.array_equal(feats, fx["hp3_threepoint_dur_" + nm])
+    with pytest.raises(ValueError):
+        g.halfphone_targets(inputs["hp3_speech"], labs)                 # 183 columns, the voice has 184

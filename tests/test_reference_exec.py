@@ -39,7 +39,8 @@ def test_committed_fixtures_equal_a_fresh_run_of_the_reference(fx, golden_epoch,
     fresh = MF.generate(golden_epoch, golden_halfphone, inp)
     assert sorted(fresh) == sorted(k for k in fx.files if not k.startswith("in_"))
     for k, v in fresh.items():
-        assert np.array_equal(fx[k], np.asarray(v), equal_nan=True), "fixture %s is stale" % k
+        v = np.asarray(v)
+        assert np.array_equal(fx[k], v, equal_nan=v.dtype.kind == "f"), "fixture %s is stale" % k
 
 
 @pytest.mark.skipif(not R.available(), reason="reference sources not present (GPU box)")
@@ -232,3 +233,22 @@ def test_minifst_py2_str_mode_rounds_through_twelve_digits():
     finally:
         minifst.Compiler.py2_str = False
     assert f.arcs[0][0][2] == np.float32(float("%.12g" % w))
+
+
+def test_oracle_and_host_label_logic_match_reference_halfphone_stats(fx, inputs):
+    """train_halfphone.get_halfphone_stats as the reference runs it: the oracle's restatement and the product's host-side
+    frame picking (snickery_b200.synth.halfphone_unit_points) give the same names, timings and sampled frames."""
+    from snickery_b200.synth import halfphone_unit_points
+    labs = MF.hp3_labels(inputs["hp3_state_ends"])
+    names, starts, middles, ends = halfphone_unit_points(labs, 70)
+    assert names.tolist() == fx["hp3_names"].tolist()
+    assert np.array_equal(np.stack([starts, ends], axis=1), fx["hp3_timings"])
+    assert ends.max() == 69                                      # the last state ran past the utterance: clipped
+    for nm, cast in (("f64", np.float64), ("f32", np.float32)):
+        st = O.standardise(np.array(inputs["hp3_speech"]), inputs["std_mean"].astype(cast), inputs["std_std"].astype(cast))
+        for rep, npts in (("onepoint", 1), ("twopoint", 2), ("threepoint", 3)):
+            n2, feats, timings = O.halfphone_stats(st, labs, rep)
+            assert n2.tolist() == names.tolist() and timings == list(zip(starts.tolist(), ends.tolist()))
+            assert np.array_equal(O.weight(feats, np.linspace(0.2, 1.1, 61 * npts)), fx["hp3_%s_%s" % (rep, nm)])
+            pts = {"onepoint": [middles], "twopoint": [starts, ends], "threepoint": [starts, middles, ends]}[rep]
+            assert np.array_equal(np.hstack([st[p] for p in pts]), feats)
