@@ -323,6 +323,22 @@ class Dist:
         self.barrier()
         return self.max(e0.elapsed_time(e1)) / reps
 
+    def timed_median(self, fn, reps, warm=1):
+        """Like timed(), one event pair per call, median over the calls: for calls that end in a host-side wait (the
+        *_finish step), where a single slow host iteration would otherwise be averaged into the device figure."""
+        torch = self.torch
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        stream = torch.cuda.current_stream()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for e0, e1 in ev:
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+        self.barrier()
+        return self.max(float(np.median([e0.elapsed_time(e1) for e0, e1 in ev])))
+
     def close(self):
         if self.world > 1:
             self.dist.barrier()
@@ -643,7 +659,9 @@ def block_halfphone(D, args, headline):
 
     reps = max(2, min(args.steps, 5))
     g.db.counters(reset=True)
-    ms_pipe = D.timed(pipeline, reps, warm=2)
+    # as the headline (--workload halfphone) the contract's timing: K calls between one pair of events; as a block of the
+    # default run the median of five calls (each ends in a host-side wait, one slow host iteration should not be averaged in)
+    ms_pipe = D.timed(pipeline, reps, warm=2) if headline else D.timed_median(pipeline, 5, warm=2)
     c = g.db.counters()
     found = int((d_plen > 0).sum().item())
     g.db.profile_enable(True)
