@@ -12,8 +12,10 @@
 //    lets tcgen05 accumulate hi.hi + hi.lo + lo.hi in fp32 (the dropped lo.lo term is 2^-22 of |x||y|);
 //  * decides natural joins by INDEX: end[a] and start[c] are the same row of the join matrix iff c == a + 1
 //    (synth_halfphone.py:693-707), and cost exactly 0;
-//  * recomputes the entries that still cancel, d^2 < theta (|x|^2 + |y|^2), from the raw float32 rows by direct
-//    float64 differences -- the reference's own arithmetic (a few per thousand on the config-3 lattices).
+//  * recomputes the entries that still cancel, d^2 < theta (|x|^2 + |y|^2), theta = 3/32, from the raw float32 rows by
+//    direct differences (exact subtraction of nearby float32 values; 1.3 % of the entries on the config-3 lattices).
+//    The error of an entry that is NOT recomputed is that of the fp32 accumulation, <= 1.4e-6 (|x|^2 + |y|^2) on d^2 over
+//    every entry measured, i.e. <= 1.4e-6 / (2 theta) = 7.5e-6 relative on the cost: inside the 1e-5 the costs are held to.
 // Measured against the float64 formula: tests/test_gpu_join_tc.py and DESIGN.md section 4.4.
 //
 // Persistent CTAs (128 threads, seven per SM) take tiles round robin.  Per tile and 32-dim group: every thread loads
@@ -89,18 +91,32 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
 
 __device__ __forceinline__ bool admissible(int64_t u, int64_t N) { return u >= 1 && u < N - 1; }
 
-// float64 direct-difference join cost of join-matrix rows re (an end row) and rs (a start row): one warp, all lanes return it
-__device__ __forceinline__ double direct_join(const jt_params &p, int re, int rs, int lane) {
+// direct-difference join cost of join-matrix rows re (an end row) and rs (a start row) from the RAW float32 voice values:
+// the subtraction of two nearby float32 numbers is exact, the weight multiplies the difference (one rounding) and the 151
+// squares are summed in float32 over a shuffle tree: ~1e-7 relative however close the rows are -- and exactly 0 for equal
+// rows.  One warp, all lanes return the cost.
+__device__ __forceinline__ float direct_join(const jt_params &p, int re, int rs, int lane) {
     const float *e = p.Jc_raw + (size_t)re * p.Dj, *s = p.Jc_raw + (size_t)rs * p.Dj;
-    double acc = 0.0;
-    for (int d = lane; d < p.Dj; d += 32) {
-        const double w = p.wj[d];
-        const double x = (double)e[d] * w - (double)s[d] * w;     // f32 * f64 products, as the reference forms them
-        acc = fma(x, x, acc);
+    float acc = 0.f;
+    for (int d0 = 0; d0 < p.Dj; d0 += 160) {           // ten loads in flight per lane: one L2 round trip per 160 dims
+        float ev[5], sv[5], wv[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int d = d0 + lane + 32 * i;
+            const bool in = d < p.Dj;
+            ev[i] = in ? __ldg(e + d) : 0.f;
+            sv[i] = in ? __ldg(s + d) : 0.f;
+            wv[i] = in ? (float)p.wj[d] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const float x = (ev[i] - sv[i]) * wv[i];
+            acc = fmaf(x, x, acc);
+        }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    return sqrt(acc);
+    return sqrtf(acc);
 }
 
 // centre, scale and split four consecutive dims of one row; store hi / lo into the swizzled operand row; return |x s|^2.
@@ -310,20 +326,20 @@ __global__ void __launch_bounds__(JT_THREADS, JT_CTAS_PER_SM) join_tile_tc_kerne
             }
         }
         __syncthreads();
-        // ---- queued entries: direct float64 differences, one warp per entry
+        // ---- queued entries: direct differences of the raw rows, one warp per entry
         const int nq = s_cnt[2];
         if (nq > 0) {
             for (int i = warp; i < min(nq, JT_PLIST); i += JT_THREADS / 32) {
                 const int a = plist[i] >> 8, cc = plist[i] & 255;
-                const double d = direct_join(p, ua[a], uc[cc], lane);
-                if (lane == 0) Jbuf[a * JT_LDJ + cc] = (float)d;
+                const float d = direct_join(p, ua[a], uc[cc], lane);
+                if (lane == 0) Jbuf[a * JT_LDJ + cc] = d;
             }
             if (nq > JT_PLIST) {      // more than the queue holds (a lattice full of duplicates): find the marked entries
                 for (int i = warp; i < K * K; i += JT_THREADS / 32) {
                     const int a = i / K, cc = i - a * K;
                     if (Jbuf[a * JT_LDJ + cc] < 0.f) {
-                        const double d = direct_join(p, ua[a], uc[cc], lane);
-                        if (lane == 0) Jbuf[a * JT_LDJ + cc] = (float)d;
+                        const float d = direct_join(p, ua[a], uc[cc], lane);
+                        if (lane == 0) Jbuf[a * JT_LDJ + cc] = d;
                     }
                 }
             }
@@ -389,7 +405,7 @@ int ensure_scale(snk_db *db, cudaStream_t st) {
 
 float join_theta() {
     if (const char *e = getenv("SNK_JOIN_THETA")) return (float)atof(e);
-    return 0.0625f;
+    return 0.09375f;
 }
 
 }  // namespace

@@ -25,7 +25,7 @@ g = Synthesiser(cfg, hp["F"], hp["Jc"])
 utts = [O.weight(x, o.target_weight_vector) for x in syn.make_targets(hp["F"], 4, 80, seed=31)]
 cands = [g.preselect_units_acoustic(u)[0] for u in utts]
 import os
-for th in ("0.0625", "0.125"):
+for th in ("0.09375", "0.0625", "0.125"):
     os.environ["SNK_JOIN_THETA"] = th
     tiles = g.db.join_tiles(cands)
     fin_total, patched = g.db.join_stats()

@@ -12,7 +12,7 @@ from snickery_b200 import Synthesiser, synthetic as syn
 
 pytestmark = pytest.mark.gpu
 
-TILE_RTOL = 2e-5     # worst finite tile entry against sqrt(sum((end[a] - start[c])^2)) in float64 (rows that nearly coincide)
+TILE_RTOL = 1e-5     # worst finite tile entry against sqrt(sum((end[a] - start[c])^2)) in float64 (rows that nearly coincide)
 TILE_P99 = 6e-6      # 99 % of the entries
 TIE_RTOL = 1e-6
 COST_RTOL = 1e-5
@@ -80,7 +80,7 @@ def test_tiles_against_float64_formula(voice, K):
     rel = np.abs(tiles[pos] - ref[pos]) / ref[pos]
     assert rel.max() <= TILE_RTOL, "worst tile entry off by %.3g relative" % rel.max()
     assert np.quantile(rel, 0.99) <= TILE_P99
-    assert 0 < patched < 0.05 * fin_total                          # near-coincident rows exist here and are few
+    assert 0 < patched < 0.1 * fin_total                           # near-coincident rows exist here and are few
 
 
 def test_search_on_tc_tiles_equals_direct_difference_tiles(voice):
