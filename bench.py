@@ -670,7 +670,6 @@ def block_halfphone(D, args, headline):
     ms_jv = D.timed(jv_only, reps, warm=1)
     pj = g.db.profile_read(engine.PROF_JOIN)
     pv = g.db.profile_read(engine.PROF_VITERBI)
-    pf = g.db.profile_read(engine.PROF_JOIN_VITERBI)
     g.db.profile_enable(False)
     # (b) host buffers
     g.db.acoustic_viterbi_batch_cat(pinned.numpy(), lens, K)
@@ -700,7 +699,7 @@ def block_halfphone(D, args, headline):
         "join_viterbi": {"ms": ms_jv, "frames_per_s": world * B * T / (ms_jv / 1e3),
                          "what": "join costs + Viterbi on given candidate lattices (snk_join_viterbi_batch_dev)"},
     }
-    for name, p in (("join_tiles", pj), ("viterbi", pv), ("fused_join_viterbi", pf)):
+    for name, p in (("join_tiles", pj), ("viterbi", pv)):
         if p["launches"]:
             msl = p["ms"] / p["launches"]
             gbs = p["work"] / p["launches"] / (msl / 1e3) / 1e9

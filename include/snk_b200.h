@@ -90,7 +90,7 @@ int snk_db_counters(const snk_db *db, int64_t counters[4], int reset);
 #define SNK_PROF_VITERBI 2
 #define SNK_PROF_ALLGATHER 3 /* work = bytes received over NVLink by this rank */
 #define SNK_PROF_MERGE 4     /* work = bytes merged */
-#define SNK_PROF_JOIN_VITERBI 5 /* fused join-cost + Viterbi kernel; work = gathered bytes */
+#define SNK_PROF_JOIN_VITERBI 5 /* reserved (a fused join-cost + Viterbi kernel was measured and not kept) */
 #define SNK_PROF_RERANK 6    /* float64 re-rank of the shortlists; work = gathered bytes */
 int snk_db_profile_enable(snk_db *db, int enable);
 int snk_db_profile_read(snk_db *db, int which, double *total_ms, int64_t *launches, double *work, int reset);
