@@ -49,51 +49,77 @@ __device__ __forceinline__ bool dpair_lt(double v1, int i1, double v2, int i2) {
     return v1 < v2 || (v1 == v2 && i1 < i2);
 }
 
-// sum over a contiguous segment of (q - f32 row * f64 weight)^2 for two rows at once; loads are issued
-// four deep before they are consumed so the gathers overlap
-__device__ __forceinline__ void seg_pair(const float *__restrict__ r0, const float *__restrict__ r1,
-                                         const double *__restrict__ w_s, const double *__restrict__ q_s, int n, int lane,
-                                         double &a0, double &a1) {
+// sum over a contiguous segment of (q - f32 row * f64 weight)^2 for R rows at once.  The row value is the reference's own:
+// the float32 voice value times the float64 weight, ROUNDED to float64 (speech_manip.py:209-213); the difference to the query
+// is rounded, its square is fused into the sum.  A row's arithmetic does not depend on R, so every caller gets the same bits.
+// Loads are issued four deep before they are consumed so the gathers overlap; the query and the weights are read from
+// shared memory once for all R rows.
+template <int R>
+__device__ __forceinline__ void seg_rows(const float *const (&r)[R], const double *__restrict__ w_s,
+                                         const double *__restrict__ q_s, int n, int lane, double (&a)[R]) {
     int d = lane;
     for (; d + 96 < n; d += 128) {
-        float y0[4], y1[4];
+        float y[R][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { y0[u] = __ldg(r0 + d + 32 * u); y1[u] = __ldg(r1 + d + 32 * u); }
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < R; ++i) y[i][u] = __ldg(r[i] + d + 32 * u);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const double w = w_s[d + 32 * u], x = q_s[d + 32 * u];
-            const double e0 = __dsub_rn(x, (double)y0[u] * w), e1 = __dsub_rn(x, (double)y1[u] * w);
-            a0 = __dadd_rn(a0, __dmul_rn(e0, e0));
-            a1 = __dadd_rn(a1, __dmul_rn(e1, e1));
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const double e = __dsub_rn(x, __dmul_rn((double)y[i][u], w));
+                a[i] = __fma_rn(e, e, a[i]);
+            }
         }
     }
     for (; d < n; d += 32) {
         const double w = w_s[d], x = q_s[d];
-        const double e0 = __dsub_rn(x, (double)__ldg(r0 + d) * w), e1 = __dsub_rn(x, (double)__ldg(r1 + d) * w);
-        a0 = __dadd_rn(a0, __dmul_rn(e0, e0));
-        a1 = __dadd_rn(a1, __dmul_rn(e1, e1));
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const double e = __dsub_rn(x, __dmul_rn((double)__ldg(r[i] + d), w));
+            a[i] = __fma_rn(e, e, a[i]);
+        }
     }
 }
 
-// squared float64 distances of rows u0 and u1 (u1 < 0: only u0) to the query held in shared memory.
+// squared float64 distances of the rows u[0..R) (u[i] < 0: skipped, +inf) to the query held in shared memory.
 // wB_s holds the target weights repeated over the m frames of the window (the window is contiguous in F_raw).
-__device__ __forceinline__ void row_pair_dist(const rr_space &sp, const double *__restrict__ q_s,
-                                              const double *__restrict__ wA_s, const double *__restrict__ wB_s, int u0,
-                                              int u1, int lane, double &out0, double &out1) {
-    double a0 = 0.0, a1 = 0.0;
-    const bool two = u1 >= 0;
-    const int v1 = two ? u1 : u0;
-    if (sp.dA > 0)
-        seg_pair(sp.A + ((int64_t)u0 + sp.a_row_off) * sp.ldA + sp.a_col, sp.A + ((int64_t)v1 + sp.a_row_off) * sp.ldA + sp.a_col,
-                 wA_s, q_s, sp.dA, lane, a0, a1);
-    seg_pair(sp.B + (int64_t)u0 * sp.ldB, sp.B + (int64_t)v1 * sp.ldB, wB_s, q_s + sp.dA, sp.dB, lane, a0, a1);
+template <int R>
+__device__ __forceinline__ void rows_dist(const rr_space &sp, const double *__restrict__ q_s, const double *__restrict__ wA_s,
+                                          const double *__restrict__ wB_s, const int (&u)[R], int lane, double (&out)[R]) {
+    double a[R];
+    int v[R];
+    int first = -1;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        a0 = __dadd_rn(a0, __shfl_xor_sync(0xffffffffu, a0, off));
-        a1 = __dadd_rn(a1, __shfl_xor_sync(0xffffffffu, a1, off));
+    for (int i = 0; i < R; ++i) {
+        a[i] = 0.0;
+        if (first < 0 && u[i] >= 0) first = u[i];
     }
-    out0 = a0;
-    out1 = two ? a1 : INFINITY;
+    if (first < 0) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) out[i] = INFINITY;
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) v[i] = u[i] >= 0 ? u[i] : first;       // absent rows recompute a present one
+    if (sp.dA > 0) {
+        const float *ra[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) ra[i] = sp.A + ((int64_t)v[i] + sp.a_row_off) * sp.ldA + sp.a_col;
+        seg_rows<R>(ra, wA_s, q_s, sp.dA, lane, a);
+    }
+    const float *rb[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) rb[i] = sp.B + (int64_t)v[i] * sp.ldB;
+    seg_rows<R>(rb, wB_s, q_s + sp.dA, sp.dB, lane, a);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int i = 0; i < R; ++i) a[i] = __dadd_rn(a[i], __shfl_xor_sync(0xffffffffu, a[i], off));
+#pragma unroll
+    for (int i = 0; i < R; ++i) out[i] = u[i] >= 0 ? a[i] : INFINITY;
 }
 
 template <bool kMerge, int THREADS>
@@ -195,19 +221,17 @@ rerank_kernel(rr_space sp, const double *__restrict__ Q, const float *__restrict
     }
     __syncthreads();
 
-    // exact distances, two shortlisted rows per warp pass
-    for (int c = 2 * warp; c < KP; c += 2 * nwarp) {
-        const int u0 = ids[c], u1 = (c + 1 < KP) ? ids[c + 1] : INT_MAX;
-        double r0 = INFINITY, r1 = INFINITY;
-        if (u0 != INT_MAX) {
-            row_pair_dist(sp, q_s, wA_s, wB_s, u0, u1 != INT_MAX ? u1 : -1, lane, r0, r1);
-        } else if (u1 != INT_MAX) {
-            double dummy;
-            row_pair_dist(sp, q_s, wA_s, wB_s, u1, -1, lane, r1, dummy);
-        }
+    // exact distances, four shortlisted rows per warp pass
+    for (int c = 4 * warp; c < KP; c += 4 * nwarp) {
+        int u[4];
+        double r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = (c + i < KP && ids[c + i] != INT_MAX) ? ids[c + i] : -1;
+        rows_dist<4>(sp, q_s, wA_s, wB_s, u, lane, r);
         if (lane == 0) {
-            d2[c] = r0;
-            if (c + 1 < KP) d2[c + 1] = r1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (c + i < KP) d2[c + i] = r[i];
         }
     }
     __syncthreads();
@@ -308,6 +332,7 @@ int snk_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, co
     const rr_space rs = make_rr(db, sp);
     const size_t smem = rr_smem(rs, KP, 0);
     const int dbg = !d_cert ? 0 : (cert_mode == SNK_CERT_FP32 ? db->debug_fail_mod2 : db->debug_fail_mod);
+    snk_prof_scope prof(db, SNK_PROF_RERANK, (double)nq * KP * sp.D * 4, st);      // work = row bytes gathered
     if (rr_small_blocks(db, nq))
         rerank_kernel<false, RR_THREADS_SMALL><<<(unsigned)nq, RR_THREADS_SMALL, smem, st>>>(
             rs, dQ, d_val, d_id, KP, 0, 0, k, d_dist, d_idx, out_stride, id_offset, sp.rows, d_qerr, d_dberr, d_qn,
@@ -334,6 +359,7 @@ int snk_merge_rerank(snk_db *db, const snk_space &sp, const double *dQ, int64_t 
     const rr_space rs = make_rr(db, sp);
     const size_t smem = rr_smem(rs, KP, nlists * lsz);
     const int dbg = d_cert ? db->debug_fail_mod : 0;
+    snk_prof_scope prof(db, SNK_PROF_RERANK, (double)nq * KP * sp.D * 4, st);
     if (rr_small_blocks(db, nq))
         rerank_kernel<true, RR_THREADS_SMALL><<<(unsigned)nq, RR_THREADS_SMALL, smem, st>>>(
             rs, dQ, d_lval, d_lid, KP, nlists, lsz, k, d_dist, d_idx, out_stride, id_offset, sp.rows, d_qerr, d_dberr,
@@ -362,12 +388,16 @@ __global__ void exact_dist_kernel(rr_space sp, const double *__restrict__ Q, int
     for (int d = tid; d < sp.dB; d += blockDim.x) wB_s[d] = sp.wB[d % sp.Dt];
     __syncthreads();
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + tid) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t u = 2 * warp; u < rows; u += 2 * nwarp) {
-        double r0, r1;
-        row_pair_dist(sp, q_s, wA_s, wB_s, (int)u, u + 1 < rows ? (int)(u + 1) : -1, lane, r0, r1);
+    for (int64_t u = 4 * warp; u < rows; u += 4 * nwarp) {
+        int uu[4];
+        double r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) uu[i] = u + i < rows ? (int)(u + i) : -1;
+        rows_dist<4>(sp, q_s, wA_s, wB_s, uu, lane, r);
         if (lane == 0) {
-            d2[u] = r0;
-            if (u + 1 < rows) d2[u + 1] = r1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (u + i < rows) d2[u + i] = r[i];
         }
     }
 }
