@@ -577,7 +577,11 @@ def block_sharded_greedy(D, db, wt, wj, cfg):
     res = {"what": "configs[1] joint rows sharded by row block over the ranks, join contexts replicated; one grouped "
                    "ncclAllGather (distance, global row, bound: B x 24 bytes per rank) + arg-min / certificate kernel per "
                    "time step, enqueued by the library; device time, max over ranks",
-           "n_gpus": world, "rows_per_gpu": int(sg.knn.hi - sg.knn.lo), "steps": steps, "cases": []}
+           "n_gpus": world, "rows_per_gpu": int(sg.knn.hi - sg.knn.lo), "steps": steps,
+           "exchange": "one kernel over NVLink peer memory (CUDA IPC): stores into every peer, epoch flag, wait, arg-min"
+                       if sg.knn.db.comm_info()["peer_exchange"] else
+                       ("grouped ncclAllGather + arg-min kernel" if world > 1 else "none (one rank)"),
+           "cases": []}
     for B in (1024, 1):
         tg = torch.from_numpy(make_batch(F, wt, B, steps * MULTIEPOCH, seed=31 + B).reshape(B, steps * MULTIEPOCH, -1)).to(dev)
         paths = [None]
@@ -591,7 +595,7 @@ def block_sharded_greedy(D, db, wt, wj, cfg):
         ag = sg.knn.db.profile_read(engine.PROF_ALLGATHER)
         sg.knn.db.profile_enable(False)
         case = {"utterances": B, "us_per_step": ms * 1e3 / steps,
-                # event time around the grouped collective on this rank: includes waiting for the slowest rank to arrive
+                # event time around the exchange on this rank: includes waiting for the slowest rank to arrive
                 "us_per_step_in_allgather": (ag["ms"] * 1e3 / ag["launches"]) if ag["launches"] else 0.0,
                 "nvlink_bytes_received_per_rank_per_step": B * 24 * (world - 1)}
         if B == 1024:       # parity sample against the replicated database

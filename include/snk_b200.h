@@ -134,6 +134,11 @@ int snk_topk_merge_dev(int device_id, const double *d_dist_all, const int64_t *d
 int snk_comm_unique_id(void *id_out, int id_bytes);
 int snk_comm_init(snk_db *db, const void *unique_id, int rank, int nranks);
 int snk_comm_info(snk_db *db, int *rank, int *nranks, int *nccl_version);
+/* 1 if the per-step exchange of snk_greedy_sharded_batch_dev runs over NVLink peer memory (every rank's exchange region
+ * is mapped into the others through CUDA IPC at snk_comm_init; one kernel per step stores into all peers, publishes an
+ * epoch and waits for the others'), 0 if it goes through ncclAllGather (a platform without IPC between the processes,
+ * SNK_COMM_NO_P2P=1, or more than 4096 utterances per step).                                                          */
+int snk_comm_peer_exchange(const snk_db *db);
 int snk_knn_sharded_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist,
                         int64_t *d_idx, int64_t id_offset, void *stream);
 int snk_knn_sharded_finish(snk_db *db);

@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 #include <string.h>
 #include <algorithm>
+#include <vector>
 
 // the slice of nccl.h this file uses (the ABI of these entry points is stable across NCCL 2.x)
 extern "C" {
@@ -22,6 +23,8 @@ typedef enum { ncclSuccess = 0 } ncclResult_t;
 typedef enum { ncclInt8 = 0, ncclInt32 = 2, ncclInt64 = 4, ncclFloat64 = 8 } ncclDataType_t;
 typedef enum { ncclSum = 0, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
 }
+
+constexpr int SNK_MAX_RANKS = 16;
 
 namespace {
 
@@ -84,12 +87,28 @@ struct snk_comm_state {
     int64_t *d_idx = nullptr;
     cudaStream_t st = nullptr;
     int *d_nfail = nullptr;    // [2]: local failures, sum over ranks
+    // peer-memory exchange of the sharded greedy search: every rank owns one region
+    //     flags [nranks] u32 (epoch of the last step rank r has delivered), padded to 256 B
+    //     data  [2 step parities][nranks writers][P2P_CAP queries] x {dist f64, row i64, bound f64}
+    // mapped into every other rank through CUDA IPC; peers[r] is rank r's region as seen from this process
+    bool p2p = false;
+    char *region = nullptr;
+    char *peers[SNK_MAX_RANKS] = {};
+    char **d_peers = nullptr;   // the same table on the device
+    unsigned epoch = 0;
 };
+constexpr int P2P_CAP = 4096;                                   // queries per exchange step (more: NCCL path)
+constexpr size_t P2P_FLAGS_BYTES = 256;
+static size_t p2p_region_bytes(int nranks) { return P2P_FLAGS_BYTES + (size_t)2 * nranks * P2P_CAP * 24; }
 
 void snk_comm_free(snk_db *db) {
     if (!db->comm) return;
     if (db->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(db->comm->comm);
     if (db->comm->d_nfail) cudaFree(db->comm->d_nfail);
+    for (int r = 0; r < db->comm->nranks && r < SNK_MAX_RANKS; ++r)
+        if (r != db->comm->rank && db->comm->peers[r]) cudaIpcCloseMemHandle(db->comm->peers[r]);
+    if (db->comm->region) cudaFree(db->comm->region);
+    if (db->comm->d_peers) cudaFree(db->comm->d_peers);
     delete db->comm;
     db->comm = nullptr;
 }
@@ -148,11 +167,86 @@ __global__ void best_of_ranks_kernel(const double *__restrict__ dist_all, const 
 // (distance, global row) per utterance and its bound on the rows outside its shortlist -> one grouped ncclAllGather
 // (n * 24 bytes per rank) -> arg-min over the ranks, written back in place, certificate flags cleared where the global
 // best is not below every bound.  Collective: every rank calls it with the same n.
+namespace {
+
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// The exchange step as ONE kernel over NVLink peer memory (one block): every thread stores its queries' (distance, row,
+// bound) into the slot this rank owns in EVERY rank's region (plain 8-byte stores to IPC-mapped addresses), a system-scope
+// fence and one release store per peer publish them under the step's epoch, then the block waits until every rank's epoch
+// has arrived in its own region and takes the arg-min / judges the certificate from local memory.  No NCCL launch, no
+// host involvement; two step parities because a fast rank may deliver step e + 1 while a slow one still reads step e
+// (it cannot deliver e + 2 before every rank has delivered e + 1, i.e. has finished reading e).
+__global__ void __launch_bounds__(1024) exchange_best_p2p_kernel(char *const *__restrict__ peers, int rank, int R, int n,
+                                                                 unsigned epoch, double *__restrict__ dist,
+                                                                 int64_t *__restrict__ ix, const double *__restrict__ bound,
+                                                                 int *__restrict__ flags, int *__restrict__ count) {
+    const size_t slot_bytes = (size_t)P2P_CAP * 24;
+    const size_t mine = P2P_FLAGS_BYTES + ((size_t)(epoch & 1u) * R + rank) * slot_bytes;
+    for (int b = threadIdx.x; b < n; b += blockDim.x) {
+        const double d = dist[b], lb = bound ? bound[b] : INFINITY;
+        const int64_t i = ix[b];
+        for (int r = 0; r < R; ++r) {
+            double *dst = reinterpret_cast<double *>(peers[r] + mine) + 3 * (size_t)b;
+            dst[0] = d;
+            reinterpret_cast<int64_t *>(dst)[1] = i;
+            dst[2] = lb;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < R) st_release_sys(reinterpret_cast<unsigned *>(peers[threadIdx.x]) + rank, epoch);
+    if (threadIdx.x < R) {
+        const unsigned *f = reinterpret_cast<const unsigned *>(peers[rank]) + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(f) - epoch) < 0)
+            if (clock64() - t0 > 20000000000LL) __trap();      // a peer that never arrives must not hang the GPU
+    }
+    __syncthreads();
+    const char *base = peers[rank] + P2P_FLAGS_BYTES + (size_t)(epoch & 1u) * R * slot_bytes;
+    for (int b = threadIdx.x; b < n; b += blockDim.x) {
+        const double *e0 = reinterpret_cast<const double *>(base) + 3 * (size_t)b;     // written by remote GPUs: read past L1
+        double bd = __ldcg(e0), lb = __ldcg(e0 + 2);
+        int64_t bi = __ldcg(reinterpret_cast<const long long *>(e0) + 1);
+        for (int r = 1; r < R; ++r) {
+            const double *e = reinterpret_cast<const double *>(base + r * slot_bytes) + 3 * (size_t)b;
+            const double d = __ldcg(e);
+            const int64_t i = __ldcg(reinterpret_cast<const long long *>(e) + 1);
+            if (d < bd || (d == bd && i < bi)) { bd = d; bi = i; }
+            lb = fmin(lb, __ldcg(e + 2));
+        }
+        dist[b] = bd;
+        ix[b] = bi;
+        if (!(bd <= lb)) {
+            if (flags[b]) atomicAdd(count, 1);
+            flags[b] = 0;
+        }
+    }
+}
+
+}  // namespace
+
 int snk_comm_exchange_best(snk_db *db, double *d_dist, int64_t *d_ix, double *d_bound, int n, int *d_flags, int *d_count,
                            cudaStream_t st) {
     snk_comm_state *c = db->comm;
     SNK_CHECK(c, "snk_comm_init has not been called");
     if (n <= 0) return 0;
+    if (c->p2p && c->nranks > 1 && n <= P2P_CAP) {
+        ++c->epoch;
+        snk_prof_scope prof(db, SNK_PROF_ALLGATHER, (double)n * 24 * (c->nranks - 1), st);
+        exchange_best_p2p_kernel<<<1, 1024, 0, st>>>(c->d_peers, c->rank, c->nranks, n, c->epoch, d_dist, d_ix, d_bound, d_flags,
+                                                     d_count);
+        SNK_CUDA(cudaGetLastError());
+        db->counters[2] += 1;
+        return 0;
+    }
     const size_t one = snk_round_up((size_t)n * 8 * c->nranks, 256);
     SNK_TRY(snk_buf_reserve(&db->ws_ag, 3 * one));
     double *rd = (double *)db->ws_ag.p;
@@ -212,8 +306,46 @@ int snk_comm_init(snk_db *db, const void *unique_id, int rank, int nranks) {
     memcpy(&id, unique_id, sizeof(id));
     SNK_NCCL(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
     SNK_CUDA(cudaMalloc((void **)&c->d_nfail, 8));
+    // Peer-memory exchange region (sharded greedy): allocate, publish the IPC handle through the communicator, map the
+    // peers'.  Every step below that can fail on a given platform (no IPC between the processes, more ranks than the table
+    // holds) only switches the exchange to the NCCL path -- on ALL ranks, agreed by an all-reduce.
+    int ok = nranks > 1 && nranks <= SNK_MAX_RANKS && !getenv("SNK_COMM_NO_P2P");
+    cudaIpcMemHandle_t *d_handles = nullptr;
+    std::vector<cudaIpcMemHandle_t> handles((size_t)nranks);
+    if (nranks > 1) {
+        const size_t bytes = p2p_region_bytes(nranks);
+        if (ok && cudaMalloc((void **)&c->region, bytes) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+        if (ok) SNK_CUDA(cudaMemset(c->region, 0, bytes));
+        cudaIpcMemHandle_t mine;
+        memset(&mine, 0, sizeof(mine));
+        if (ok && cudaIpcGetMemHandle(&mine, c->region) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+        SNK_CUDA(cudaMalloc((void **)&d_handles, sizeof(cudaIpcMemHandle_t) * (size_t)(nranks + 1)));
+        SNK_CUDA(cudaMemcpy(d_handles + nranks, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+        SNK_NCCL(g_nccl.AllGather(d_handles + nranks, d_handles, sizeof(mine), ncclInt8, c->comm, db->stream));
+        SNK_CUDA(cudaStreamSynchronize(db->stream));
+        SNK_CUDA(cudaMemcpy(handles.data(), d_handles, sizeof(mine) * (size_t)nranks, cudaMemcpyDeviceToHost));
+        for (int r = 0; r < nranks && ok; ++r) {
+            if (r == rank) { c->peers[r] = c->region; continue; }
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, handles[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+            c->peers[r] = (char *)ptr;
+        }
+        // all or none
+        SNK_CUDA(cudaMemcpy(c->d_nfail, &ok, 4, cudaMemcpyHostToDevice));
+        SNK_NCCL(g_nccl.AllReduce(c->d_nfail, c->d_nfail, 1, ncclInt32, ncclMin, c->comm, db->stream));
+        SNK_CUDA(cudaStreamSynchronize(db->stream));
+        SNK_CUDA(cudaMemcpy(&ok, c->d_nfail, 4, cudaMemcpyDeviceToHost));
+        cudaFree(d_handles);
+        if (ok) {
+            SNK_CUDA(cudaMalloc((void **)&c->d_peers, sizeof(char *) * SNK_MAX_RANKS));
+            SNK_CUDA(cudaMemcpy(c->d_peers, c->peers, sizeof(char *) * SNK_MAX_RANKS, cudaMemcpyHostToDevice));
+        }
+    }
+    c->p2p = ok != 0;
     return 0;
 }
+
+int snk_comm_peer_exchange(const snk_db *db) { return db && db->comm && db->comm->p2p ? 1 : 0; }
 
 int snk_comm_info(snk_db *db, int *rank, int *nranks, int *nccl_version) {
     SNK_CHECK(db && db->comm, "snk_comm_init has not been called");

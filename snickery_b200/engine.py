@@ -65,6 +65,7 @@ def load_library(path=None):
         "snk_greedy_batch_finish": [vp],
         "snk_comm_unique_id": [vp, i32],
         "snk_comm_init": [vp, vp, i32, i32],
+        "snk_comm_peer_exchange": [vp],
         "snk_comm_info": [vp, P(i32), P(i32), P(i32)],
         "snk_knn_sharded_dev": [vp, i32, vp, i64, i32, vp, vp, i64, vp],
         "snk_knn_sharded_finish": [vp],
@@ -104,7 +105,7 @@ EXPORTED_SYMBOLS = ["snk_last_error", "snk_version", "snk_device_count", "snk_db
                     "snk_db_info", "snk_db_set_weights", "snk_db_set_engine", "snk_db_counters", "snk_db_profile_enable",
                     "snk_db_profile_read", "snk_knn",
                     "snk_knn_dev", "snk_knn_finish", "snk_debug_tc_keys", "snk_topk_merge_dev", "snk_comm_unique_id", "snk_comm_init",
-                    "snk_comm_info", "snk_knn_sharded_dev", "snk_knn_sharded_finish", "snk_greedy_batch",
+                    "snk_comm_info", "snk_comm_peer_exchange", "snk_knn_sharded_dev", "snk_knn_sharded_finish", "snk_greedy_batch",
                     "snk_greedy_batch_dev", "snk_greedy_batch_finish", "snk_greedy_sharded_batch_dev",
                     "snk_db_set_standardisation", "snk_prepare_targets", "snk_halfphone_targets",
                     "snk_halfphone_targets_dev", "snk_greedy_batch_unnorm",
@@ -242,7 +243,8 @@ class UnitDatabase:
     def comm_info(self):
         r, n, v = C.c_int(), C.c_int(), C.c_int()
         _check(load_library().snk_comm_info(self._h, C.byref(r), C.byref(n), C.byref(v)))
-        return {"rank": r.value, "nranks": n.value, "nccl_version": v.value}
+        return {"rank": r.value, "nranks": n.value, "nccl_version": v.value,
+                "peer_exchange": bool(load_library().snk_comm_peer_exchange(self._h))}
 
     def knn_sharded_dev(self, q_ptr, nq, k, dist_ptr, idx_ptr, space=SPACE_TARGET, id_offset=0, stream=0):
         _check(load_library().snk_knn_sharded_dev(self._h, space, C.c_void_p(q_ptr), int(nq), int(k), C.c_void_p(dist_ptr),
