@@ -103,6 +103,11 @@ int snk_db_profile_read(snk_db *db, int which, double *total_ms, int64_t *launch
  * operands and checks the measured error against eps_rel (||x~||^2 + 2 maxnorm).           */
 int snk_debug_tc_keys(snk_db *db, int space, const double *Q, int64_t nq, int64_t row0, int64_t nrows,
                       float *keys, float *qnorm, float *eps_rel, float *maxnorm);
+/* The same for the single-utterance greedy kernel (greedy_one.cu, mma.sync keys): keys [N'] of the FIRST step of an
+ * utterance whose first window is targets [multiepoch, Dt] (weighted float64, host) after start_state (-1: none);
+ * *qnorm = the fp32 ||x~||^2 of that query.                                                     */
+int snk_debug_greedy_one_keys(snk_db *db, const double *targets, int64_t start_state, float *keys, float *qnorm,
+                              float *eps_rel, float *maxnorm);
 
 /* ---- k-NN: tree.query(X, k) ------------------------------------------------------------
  * Replaces cKDTree.query / sklearn KDTree.query (synth_halfphone.py:1364,1384;

@@ -20,7 +20,7 @@ OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libsnk_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 SOURCES = ["api.cu", "weights.cu", "knn_simt.cu", "knn_tc.cu", "rerank.cu", "search.cu", "join_viterbi.cu", "scores.cu",
-           "concat.cu", "comm.cu", "join_tc.cu"]
+           "concat.cu", "comm.cu", "join_tc.cu", "greedy_one.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

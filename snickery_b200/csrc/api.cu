@@ -185,7 +185,7 @@ int snk_db_destroy(snk_db *db) {
     cudaFree(db->nrm_t16); cudaFree(db->nrm_j16); cudaFree(db->err_t16);
     snk_buf *bufs[] = {&db->ws_q, &db->ws_dist, &db->ws_list, &db->ws_misc, &db->ws_io, &db->ws_io2, &db->ws_tiles,
                        &db->ws_bp, &db->ws_tc, &db->ws_h0, &db->ws_h1, &db->ws_h2, &db->ws_h3, &db->ws_flags,
-                       &db->ws_kflags, &db->ws_meta, &db->ws_ag, &db->ws_jv};
+                       &db->ws_kflags, &db->ws_meta, &db->ws_ag, &db->ws_jv, &db->ws_g1};
     for (snk_buf *b : bufs) snk_buf_free(b);
     if (db->ev) cudaEventDestroy(db->ev);
     for (cudaEvent_t e : db->upload_events) cudaEventDestroy(e);

@@ -5,7 +5,7 @@
 // greedy batch    : Synthesiser.greedy_joint_search (reference script/synth_simple.py:458-503)
 //                   for B utterances at once; the chain over time steps stays sequential, the
 //                   B queries of one step form one batched search over the whole database.
-#include "common.cuh"
+#include "greedy_dev.cuh"
 #include <algorithm>
 #include <vector>
 
@@ -49,15 +49,6 @@ __global__ void cvt_q32_kernel(const double *__restrict__ Q, int D, int64_t nq, 
 // One block of CVT_THREADS per (padded) query row: a row is only ~600 columns, so a warp per row would
 // walk it in ~18 dependent gathers; four warps finish in five.
 constexpr int CVT_THREADS = 128;
-// one query value -> fp16 operand element; accumulates the squared rounded value and the squared rounding error
-__device__ __forceinline__ __half cvt_element(double x, float &n2, float &e2) {
-    const __half h = __double2half(x);
-    const float hf = __half2float(h);
-    n2 = fmaf(hf, hf, n2);
-    const float df = (float)(x - (double)hf);
-    e2 = fmaf(df, df, e2);
-    return h;
-}
 // block-wide sums of (n2, e2); thread 0 returns them.  Ends with a barrier so `red` can be reused at once.
 __device__ __forceinline__ void cvt_reduce(float &n2, float &e2, float (&red)[2][CVT_THREADS / 32]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -133,7 +124,6 @@ int search_simt(snk_db *db, const snk_space &sp, const double *dQ, int64_t nq, c
 
 // A greedy step hands the search a recipe for its queries instead of finished rows (greedy_src, below): the
 // tensor-core path then builds, converts and norms every row in ONE kernel; other paths assemble first.
-namespace { struct greedy_src; }
 static int greedy_launch_assemble(snk_db *db, const greedy_src *gs, int nact, double *Q, cudaStream_t st);
 static int greedy_launch_assemble_cvt(snk_db *db, const greedy_src *gs, int64_t nq, int64_t qpad, int D, const short *qmap,
                                       int ld16, double *Q, __half *q16, float *qn, float *qerr, cudaStream_t st);
@@ -261,37 +251,6 @@ extern "C" int snk_debug_tc_keys(snk_db *db, int space, const double *Q, int64_t
 // greedy joint search
 namespace {
 
-struct greedy_meta {
-    int64_t tgt_off;    // first frame of the utterance in the concatenated targets
-    int64_t path_off;   // first step of the utterance in the concatenated paths
-    int64_t nsteps;
-    int64_t start_state;
-};
-
-// standardise() then weight() of one un-normalised target value, in the reference's float64 arithmetic
-// (data_manipulation.py:162-186: (x - mean) / std, unvoiced marker -> std * -1.0 * uv_scaling_factor;
-// speech_manip.py:209-213: * weight).  x is the float32 value compose_speech produced.
-// f32: the statistics are float32 (as read from the voice file, train_simple.py:94-97) and numpy keeps the
-// whole standardisation in float32; otherwise float64 statistics promote it to float64.
-struct std_params {
-    const double *mean, *sd, *w;
-    double uv_special, uv_scale;
-    int f32;
-};
-__device__ __forceinline__ double standardise_weight(float x, int c, const std_params &sp) {
-    double v;
-    if (sp.f32) {
-        const float sd = (float)sp.sd[c];
-        v = (double)(x == (float)sp.uv_special ? __fmul_rn(__fmul_rn(sd, -1.0f), (float)sp.uv_scale)
-                                               : __fdiv_rn(__fsub_rn(x, (float)sp.mean[c]), sd));
-    } else {
-        const double sd = sp.sd[c];
-        v = (double)x == sp.uv_special ? __dmul_rn(__dmul_rn(sd, -1.0), sp.uv_scale)
-                                       : __ddiv_rn(__dsub_rn((double)x, sp.mean[c]), sd);
-    }
-    return __dmul_rn(v, sp.w[c]);
-}
-
 __global__ void prepare_targets_kernel(const float *__restrict__ x, int64_t total, int Dt, std_params sp,
                                        double *__restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
@@ -315,51 +274,6 @@ __global__ void halfphone_targets_kernel(const float *__restrict__ x, int64_t fr
         if (f < 0) f += frames;                      // numpy's negative indexing
         out[i] = (f >= 0 && f < frames) ? standardise_weight(x[f * dim + col % dim], col, sp) : NAN;
     }
-}
-
-// Query b of step t = [ prev_join_vector || m consecutive target frames ]   (synth_simple.py:467-470,488,501).
-// The recipe: where the previous choices and the target frames are, and where finished steps go.
-// targets: weighted float64 frames, or (targets32 != nullptr) un-normalised float32 frames that are
-// standardised and weighted on the fly (synth_simple.py:371-391).
-struct greedy_src {
-    const greedy_meta *meta;
-    int nact_prev;
-    int64_t t;
-    const double *targets;
-    const float *targets32;
-    std_params stp;
-    int Dt, m;
-    const float *Jc_raw;
-    const double *wj;
-    int Dj, Djq, prev_row_off, prev_col, cur_row_off, cur_col;
-    const int64_t *ix_prev;
-    const double *dist_prev;
-    int64_t *paths;
-    double *step_dist;
-};
-
-// the previous step's result of utterance b goes to its place in the output path
-__device__ __forceinline__ void greedy_scatter(const greedy_src &g, const greedy_meta &mt, int64_t b) {
-    if (g.t > 0 && b < g.nact_prev) {
-        g.paths[mt.path_off + g.t - 1] = g.ix_prev[b];
-        if (g.step_dist) g.step_dist[mt.path_off + g.t - 1] = g.dist_prev[b];
-    }
-}
-// row / column of the join vector that precedes step t of utterance b (row < 0: none, zeros)
-__device__ __forceinline__ void greedy_prev(const greedy_src &g, const greedy_meta &mt, int64_t b, int64_t &row, int &col) {
-    row = -1;
-    col = 0;
-    if (g.t == 0) {
-        if (mt.start_state >= 0) { row = mt.start_state + g.prev_row_off; col = g.prev_col; }
-    } else {
-        row = g.ix_prev[b] + g.cur_row_off;
-        col = g.cur_col;
-    }
-}
-__device__ __forceinline__ double greedy_value(const greedy_src &g, const greedy_meta &mt, int64_t row, int col, int d) {
-    if (d < g.Djq) return row >= 0 ? (double)g.Jc_raw[row * g.Dj + col + d] * g.wj[col + d] : 0.0;
-    const int64_t i = (mt.tgt_off + g.t * g.m) * g.Dt + (d - g.Djq);
-    return g.targets32 ? standardise_weight(g.targets32[i], (d - g.Djq) % g.Dt, g.stp) : g.targets[i];
 }
 
 // float64 query rows only (SIMT engine, table-free paths, the last scatter-only step)
@@ -447,6 +361,11 @@ int greedy_run(snk_db *db, const std::vector<greedy_meta> &meta, const double *d
                int64_t *d_paths, double *d_step_dist, int *d_flags, int *d_count, cudaStream_t st,
                const greedy_shard *sh = nullptr) {
     const int B = (int)meta.size();
+    if (B == 1 && !sh && snk_greedy_one_supported(db)) {
+        // one utterance: the whole chain is one persistent kernel (greedy_one.cu); all its frames must have landed
+        for (auto &w : db->step_waits) SNK_CUDA(cudaStreamWaitEvent(st, w.second, 0));
+        return snk_greedy_one_launch(db, &meta[0], d_targets, d_unnorm, d_paths, d_step_dist, d_flags, d_count, nullptr, st);
+    }
     const std_params stp{db->std_mean, db->std_sd, db->wt, db->uv_special, db->uv_scale, db->std_f32};
     const int m = db->m;
     const snk_space sp = snk_make_space(db, SNK_SPACE_JOINT);
@@ -780,5 +699,6 @@ extern "C" int snk_greedy_batch_finish(snk_db *db) {
         ps->pool.push_back(job.fb);
     }
     ps->greedy.clear();
+    snk_greedy_one_release_l2(db);
     return rc;
 }

@@ -62,6 +62,7 @@ def load_library(path=None):
         "snk_topk_merge_dev": [i32, vp, vp, i32, i64, i32, vp, vp, vp],
         "snk_knn_finish": [vp],
         "snk_debug_tc_keys": [vp, i32, P(dbl), i64, i64, i64, P(flt), P(flt), P(flt), P(flt)],
+        "snk_debug_greedy_one_keys": [vp, P(dbl), i64, P(flt), P(flt), P(flt), P(flt)],
         "snk_greedy_batch_finish": [vp],
         "snk_comm_unique_id": [vp, i32],
         "snk_comm_init": [vp, vp, i32, i32],
@@ -104,7 +105,7 @@ STD_FLOAT32 = 1
 EXPORTED_SYMBOLS = ["snk_last_error", "snk_version", "snk_device_count", "snk_db_create", "snk_db_destroy",
                     "snk_db_info", "snk_db_set_weights", "snk_db_set_engine", "snk_db_counters", "snk_db_profile_enable",
                     "snk_db_profile_read", "snk_knn",
-                    "snk_knn_dev", "snk_knn_finish", "snk_debug_tc_keys", "snk_topk_merge_dev", "snk_comm_unique_id", "snk_comm_init",
+                    "snk_knn_dev", "snk_knn_finish", "snk_debug_tc_keys", "snk_debug_greedy_one_keys", "snk_topk_merge_dev", "snk_comm_unique_id", "snk_comm_init",
                     "snk_comm_info", "snk_comm_peer_exchange", "snk_knn_sharded_dev", "snk_knn_sharded_finish", "snk_greedy_batch",
                     "snk_greedy_batch_dev", "snk_greedy_batch_finish", "snk_greedy_sharded_batch_dev",
                     "snk_db_set_standardisation", "snk_prepare_targets", "snk_halfphone_targets",
@@ -262,6 +263,18 @@ class UnitDatabase:
         _check(load_library().snk_debug_tc_keys(self._h, space, _ptr(Q, C.c_double), Q.shape[0], int(row0), int(nrows),
                                                 _ptr(keys, C.c_float), _ptr(qn, C.c_float), C.byref(eps), C.byref(mx)))
         return keys, qn, eps.value, mx.value
+
+    def debug_greedy_one_keys(self, window, start_state=-1):
+        """Keys [N'] of the single-utterance greedy kernel for the first step of an utterance starting with `window`
+        [multiepoch, Dt] (weighted float64) + the query norm, slack and max row norm (test instrumentation)."""
+        window = np.ascontiguousarray(window, dtype=np.float64)
+        if window.shape != (self.multiepoch, self.Dt):
+            raise ValueError("window must be [%d, %d], got %s" % (self.multiepoch, self.Dt, window.shape))
+        keys = np.empty(self.Nprime, dtype=np.float32)
+        qn, eps, mx = C.c_float(), C.c_float(), C.c_float()
+        _check(load_library().snk_debug_greedy_one_keys(self._h, _ptr(window, C.c_double), int(start_state), _ptr(keys, C.c_float),
+                                                        C.byref(qn), C.byref(eps), C.byref(mx)))
+        return keys, qn.value, eps.value, mx.value
 
     # -- searches (host arrays in, host arrays out)
     def knn(self, Q, k, space=SPACE_TARGET):
