@@ -130,10 +130,6 @@ struct snk_db {
     snk_comm_state *comm = nullptr;
     snk_pending_state *pending = nullptr;
     snk_acoustic_job *acoustic = nullptr;
-    // greedy_one.cu: persisting-L2 window over the frame operand rows (0: not sized yet, 1: in use, -1: unavailable)
-    int g1_l2_state = 0;
-    size_t g1_l2_bytes = 0, g1_l2_window = 0;
-    bool g1_l2_dirty = false;
     int64_t counters[4] = {0, 0, 0, 0};
     // optional kernel timing (snk_db_profile_*)
     bool prof_on = false;
@@ -258,7 +254,6 @@ int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, d
                    cudaStream_t st);
 // ---- greedy_one.cu : one utterance as one persistent kernel (meta: the utterance's greedy_meta, greedy_dev.cuh)
 bool snk_greedy_one_supported(const snk_db *db);
-void snk_greedy_one_release_l2(snk_db *db);
 int snk_greedy_one_launch(snk_db *db, const void *meta, const double *d_targets, const float *d_unnorm, int64_t *d_paths,
                           double *d_step_dist, int *d_flags, int *d_count, float *d_keys, cudaStream_t st);
 // enqueue a search with deferred certificates; snk_knn_finish(db) completes it (see search.cu)

@@ -7,19 +7,26 @@
 // path (search.cu) spends three launches per step and multiplies a 128-row tcgen05 query tile that holds one query; here one
 // cooperative launch runs the whole utterance, one CTA per SM:
 //
-//   per step   scan      every warp walks 16-row groups of its CTA's row slice; the keys ||y~||^2 - 2 x~.y~ come from
-//                        mma.sync.m16n8k16 (fp16 x fp16 -> fp32; database rows are the M dimension, the query is column 0 of
-//                        the N dimension) on the SAME operand rows, embedded norm pieces included, as the tcgen05 kernel, so
-//                        the certificate's error model (34 K = 16 steps, knn_tc.cu::snk_tc_eps_rel) carries over.  Operand
-//                        rows go from global memory straight into the A fragments: the K order of a dot product is free, so
-//                        lane (g, t) takes the 16 bytes at offset 16 t of each 64-byte chunk of row g / g + 8 and the query
-//                        fragment is permuted to match.  The join part is prefetched one group ahead (L1 bypassed), the m
-//                        frame blocks of a window hit L1 after the first.  Two smallest keys per thread.
+//   per step   scan      every warp walks a contiguous run of 16-row tiles of its CTA's row slice.  The keys
+//                        ||y~||^2 - 2 x~.y~ come from mma.sync.m16n8k16 (fp16 x fp16 -> fp32, database rows are the M dimension)
+//                        on the SAME operand rows, embedded norm pieces included, as the tcgen05 kernel: 34 K = 16 steps per
+//                        key, so the certificate's error model (knn_tc.cu::snk_tc_eps_rel) carries over.  Operand rows go
+//                        from global memory straight into the A fragments: the K order of a dot product is free, so lane
+//                        (g, t) takes the 16 bytes at offset 16 t of each 64-byte chunk of row g / g + 8 and the query
+//                        fragment is permuted to match.  The N dimension carries the m frames of the query window: one pass
+//                        over a frame row yields its products with all m window positions, and a row's key is the join
+//                        product plus a diagonal sum over m consecutive frame rows (shuffles).  That is what makes the
+//                        scan HBM-bound: reading every frame row m times (from L1) left it bound by L1 wavefronts -- eight
+//                        128-byte lines per load instruction -- at 0.74 of the HBM rate (ncu, profiles/).
+//                        Join rows are requested one tile ahead (L1 bypassed), frame rows two.  Two smallest keys per thread.
 //              merge     per CTA the 8 smallest of its threads' lists + tau (no dropped row has a smaller key) -> global.
-//              barrier   one grid-wide arrive/wait (monotonic counter, system of two list parities).
-//              re-rank   EVERY CTA merges the CTA lists, recomputes the 16 best rows in the reference's float64 arithmetic
-//                        (rerank_dev.cuh), judges the certificate and assembles the next query from the chosen row -- the
-//                        same deterministic code on the same data, so no second barrier and no broadcast is needed.
+//              barrier   one grid-wide arrive/wait (monotonic counter, two list parities); meanwhile the frame part of the
+//                        next query, which does not depend on this step's answer, is assembled.
+//              re-rank   EVERY CTA merges the CTA lists (a list whose head is not among the 16 smallest heads holds none of
+//                        the 16 smallest entries), recomputes the 16 best rows in the reference's float64 arithmetic
+//                        (rerank_dev.cuh; one row per warp, all loads of a row in flight at once), judges the certificate
+//                        and assembles the join part of the next query from the chosen row -- the same deterministic code
+//                        on the same data, so no second barrier and no broadcast is needed.
 //
 // An uncertified step clears the utterance's flag; snk_greedy_batch_finish then repeats the utterance with the next
 // engine of the chain, exactly as for a batch.
@@ -135,7 +142,6 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
 
 template <int M, int NCS, int NCG>
 __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_params p) {
-    constexpr int NCH = NCS + M * NCG;
     extern __shared__ __align__(16) unsigned char g1_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
@@ -160,6 +166,7 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
     short *qmap_s = reinterpret_cast<short *>(q16_s + p.ld16 + 8);  // [ld16]; q16_s[ld16 .. ld16 + 8) stays zero
     __shared__ int64_t s_ix;
     __shared__ float s_qn, s_qerr;
+    __shared__ double s_best;
     __shared__ int s_sel[G1_KP];
 
     for (int d = tid; d < rs.dA; d += G1_THREADS) wA_s[d] = rs.wA[rs.a_col + d];
@@ -218,93 +225,118 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
     finish_query();
 
     const int64_t grp_lo = (int64_t)cta * p.groups_per_cta, grp_hi = min(p.ngroups, grp_lo + p.groups_per_cta);
-    const int64_t last = p.Np - 1;
+    const int64_t last = p.Np - 1, glast = p.Np + M - 2;      // last searchable row, last frame row
+    // the warp's run of tiles: the CTA's slice in NW nearly equal parts
+    const int64_t cta_groups = max((int64_t)0, grp_hi - grp_lo), w_base = cta_groups / G1_NW, w_rem = cta_groups % G1_NW;
+    const int64_t w_lo = grp_lo + warp * w_base + min((int64_t)warp, w_rem), w_hi = w_lo + w_base + (warp < w_rem ? 1 : 0);
     const uint4 *S4 = reinterpret_cast<const uint4 *>(p.S16) + t4, *G4 = reinterpret_cast<const uint4 *>(p.G16) + t4;
 
     for (int64_t step = 0; step < nsteps; ++step) {
         const int par = (int)(step & 1);
         const double *q_cur = q_s + par * rs.D;
         double *q_nxt = q_s + (par ^ 1) * rs.D;
-        // ---- scan.  Every lane reads the query halves of its K slice (all eight N columns of the mma then hold the same
-        // dot product; column 0 is the one that is read back), at compile-time offsets from one base address.
-        const unsigned q_base = (unsigned)__cvta_generic_to_shared(q16_s + 8 * t4);
-        auto q_off = [](int c) { return 2u * (unsigned)(c < NCS ? 32 * c : LDS_H + ((c - NCS) / NCG) * LDG_H + ((c - NCS) % NCG) * 32); };
+        // ---- scan.  A warp walks a contiguous run of 16-row tiles.  Per tile k:
+        //   J(k)   = join part, NCS chunks: every N column of the mma carries the same query, column 0 is read back;
+        //   C(k+1) = frame products of the NEXT tile, NCG chunks: N column j carries frame j of the query window, so ONE pass
+        //            over a frame row yields its products with all m window positions (C[f][j] = G[f] . x_j), instead of m
+        //            passes over the row;
+        //   key(u) = -2 (J[u] + sum_j C[u + j][j]): the diagonal sum takes rows of tile k and the first m - 1 rows of
+        //            tile k + 1 from the lanes that hold them (shuffles), then the four lanes of a row add their columns.
+        const unsigned qj_base = (unsigned)__cvta_generic_to_shared(q16_s + 8 * t4);
+        const unsigned qt_base = (unsigned)__cvta_generic_to_shared(q16_s + LDS_H + min(g, M - 1) * LDG_H + 8 * t4);
         float k0 = INFINITY, k1 = INFINITY;
         int i0 = -1, i1 = -1;
-        // operand rows in 16-byte units: row pitch LDS_H / 8 (join contexts), LDG_H / 8 (frames), 4 units per 32-column chunk
-        uint4 sA[NCS], sB[NCS], pA[NCG], pB[NCG];
-        const uint4 *ga = G4, *gb = G4;
-        int64_t grp = grp_lo + warp;
-        if (grp < grp_hi) {
-            const int64_t ra = min(grp * 16 + g, last), rb = min(grp * 16 + g + 8, last);
-            const uint4 *sa = S4 + ra * (LDS_H / 8), *sb = S4 + rb * (LDS_H / 8);
-            ga = G4 + ra * (LDG_H / 8);
-            gb = G4 + rb * (LDG_H / 8);
+        if (w_lo < w_hi) {
+            // operand rows in 16-byte units: row pitch LDS_H / 8 (join contexts), LDG_H / 8 (frames), 4 units per 32-column chunk
+            uint4 sA[NCS], sB[NCS], gA[NCG], gB[NCG];
+            float cp[4];          // C(k): (row g, column 2 t4), (row g, 2 t4 + 1), (row g + 8, 2 t4), (row g + 8, 2 t4 + 1)
+            {
+                const int64_t ra = min(w_lo * 16 + g, last), rb = min(w_lo * 16 + g + 8, last);
+                const uint4 *sa = S4 + ra * (LDS_H / 8), *sb = S4 + rb * (LDS_H / 8);
+                const uint4 *ga = G4 + min(w_lo * 16 + g, glast) * (LDG_H / 8), *gb = G4 + min(w_lo * 16 + g + 8, glast) * (LDG_H / 8);
 #pragma unroll
-            for (int c = 0; c < NCS; ++c) { sA[c] = ld_stream(sa + 4 * c); sB[c] = ld_stream(sb + 4 * c); }
+                for (int c = 0; c < NCS; ++c) { sA[c] = ld_stream(sa + 4 * c); sB[c] = ld_stream(sb + 4 * c); }
 #pragma unroll
-            for (int h = 0; h < NCG; ++h) { pA[h] = ld_keep(ga + 4 * h); pB[h] = ld_keep(gb + 4 * h); }
-        }
-        for (; grp < grp_hi; grp += G1_NW) {
-            // the rows requested while this group is multiplied: the warp's next group (after the last one: this group again,
-            // whose rows are in cache -- no branch around the loads)
-            const int64_t nxt = grp + G1_NW < grp_hi ? grp + G1_NW : grp;
-            const int64_t na = min(nxt * 16 + g, last), nb = min(nxt * 16 + g + 8, last);
-            const uint4 *nsa = S4 + na * (LDS_H / 8), *nsb = S4 + nb * (LDS_H / 8);
-            const uint4 *nga = G4 + na * (LDG_H / 8), *ngb = G4 + nb * (LDG_H / 8);
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            uint4 xA[NCG], xB[NCG], yA[NCG], yB[NCG];
-            if (M > 1) {
+                for (int h = 0; h < NCG; ++h) { gA[h] = ld_keep(ga + 4 * h); gB[h] = ld_keep(gb + 4 * h); }
+                cp[0] = cp[1] = cp[2] = cp[3] = 0.f;
+                const int64_t na = min(w_lo * 16 + 16 + g, glast), nb = min(w_lo * 16 + 24 + g, glast);
+                const uint4 *nga = G4 + na * (LDG_H / 8), *ngb = G4 + nb * (LDG_H / 8);
 #pragma unroll
-                for (int h = 0; h < NCG; ++h) { xA[h] = ld_keep(ga + (LDG_H / 8) + 4 * h); xB[h] = ld_keep(gb + (LDG_H / 8) + 4 * h); }
+                for (int h = 0; h < NCG; ++h) {
+                    chunk_mma(cp, gA[h], gB[h], ld_query(qt_base + 64 * h));
+                    gA[h] = ld_keep(nga + 4 * h);
+                    gB[h] = ld_keep(ngb + 4 * h);
+                }
             }
-            uint4 qc = ld_query(q_base + q_off(0));
+            // shuffle sources of the diagonal sum: the lane that holds row g + j (mod 8) in the same column pair
+            const int j0 = 2 * t4, j1 = 2 * t4 + 1;
+            const int src0 = (((g + j0) & 7) << 2) | t4, src1 = (((g + j1) & 7) << 2) | t4;
+            const bool lo0 = g + j0 < 8, lo1 = g + j1 < 8, on0 = j0 < M, on1 = j1 < M;
+            for (int64_t grp = w_lo; grp < w_hi; ++grp) {
+                // requested while this tile is multiplied: join rows of tile k + 1 (after the last tile: this one again,
+                // in cache -- no branch around the loads), frame rows of tile k + 2
+                const int64_t nxt = grp + 1 < w_hi ? grp + 1 : grp;
+                const int64_t na = min(nxt * 16 + g, last), nb = min(nxt * 16 + g + 8, last);
+                const uint4 *nsa = S4 + na * (LDS_H / 8), *nsb = S4 + nb * (LDS_H / 8);
+                const int64_t fa = min(grp * 16 + 32 + g, glast), fb = min(grp * 16 + 40 + g, glast);
+                const uint4 *nga = G4 + fa * (LDG_H / 8), *ngb = G4 + fb * (LDG_H / 8);
+                float cn[4] = {0.f, 0.f, 0.f, 0.f}, cj[4] = {0.f, 0.f, 0.f, 0.f};
+                uint4 qc = ld_query(qt_base);
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                uint4 qn = qc;
-                if (c + 1 < NCH) qn = ld_query(q_base + q_off(c + 1));
-                if (c < NCS) {
-                    chunk_mma(acc, sA[c], sB[c], qc);
+                for (int h = 0; h < NCG; ++h) {
+                    uint4 qn = qc;
+                    if (h + 1 < NCG) qn = ld_query(qt_base + 64 * (h + 1));
+                    else qn = ld_query(qj_base);
+                    chunk_mma(cn, gA[h], gB[h], qc);
+                    gA[h] = ld_keep(nga + 4 * h);
+                    gB[h] = ld_keep(ngb + 4 * h);
+                    qc = qn;
+                }
+#pragma unroll
+                for (int c = 0; c < NCS; ++c) {
+                    uint4 qn = qc;
+                    if (c + 1 < NCS) qn = ld_query(qj_base + 64 * (c + 1));
+                    chunk_mma(cj, sA[c], sB[c], qc);
                     sA[c] = ld_stream(nsa + 4 * c);
                     sB[c] = ld_stream(nsb + 4 * c);
-                } else {
-                    const int j = (c - NCS) / NCG, h = (c - NCS) % NCG;
-                    if (j == 0) {
-                        chunk_mma(acc, pA[h], pB[h], qc);
-                        pA[h] = ld_keep(nga + 4 * h);
-                        pB[h] = ld_keep(ngb + 4 * h);
-                    } else {
-                        if (h == 0 && j + 1 < M) {       // the next frame block is requested before this one is multiplied
+                    qc = qn;
+                }
+                // diagonal sum.  Row g + j sits in the row-g half of C(k) while g + j < 8, else in its row-(g + 8) half; row
+                // g + 8 + j in the row-(g + 8) half of C(k) while g + j < 8, else in the row-g half of C(k + 1).
+                float ta, tb;
+                {
+                    const float a0 = __shfl_sync(0xffffffffu, cp[0], src0), b0 = __shfl_sync(0xffffffffu, cp[2], src0),
+                                n0 = __shfl_sync(0xffffffffu, cn[0], src0);
+                    const float a1 = __shfl_sync(0xffffffffu, cp[1], src1), b1 = __shfl_sync(0xffffffffu, cp[3], src1),
+                                n1 = __shfl_sync(0xffffffffu, cn[1], src1);
+                    const float ea = on0 ? (lo0 ? a0 : b0) : 0.f, eb = on0 ? (lo0 ? b0 : n0) : 0.f;
+                    const float oa = on1 ? (lo1 ? a1 : b1) : 0.f, ob = on1 ? (lo1 ? b1 : n1) : 0.f;
+                    ta = ea + oa;
+                    tb = eb + ob;
+                    ta += __shfl_xor_sync(0xffffffffu, ta, 1);
+                    tb += __shfl_xor_sync(0xffffffffu, tb, 1);
+                    ta += __shfl_xor_sync(0xffffffffu, ta, 2);
+                    tb += __shfl_xor_sync(0xffffffffu, tb, 2);
+                }
 #pragma unroll
-                            for (int hh = 0; hh < NCG; ++hh) {
-                                if (j & 1) { yA[hh] = ld_keep(ga + (j + 1) * (LDG_H / 8) + 4 * hh); yB[hh] = ld_keep(gb + (j + 1) * (LDG_H / 8) + 4 * hh); }
-                                else { xA[hh] = ld_keep(ga + (j + 1) * (LDG_H / 8) + 4 * hh); xB[hh] = ld_keep(gb + (j + 1) * (LDG_H / 8) + 4 * hh); }
-                            }
-                        }
-                        if (j & 1) chunk_mma(acc, xA[h], xB[h], qc);
-                        else chunk_mma(acc, yA[h], yB[h], qc);
+                for (int i = 0; i < 4; ++i) cp[i] = cn[i];
+                if (t4 == 0) {
+                    // key = ||y~||^2 - 2 x~.y~ = -2 * accumulator (the norms ride in the operand rows)
+                    const int64_t r0 = grp * 16 + g, r1 = r0 + 8;
+                    const float ka = r0 <= last ? -2.f * (cj[0] + ta) : INFINITY, kb = r1 <= last ? -2.f * (cj[2] + tb) : INFINITY;
+                    if (p.dbg_keys && step == 0) {
+                        if (cta == 0 && tid == 0) p.dbg_keys[p.Np] = s_qn;
+                        if (r0 <= last) p.dbg_keys[r0] = ka;
+                        if (r1 <= last) p.dbg_keys[r1] = kb;
                     }
-                }
-                qc = qn;
-            }
-            ga = nga;
-            gb = ngb;
-            if (t4 == 0) {
-                // key = ||y~||^2 - 2 x~.y~ = -2 * accumulator (the norm rides in the operands)
-                const int64_t r0 = grp * 16 + g, r1 = r0 + 8;
-                const float ka = r0 <= last ? -2.f * acc[0] : INFINITY, kb = r1 <= last ? -2.f * acc[2] : INFINITY;
-                if (p.dbg_keys && step == 0) {
-                    if (cta == 0 && tid == 0) p.dbg_keys[p.Np] = s_qn;
-                    if (r0 <= last) p.dbg_keys[r0] = ka;
-                    if (r1 <= last) p.dbg_keys[r1] = kb;
-                }
-                if (ka < k1) {
-                    if (ka < k0) { k1 = k0; i1 = i0; k0 = ka; i0 = (int)r0; }
-                    else { k1 = ka; i1 = (int)r0; }
-                }
-                if (kb < k1) {
-                    if (kb < k0) { k1 = k0; i1 = i0; k0 = kb; i0 = (int)r1; }
-                    else { k1 = kb; i1 = (int)r1; }
+                    if (ka < k1) {
+                        if (ka < k0) { k1 = k0; i1 = i0; k0 = ka; i0 = (int)r0; }
+                        else { k1 = ka; i1 = (int)r0; }
+                    }
+                    if (kb < k1) {
+                        if (kb < k0) { k1 = k0; i1 = i0; k0 = kb; i0 = (int)r1; }
+                        else { k1 = kb; i1 = (int)r1; }
+                    }
                 }
             }
         }
@@ -398,12 +430,17 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
             if (timing) p.dbg_times[step * 16 + 6] = global_ns();
             // A CTA's list is ascending, so a list whose head is not among the KP smallest heads holds none of the KP smallest
             // entries (KP smaller heads precede everything in it): rank the heads, then only the entries of those KP lists.
-            for (int l = tid; l < grid; l += G1_THREADS) {
-                const unsigned long long me = mkey[l * G1_LC];
+            // two threads per head, four per candidate entry: the counting loops are the serial part of the step
+            for (int l0 = 0; l0 < grid; l0 += G1_THREADS / 2) {         // warp-uniform trip count (the shuffle below)
+                const int l = l0 + (tid >> 1);
+                const unsigned long long me = l < grid ? mkey[l * G1_LC] : 0ull;
                 int rank = 0;
+                if (l < grid) {
 #pragma unroll 4
-                for (int j = 0; j < grid; ++j) rank += mkey[j * G1_LC] < me ? 1 : 0;
-                if (rank < G1_KP) s_sel[rank] = l;
+                    for (int j = tid & 1; j < grid; j += 2) rank += mkey[j * G1_LC] < me ? 1 : 0;
+                }
+                rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+                if (l < grid && (tid & 1) == 0 && rank < G1_KP) s_sel[rank] = l;
             }
             __syncthreads();
             if (tid < G1_KP * G1_LC) {
@@ -411,12 +448,15 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
                 wk[tid] = l >= 0 ? mkey[l * G1_LC + tid % G1_LC] : pad_key(nmerge + tid);
             }
             __syncthreads();
-            if (tid < G1_KP * G1_LC) {
-                const unsigned long long me = wk[tid];
+            static_assert(G1_KP * G1_LC * 4 == G1_THREADS, "four threads per candidate entry");
+            {
+                const unsigned long long me = wk[tid >> 2];
                 int rank = 0;
 #pragma unroll 8
-                for (int j = 0; j < G1_KP * G1_LC; ++j) rank += wk[j] < me ? 1 : 0;
-                if (rank < G1_KP) unpack_key(me, sval[rank], ids[rank]);
+                for (int j = tid & 3; j < G1_KP * G1_LC; j += 4) rank += wk[j] < me ? 1 : 0;
+                rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+                rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+                if ((tid & 3) == 0 && rank < G1_KP) unpack_key(me, sval[rank], ids[rank]);
             }
             __syncthreads();
             if (timing) p.dbg_times[step * 16 + 7] = global_ns();
@@ -424,7 +464,7 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
 
         // ---- float64 distances of the KP rows, one per warp; the join context that would follow each of them is requested
         // into L2 meanwhile (one of them becomes the next query's join part)
-        static_assert(G1_KP <= G1_NW && G1_KP * G1_LC <= G1_NW * G1_KP, "one shortlisted row per warp; the winners fit wk");
+        static_assert(G1_KP <= G1_NW && G1_KP * G1_LC <= G1_NW * G1_KP && G1_KP <= 32 && G1_NW <= 32, "one shortlisted row per warp; the winners fit wk");
         if (warp < G1_KP) {
             const int u = ids[warp];
             double r = INFINITY;
@@ -438,31 +478,46 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
         __syncthreads();
         if (timing) p.dbg_times[step * 16 + 8] = global_ns();
 
-        // ---- the nearest row, its certificate, the outputs
-        if (tid < G1_KP) {
-            const double v = d2[tid];
-            const int i = ids[tid];
-            int rank = 0;
-            for (int j = 0; j < G1_KP; ++j)
-                rank += (dpair_lt(d2[j], ids[j], v, i) || (d2[j] == v && ids[j] == i && j < tid)) ? 1 : 0;
-            if (rank == 0) {
-                const bool ok = i != INT_MAX;
-                float mx = -INFINITY;
-                bool full = true;
-                for (int j = 0; j < G1_KP; ++j) {
-                    if (ids[j] == INT_MAX) full = false;
-                    else mx = fmaxf(mx, sval[j]);
-                }
+        // ---- the nearest row (ties: lowest id): lexicographic minimum over the KP lanes of warp 0
+        if (warp == 0) {
+            double v = lane < G1_KP ? d2[lane] : INFINITY;
+            int i = lane < G1_KP ? ids[lane] : INT_MAX;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, i, off);
+                if (dpair_lt(ov, oi, v, i)) { v = ov; i = oi; }
+            }
+            if (lane == 0) {
+                s_ix = i != INT_MAX ? (int64_t)i : p.Np;
+                s_best = v;
+            }
+        }
+        __syncthreads();
+        if (timing) p.dbg_times[step * 16 + 4] = global_ns();
+
+        // ---- the last warp judges the certificate and writes the outputs while the others assemble the join part of the
+        // next query from the chosen row (s_qn / s_qerr of THIS query are read before finish_query's barrier replaces them)
+        if (warp == G1_NW - 1) {
+            float mx = lane < G1_KP && ids[lane] != INT_MAX ? sval[lane] : -INFINITY;
+            const bool full = __all_sync(0xffffffffu, lane >= G1_KP || ids[lane] != INT_MAX);
+            float tl = lane < G1_NW ? red[2 * G1_NW + lane] : INFINITY;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+                tl = fminf(tl, __shfl_xor_sync(0xffffffffu, tl, off));
+            }
+            if (lane == 0) {
                 if (!full) mx = INFINITY;                         // the final merge dropped nothing
-                for (int w = 0; w < G1_NW; ++w) mx = fminf(mx, red[2 * G1_NW + w]);   // ... earlier stages may have
-                const double dk = ok ? sqrt(v) : INFINITY;
+                mx = fminf(mx, tl);                               // ... earlier stages may have
+                const bool ok = s_ix < p.Np;
+                const double dk = ok ? sqrt(s_best) : INFINITY;
                 int good = 1;
                 double bound = INFINITY;
                 if (mx < INFINITY) good = cert_fp16(mx, s_qn, *p.maxn, p.eps_rel, s_qerr, *p.dberr, dk, bound);
                 if (p.debug_fail_mod > 0) good = 0;               // test hook (query 0 of a batch of one)
-                s_ix = ok ? (int64_t)i : p.Np;
                 if (cta == 0) {
-                    gl.paths[mt.path_off + step] = ok ? (int64_t)i : p.Np;
+                    gl.paths[mt.path_off + step] = s_ix;
                     if (gl.step_dist) gl.step_dist[mt.path_off + step] = dk;
                     if (!good) {
                         p.flags[0] = 0;
@@ -471,13 +526,11 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
                 }
             }
         }
-        __syncthreads();
-        if (timing) p.dbg_times[step * 16 + 4] = global_ns();
-
-        // ---- join part of the next query from the chosen row
         if (has_next) {
             fill(q_nxt, s_ix + gl.cur_row_off, gl.cur_col, 0, gl.Djq);
             finish_query();
+        } else {
+            __syncthreads();      // s_ix / s_best are rewritten by the next step only after every reader is done
         }
         if (timing) p.dbg_times[step * 16 + 5] = global_ns();
     }
@@ -551,40 +604,12 @@ int snk_greedy_one_launch(snk_db *db, const void *meta_, const double *d_targets
     const size_t smem = g1_smem_bytes(p.rs, grid, p.ld16);
     SNK_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {(void *)&p};
-    // The operand rows are the same in every step, and the 64-column frame rows (G16) are about as large as the part of L2
-    // that can be set aside for persisting lines: the launch carries an access-policy window over G16 (hits persist, the
-    // rest streams), so after the first step only the join contexts come from HBM.  snk_greedy_batch_finish returns the
-    // lines to normal use.  SNK_G1_L2_MB caps the window (0: none).
-    cudaLaunchAttribute attrs[2];
+    // cooperative launch: all CTAs are resident, the grid barrier cannot deadlock
+    cudaLaunchAttribute attrs[1];
     memset(attrs, 0, sizeof(attrs));
     attrs[0].id = cudaLaunchAttributeCooperative;
     attrs[0].val.cooperative = 1;
-    int nattr = 1;
-    if (db->g1_l2_state == 0) {          // once per database handle: size the set-aside
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, db->device);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, db->device);
-        double want = getenv("SNK_G1_L2_MB") ? atof(getenv("SNK_G1_L2_MB")) * 1048576.0 : 1e18;
-        want = std::min(want, (double)max_persist);
-        db->g1_l2_state = -1;
-        if (want >= 1048576.0 && max_window > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want) == cudaSuccess) {
-            db->g1_l2_state = 1;
-            db->g1_l2_bytes = (size_t)want;
-            db->g1_l2_window = (size_t)max_window;
-        }
-        cudaGetLastError();
-    }
-    if (db->g1_l2_state == 1) {
-        const size_t g_bytes = (size_t)db->N * db->ldG16 * 2, win = std::min(g_bytes, db->g1_l2_window);
-        attrs[1].id = cudaLaunchAttributeAccessPolicyWindow;
-        attrs[1].val.accessPolicyWindow.base_ptr = (void *)db->G16;
-        attrs[1].val.accessPolicyWindow.num_bytes = win;
-        attrs[1].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)db->g1_l2_bytes / (double)win);
-        attrs[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attrs[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        nattr = 2;
-        db->g1_l2_dirty = true;
-    }
+    const int nattr = 1;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);
@@ -597,14 +622,6 @@ int snk_greedy_one_launch(snk_db *db, const void *meta_, const double *d_targets
     db->counters[0] += meta.nsteps;
     db->counters[2] += 1;
     return 0;
-}
-
-// called by snk_greedy_batch_finish (a point where the host waits anyway): persisting L2 lines go back to normal use
-void snk_greedy_one_release_l2(snk_db *db) {
-    if (!db->g1_l2_dirty) return;
-    cudaCtxResetPersistingL2Cache();
-    cudaGetLastError();
-    db->g1_l2_dirty = false;
 }
 
 // Test instrumentation (include/snk_b200.h): the keys the single-utterance kernel computes for the first step of an

@@ -699,6 +699,5 @@ extern "C" int snk_greedy_batch_finish(snk_db *db) {
         ps->pool.push_back(job.fb);
     }
     ps->greedy.clear();
-    snk_greedy_one_release_l2(db);
     return rc;
 }
