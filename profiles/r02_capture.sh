@@ -7,3 +7,4 @@ ncu --set full --import-source on --clock-control none -k regex:"rerank_kernel|s
 ncu --set full --import-source on --clock-control none -k regex:knn_tc_kernel -s 30 -c 1 -o gpurun_out/r02_knn_greedy -f python bench.py --steps 1 --warmup 1 --no-cpu --no-secondary > gpurun_out/r02_ncu_greedy.log 2>&1
 python bench.py > gpurun_out/bench_r2d.json 2> gpurun_out/bench_r2d.err
 tail -c 300 gpurun_out/bench_r2d.err
+PROBE_NCU=1 ncu --set full --clock-control none --import-source on -k regex:greedy_one -s 1 -c 1 -f -o gpurun_out/r02_greedy_one python tests/multigpu/probe_single.py > gpurun_out/r02_ncu_greedy_one.log 2>&1
