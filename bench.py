@@ -616,6 +616,10 @@ def block_sharded_greedy(D, db, wt, wj, cfg):
                 "nvlink_bytes_received_per_rank_per_step": B * 24 * (world - 1)}
         if B == 1024:       # parity sample against the replicated database
             case["paths_hash"] = int(paths[0].sum().item() % 1000003)
+        else:               # one utterance: the persistent kernel with the exchange inside it (greedy_one.cu) when peers are mapped
+            case["path"] = "one persistent kernel per utterance, exchange through peer memory inside it" \
+                if (world > 1 and sg.knn.db.comm_info()["peer_exchange"]) else "batched path (three launches + exchange per step)"
+            keep1 = paths[0][0].cpu().numpy()
         res["cases"].append(case)
         keep = paths[0][:4].cpu().numpy() if B == 1024 else None
         if B == 1024 and rank == 0:
@@ -623,6 +627,11 @@ def block_sharded_greedy(D, db, wt, wj, cfg):
             utts = [tg[b].cpu().numpy() for b in range(4)]
             want = ref.greedy_joint_search_batch(utts)
             res["first_4_paths_equal_replicated_search"] = bool(all(keep[b].tolist() == want[b] for b in range(4)))
+            ref.db.close()
+        if B == 1 and rank == 0:
+            ref = Synthesiser(cfg, F, Jc, device=D.local)
+            res["single_utterance_path_equals_replicated_search"] = bool(
+                keep1.tolist() == ref.greedy_joint_search_batch([tg[0].cpu().numpy()])[0])
             ref.db.close()
     c = sg.knn.db.counters()
     res["exactness"] = {"utterances_recertified": int(c["recertified"]), "exhaustive_f64": int(c["exhaustive"])}

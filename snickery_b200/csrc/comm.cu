@@ -280,6 +280,23 @@ int snk_comm_allreduce_min(snk_db *db, int *d_buf, int n, cudaStream_t st) {
 
 int snk_comm_nranks(const snk_db *db) { return db->comm ? db->comm->nranks : 1; }
 
+bool snk_comm_has_p2p(const snk_db *db) { return db->comm && db->comm->p2p && db->comm->nranks > 1; }
+
+int snk_comm_p2p_claim(snk_db *db, int nsteps, char *const **peers, int *rank, int *nranks, unsigned *epoch0, size_t *flags_bytes,
+                       size_t *slot_bytes) {
+    snk_comm_state *c = db->comm;
+    *peers = nullptr;
+    if (!c || !c->p2p || c->nranks < 2) return 0;
+    *peers = c->d_peers;
+    *rank = c->rank;
+    *nranks = c->nranks;
+    *epoch0 = c->epoch;
+    c->epoch += (unsigned)nsteps;
+    *flags_bytes = P2P_FLAGS_BYTES;
+    *slot_bytes = (size_t)P2P_CAP * 24;
+    return 0;
+}
+
 extern "C" {
 
 int snk_comm_unique_id(void *id_out, int id_bytes) {

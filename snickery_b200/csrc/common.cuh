@@ -254,8 +254,15 @@ int snk_search_dev(snk_db *db, int space, const double *dQ, int64_t nq, int k, d
                    cudaStream_t st);
 // ---- greedy_one.cu : one utterance as one persistent kernel (meta: the utterance's greedy_meta, greedy_dev.cuh)
 bool snk_greedy_one_supported(const snk_db *db);
+// d_Jc_full != nullptr: database-sharded (rows [id_offset, id_offset + Np) here), exchange over peer memory inside the kernel
 int snk_greedy_one_launch(snk_db *db, const void *meta, const double *d_targets, const float *d_unnorm, int64_t *d_paths,
-                          double *d_step_dist, int *d_flags, int *d_count, float *d_keys, cudaStream_t st);
+                          double *d_step_dist, int *d_flags, int *d_count, float *d_keys, cudaStream_t st,
+                          const float *d_Jc_full, int64_t id_offset);
+// comm.cu: the peer-memory exchange regions for a kernel that runs `nsteps` exchange steps by itself (claims their epochs);
+// *peers == nullptr if the communicator has no peer-memory path
+int snk_comm_p2p_claim(snk_db *db, int nsteps, char *const **peers, int *rank, int *nranks, unsigned *epoch0, size_t *flags_bytes,
+                       size_t *slot_bytes);
+bool snk_comm_has_p2p(const snk_db *db);
 // enqueue a search with deferred certificates; snk_knn_finish(db) completes it (see search.cu)
 int snk_knn_enqueue(snk_db *db, int space, const double *dQ, int64_t nq, int k, double *d_dist, int64_t *d_idx,
                     int64_t out_stride, int64_t id_offset, cudaStream_t st);

@@ -60,6 +60,13 @@ struct g1_params {
     int debug_fail_mod;
     int *flags, *count;
     float *dbg_keys;              // test instrumentation: keys of step 0, [Np]
+    // database-sharded search: this rank scans joint rows [id_offset, id_offset + Np); after
+    // the local re-rank the ranks exchange (distance, global row, bound) through their IPC-mapped regions (comm.cu)
+    char *const *peers;           // peers[r] = rank r's exchange region as mapped here; nullptr: single GPU
+    int rank, R;
+    unsigned epoch0;              // epoch of step s is epoch0 + 1 + s
+    int64_t id_offset;
+    size_t xflags_bytes, xslot_bytes;   // layout of a region: flags, then [parity][writer rank] slots of xslot_bytes
     unsigned long long *dbg_times;   // SNK_G1_TIMING: CTA 0's globaltimer at up to 16 points of every step, [steps][16]
 };
 
@@ -134,6 +141,14 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -167,6 +182,7 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
     __shared__ int64_t s_ix;
     __shared__ float s_qn, s_qerr;
     __shared__ double s_best;
+    __shared__ float s_mx;
     __shared__ int s_sel[G1_KP];
 
     for (int d = tid; d < rs.dA; d += G1_THREADS) wA_s[d] = rs.wA[rs.a_col + d];
@@ -478,56 +494,112 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
         __syncthreads();
         if (timing) p.dbg_times[step * 16 + 8] = global_ns();
 
-        // ---- the nearest row (ties: lowest id): lexicographic minimum over the KP lanes of warp 0
+        // ---- the nearest row (ties: lowest id): lexicographic minimum over the KP lanes of warp 0; the same warp works out
+        // what the certificate needs (tau: no row outside the shortlist has a smaller key)
         if (warp == 0) {
             double v = lane < G1_KP ? d2[lane] : INFINITY;
             int i = lane < G1_KP ? ids[lane] : INT_MAX;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, v, off);
-                const int oi = __shfl_xor_sync(0xffffffffu, i, off);
-                if (dpair_lt(ov, oi, v, i)) { v = ov; i = oi; }
-            }
-            if (lane == 0) {
-                s_ix = i != INT_MAX ? (int64_t)i : p.Np;
-                s_best = v;
-            }
-        }
-        __syncthreads();
-        if (timing) p.dbg_times[step * 16 + 4] = global_ns();
-
-        // ---- the last warp judges the certificate and writes the outputs while the others assemble the join part of the
-        // next query from the chosen row (s_qn / s_qerr of THIS query are read before finish_query's barrier replaces them)
-        if (warp == G1_NW - 1) {
             float mx = lane < G1_KP && ids[lane] != INT_MAX ? sval[lane] : -INFINITY;
             const bool full = __all_sync(0xffffffffu, lane >= G1_KP || ids[lane] != INT_MAX);
             float tl = lane < G1_NW ? red[2 * G1_NW + lane] : INFINITY;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, i, off);
+                if (dpair_lt(ov, oi, v, i)) { v = ov; i = oi; }
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
                 tl = fminf(tl, __shfl_xor_sync(0xffffffffu, tl, off));
             }
             if (lane == 0) {
-                if (!full) mx = INFINITY;                         // the final merge dropped nothing
-                mx = fminf(mx, tl);                               // ... earlier stages may have
-                const bool ok = s_ix < p.Np;
-                const double dk = ok ? sqrt(s_best) : INFINITY;
-                int good = 1;
-                double bound = INFINITY;
-                if (mx < INFINITY) good = cert_fp16(mx, s_qn, *p.maxn, p.eps_rel, s_qerr, *p.dberr, dk, bound);
-                if (p.debug_fail_mod > 0) good = 0;               // test hook (query 0 of a batch of one)
-                if (cta == 0) {
-                    gl.paths[mt.path_off + step] = s_ix;
-                    if (gl.step_dist) gl.step_dist[mt.path_off + step] = dk;
-                    if (!good) {
-                        p.flags[0] = 0;
-                        atomicAdd(p.count, 1);
+                s_ix = i != INT_MAX ? (int64_t)i + p.id_offset : -1;
+                s_best = v;
+                s_mx = fminf(full ? mx : INFINITY, tl);   // the final merge dropped nothing unless it was full; earlier stages may have
+            }
+        }
+        __syncthreads();
+        if (timing) p.dbg_times[step * 16 + 4] = global_ns();
+
+        if (p.peers) {
+            // ---- database-sharded: this rank's best is one candidate.  CTA 0 stores (distance, global row, bound) into its
+            // slot in EVERY rank's region and publishes the step's epoch (system-scope release); every CTA of every rank
+            // waits until all ranks' epochs have arrived in the local region and takes the arg-min.  The answer stands iff it
+            // is not above any rank's bound (a shard without a close row cannot certify its own best, and need not).
+            const unsigned epoch = p.epoch0 + 1u + (unsigned)step;
+            const size_t slot0 = p.xflags_bytes + (size_t)(epoch & 1u) * p.R * p.xslot_bytes;
+            if (cta == 0 && warp == 0) {
+                double dk = INFINITY, bound = INFINITY;
+                if (lane == 0) {
+                    dk = s_ix >= 0 ? sqrt(s_best) : INFINITY;
+                    if (s_mx < INFINITY) cert_fp16(s_mx, s_qn, *p.maxn, p.eps_rel, s_qerr, *p.dberr, dk, bound);
+                    if (p.debug_fail_mod > 0) bound = -INFINITY;
+                }
+                dk = __shfl_sync(0xffffffffu, dk, 0);
+                bound = __shfl_sync(0xffffffffu, bound, 0);
+                if (lane < p.R) {
+                    double *dst = reinterpret_cast<double *>(p.peers[lane] + slot0 + (size_t)p.rank * p.xslot_bytes);
+                    dst[0] = dk;
+                    reinterpret_cast<int64_t *>(dst)[1] = s_ix >= 0 ? s_ix : (int64_t)0x7fffffffffffffffll;
+                    dst[2] = bound;
+                    __threadfence_system();
+                    st_release_sys(reinterpret_cast<unsigned *>(p.peers[lane]) + p.rank, epoch);
+                }
+            }
+            if (warp == 1) {
+                if (lane < p.R) {
+                    const unsigned *f = reinterpret_cast<const unsigned *>(p.peers[p.rank]) + lane;
+                    const long long t_start = clock64();
+                    while ((int)(ld_acquire_sys(f) - epoch) < 0)
+                        if (clock64() - t_start > 20000000000ll) __trap();   // a peer that never arrives must not hang the GPU
+                }
+                __syncwarp();
+                double bd = INFINITY, lb = INFINITY;
+                int64_t bi = 0x7fffffffffffffffll;
+                if (lane < p.R) {      // written by remote GPUs: read past L1
+                    const double *e = reinterpret_cast<const double *>(p.peers[p.rank] + slot0 + (size_t)lane * p.xslot_bytes);
+                    bd = __ldcg(e);
+                    bi = __ldcg(reinterpret_cast<const long long *>(e) + 1);
+                    lb = __ldcg(e + 2);
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+                    const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+                    lb = fmin(lb, __shfl_xor_sync(0xffffffffu, lb, off));
+                }
+                if (lane == 0) {
+                    s_ix = bi;
+                    if (cta == 0) {
+                        gl.paths[mt.path_off + step] = bi;
+                        if (gl.step_dist) gl.step_dist[mt.path_off + step] = bd;
+                        if (!(bd <= lb)) {
+                            if (p.flags[0]) atomicAdd(p.count, 1);
+                            p.flags[0] = 0;
+                        }
                     }
+                }
+            }
+            __syncthreads();
+        } else if (warp == G1_NW - 1 && lane == 0) {
+            // ---- single GPU: the last warp judges the certificate and writes the outputs while the others assemble the join
+            // part of the next query (s_qn / s_qerr of THIS query are read before finish_query's barrier replaces them)
+            const bool ok = s_ix >= 0;
+            const double dk = ok ? sqrt(s_best) : INFINITY;
+            int good = 1;
+            double bound = INFINITY;
+            if (s_mx < INFINITY) good = cert_fp16(s_mx, s_qn, *p.maxn, p.eps_rel, s_qerr, *p.dberr, dk, bound);
+            if (p.debug_fail_mod > 0) good = 0;               // test hook (query 0 of a batch of one)
+            if (cta == 0) {
+                gl.paths[mt.path_off + step] = ok ? s_ix : p.Np;
+                if (gl.step_dist) gl.step_dist[mt.path_off + step] = dk;
+                if (!good) {
+                    p.flags[0] = 0;
+                    atomicAdd(p.count, 1);
                 }
             }
         }
         if (has_next) {
-            fill(q_nxt, s_ix + gl.cur_row_off, gl.cur_col, 0, gl.Djq);
+            fill(q_nxt, (s_ix >= 0 ? s_ix : p.Np) + gl.cur_row_off, gl.cur_col, 0, gl.Djq);
             finish_query();
         } else {
             __syncthreads();      // s_ix / s_best are rewritten by the next step only after every reader is done
@@ -567,13 +639,14 @@ bool snk_greedy_one_supported(const snk_db *db) {
 
 // d_keys (optional, [Np] floats): the kernel also stores the keys of step 0 (certificate tests)
 int snk_greedy_one_launch(snk_db *db, const void *meta_, const double *d_targets, const float *d_unnorm, int64_t *d_paths,
-                          double *d_step_dist, int *d_flags, int *d_count, float *d_keys, cudaStream_t st) {
+                          double *d_step_dist, int *d_flags, int *d_count, float *d_keys, cudaStream_t st,
+                          const float *d_Jc_full, int64_t id_offset) {
     const greedy_meta &meta = *(const greedy_meta *)meta_;
     const snk_space sp = snk_make_space(db, SNK_SPACE_JOINT);
     g1_params p;
     memset(&p, 0, sizeof(p));
     const std_params stp{db->std_mean, db->std_sd, db->wt, db->uv_special, db->uv_scale, db->std_f32};
-    p.g = greedy_src{nullptr, 0, 0, d_targets, d_unnorm, stp, db->Dt, db->m, db->Jc_raw, db->wj, db->Dj, db->Djq,
+    p.g = greedy_src{nullptr, 0, 0, d_targets, d_unnorm, stp, db->Dt, db->m, d_Jc_full ? d_Jc_full : db->Jc_raw, db->wj, db->Dj, db->Djq,
                      db->prev_row_off, db->prev_col, db->cur_row_off, db->cur_col, nullptr, nullptr, d_paths, d_step_dist};
     p.meta = meta;
     p.rs = make_rr(db, sp);
@@ -599,6 +672,11 @@ int snk_greedy_one_launch(snk_db *db, const void *meta_, const double *d_targets
     p.debug_fail_mod = db->debug_fail_mod;
     p.flags = d_flags; p.count = d_count;
     p.dbg_keys = d_keys;
+    p.id_offset = id_offset;
+    if (d_Jc_full) {       // database-sharded: the exchange regions of the communicator; this launch owns the next nsteps epochs
+        SNK_TRY(snk_comm_p2p_claim(db, (int)meta.nsteps, &p.peers, &p.rank, &p.R, &p.epoch0, &p.xflags_bytes, &p.xslot_bytes));
+        SNK_CHECK(p.peers && p.R >= 2 && p.R <= 32, "internal: single-utterance sharded search needs the peer-memory exchange");
+    }
     g1_fn fn = g1_pick(db->m);
     SNK_CHECK(fn, "internal: no single-utterance kernel for multiepoch %d", db->m);
     const size_t smem = g1_smem_bytes(p.rs, grid, p.ld16);
@@ -645,7 +723,7 @@ extern "C" int snk_debug_greedy_one_keys(snk_db *db, const double *targets, int6
     SNK_CUDA(cudaMemsetAsync(flags, 0, 8, st));
     const greedy_meta meta{0, 0, 1, start_state};
     SNK_TRY(snk_greedy_one_launch(db, &meta, (const double *)db->ws_h0.p, nullptr, path, nullptr, flags, flags + 1,
-                                  (float *)db->ws_dist.p, st));
+                                  (float *)db->ws_dist.p, st, nullptr, 0));
     SNK_CUDA(cudaMemcpyAsync(keys, db->ws_dist.p, (size_t)db->Np * 4, cudaMemcpyDeviceToHost, st));
     if (qnorm) SNK_CUDA(cudaMemcpyAsync(qnorm, (float *)db->ws_dist.p + db->Np, 4, cudaMemcpyDeviceToHost, st));
     if (maxnorm) SNK_CUDA(cudaMemcpyAsync(maxnorm, db->maxn_j16, 4, cudaMemcpyDeviceToHost, st));

@@ -361,10 +361,12 @@ int greedy_run(snk_db *db, const std::vector<greedy_meta> &meta, const double *d
                int64_t *d_paths, double *d_step_dist, int *d_flags, int *d_count, cudaStream_t st,
                const greedy_shard *sh = nullptr) {
     const int B = (int)meta.size();
-    if (B == 1 && !sh && snk_greedy_one_supported(db)) {
-        // one utterance: the whole chain is one persistent kernel (greedy_one.cu); all its frames must have landed
+    if (B == 1 && snk_greedy_one_supported(db) && (!sh || snk_comm_has_p2p(db))) {
+        // one utterance: the whole chain is one persistent kernel (greedy_one.cu), over a sharded database with the per-step
+        // exchange through peer memory inside it; all its frames must have landed
         for (auto &w : db->step_waits) SNK_CUDA(cudaStreamWaitEvent(st, w.second, 0));
-        return snk_greedy_one_launch(db, &meta[0], d_targets, d_unnorm, d_paths, d_step_dist, d_flags, d_count, nullptr, st);
+        return snk_greedy_one_launch(db, &meta[0], d_targets, d_unnorm, d_paths, d_step_dist, d_flags, d_count, nullptr, st,
+                                     sh ? sh->Jc_full : nullptr, sh ? sh->id_offset : 0);
     }
     const std_params stp{db->std_mean, db->std_sd, db->wt, db->uv_special, db->uv_scale, db->std_f32};
     const int m = db->m;

@@ -37,6 +37,23 @@ def main():
     del os.environ["SNK_DEBUG_CERT_FAIL"]
     paths2 = sg2.search(tg, starts).cpu().numpy()
     ok = ok and all(paths2[b].tolist() == want[b] for b in range(B)) and sg2.knn.db.counters()["recertified"] > 0
+    # one utterance at a time: the persistent single-utterance kernel with the exchange through peer memory inside it
+    # (greedy_one.cu) -- paths AND distances must equal the replicated search's, with and without a start state, and with
+    # the certificate forced to fail (repair through the batched fp32 engine, all ranks in lockstep)
+    ok1 = True
+    for b in (0, 5, B - 1):
+        sg.knn.db.counters(reset=True)
+        p1, d1 = sg.search(tg[b:b + 1], [starts[b]], return_dists=True)
+        launches = sg.knn.db.counters()["launches"]
+        w1, wd1 = ref.greedy_joint_search_batch([utts[b]], [starts[b]], return_dists=True)
+        same = p1[0].cpu().numpy().tolist() == w1[0] and np.array_equal(d1[0].cpu().numpy(), np.asarray(wd1[0]))
+        used_one = launches <= 3 if (world > 1 and sg.knn.db.comm_info()["peer_exchange"]) else True
+        ok1 = ok1 and same and used_one
+        if rank == 0:
+            print("single utterance %d: same=%s launches=%d" % (b, same, launches), flush=True)
+    p2 = sg2.search(tg[2:3], [starts[2]]).cpu().numpy()
+    ok1 = ok1 and p2[0].tolist() == want[2]
+    ok = ok and ok1
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
