@@ -108,6 +108,9 @@ int snk_debug_tc_keys(snk_db *db, int space, const double *Q, int64_t nq, int64_
  * *qnorm = the fp32 ||x~||^2 of that query.                                                     */
 int snk_debug_greedy_one_keys(snk_db *db, const double *targets, int64_t start_state, float *keys, float *qnorm,
                               float *eps_rel, float *maxnorm);
+/* Diagnostic: with SNK_G1_TIMING=1 in the environment the single-utterance kernel records CTA 0's %globaltimer at up to 16
+ * points of every step; out [steps][16] nanoseconds of the last launch (tests/multigpu/probe_single.py prints the split). */
+int snk_debug_greedy_one_times(snk_db *db, unsigned long long *out, int steps);
 
 /* ---- k-NN: tree.query(X, k) ------------------------------------------------------------
  * Replaces cKDTree.query / sklearn KDTree.query (synth_halfphone.py:1364,1384;
@@ -154,7 +157,11 @@ int snk_knn_sharded_finish(snk_db *db);
  * utterances' weighted unit_features [T_b, Dt] concatenated; lens[b] = T_b;
  * start_state[b] = -1 or a unit id (may be NULL = all -1).  Outputs: paths, the
  * T_b // multiepoch selected row ids per utterance concatenated; step_dist (optional,
- * may be NULL) the joint Euclidean distance of each step.                              */
+ * may be NULL) the joint Euclidean distance of each step.
+ * B = 1 -- the reference's own call, one utterance at a time (synth_simple.py:413) -- runs as ONE
+ * persistent cooperative kernel for the shipped epoch-voice shapes (greedy_one.cu: every step
+ * streams the operand rows once, grid barrier, float64 re-rank and next query inside the kernel);
+ * the results are bit-identical to the batched path (SNK_GREEDY_NO_ONE=1 forces that one).  */
 int snk_greedy_batch(snk_db *db, const double *targets, const int64_t *lens, int B,
                      const int64_t *start_state, int64_t *paths, double *step_dist);
 /* device variant: d_targets as above in device memory; lens / start_state are HOST arrays
@@ -174,6 +181,8 @@ int snk_greedy_batch_finish(snk_db *db);
  * their shortlist can lie -- one grouped ncclAllGather of B * 24 bytes plus an arg-min kernel, enqueued by the library --
  * so the paths (GLOBAL row ids) are identical on every rank, and an answer is certified when it is not above any rank's
  * bound (a shard that holds no close row cannot certify its own best, and does not need to).
+ * B = 1 with mapped peers: the single-utterance persistent kernel scans the shard and performs that exchange itself
+ * (24-byte stores into every peer's region + epoch flag, once per step) -- one launch per utterance on every rank.
  * Collective: every rank calls it with the same targets, then snk_greedy_batch_finish (which also agrees, with one
  * all-reduce, on the utterances whose certificates failed on any rank and repeats them in lockstep).               */
 int snk_greedy_sharded_batch_dev(snk_db *db, const double *d_targets, const int64_t *lens, int B, const int64_t *start_state,
