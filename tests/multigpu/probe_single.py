@@ -72,7 +72,7 @@ for mb in [0.0]:
     assert lib.snk_debug_greedy_one_times(syn.db._h, tt.ctypes.data, steps) == 0
     tt = tt.astype(np.int64)[2:]
     med = lambda a, b: np.median(tt[:, a] - tt[:, b]) / 1e3
-    print("keep %3d MB us: scan %.1f | warps %.1f cta-merge %.1f publish %.1f fence %.1f | wait %.1f | lists %.1f select %.1f rerank %.1f "
+    print("phases (%d) us: scan %.1f | warps %.1f cta-merge %.1f publish %.1f fence %.1f | wait %.1f | lists %.1f select %.1f rerank %.1f "
           "cert %.1f query %.1f | step %.1f" % (
               mb, np.median(tt[1:, 0] - tt[:-1, 5]) / 1e3, med(1, 0), med(9, 1), med(10, 9), med(2, 10), med(3, 2), med(6, 3),
               med(7, 6), med(8, 7), med(4, 8), med(5, 4), np.median(tt[1:, 5] - tt[:-1, 5]) / 1e3), flush=True)
