@@ -111,6 +111,8 @@ int snk_debug_greedy_one_keys(snk_db *db, const double *targets, int64_t start_s
 /* Diagnostic: with SNK_G1_TIMING=1 in the environment the single-utterance kernel records CTA 0's %globaltimer at up to 16
  * points of every step; out [steps][16] nanoseconds of the last launch (tests/multigpu/probe_single.py prints the split). */
 int snk_debug_greedy_one_times(snk_db *db, unsigned long long *out, int steps);
+/* ... and every CTA's timestamp at the end of its scan, out [steps <= 256][SM count]: the skew the grid barrier waits for */
+int snk_debug_greedy_one_cta_times(snk_db *db, unsigned long long *out, int steps);
 
 /* ---- k-NN: tree.query(X, k) ------------------------------------------------------------
  * Replaces cKDTree.query / sklearn KDTree.query (synth_halfphone.py:1364,1384;

@@ -130,6 +130,7 @@ struct snk_db {
     snk_comm_state *comm = nullptr;
     snk_pending_state *pending = nullptr;
     snk_acoustic_job *acoustic = nullptr;
+    int g1_resident = 0;         // greedy_one.cu: 1 = the cooperative single-utterance kernel fits this device, -1 = it does not
     int64_t counters[4] = {0, 0, 0, 0};
     // optional kernel timing (snk_db_profile_*)
     bool prof_on = false;

@@ -54,6 +54,8 @@ struct g1_params {
     int64_t ngroups, groups_per_cta;
     unsigned long long *lists;    // [2][grid][G1_LC] packed (key, row)
     float *taus;                  // [2][grid]
+    unsigned *durs;               // [2][grid] nanoseconds every CTA's scan took (row-slice balancing)
+    int balance;                  // 1: the CTAs' row slices follow their measured scan rates
     unsigned *bar;                // arrive counter, zero at launch
     const float *dberr, *maxn;
     float eps_rel;
@@ -67,6 +69,7 @@ struct g1_params {
     unsigned epoch0;              // epoch of step s is epoch0 + 1 + s
     int64_t id_offset;
     size_t xflags_bytes, xslot_bytes;   // layout of a region: flags, then [parity][writer rank] slots of xslot_bytes
+    unsigned long long *dbg_cta;     // SNK_G1_TIMING: every CTA's globaltimer when its scan ends, [steps <= 256][grid]
     unsigned long long *dbg_times;   // SNK_G1_TIMING: CTA 0's globaltimer at up to 16 points of every step, [steps][16]
 };
 
@@ -179,6 +182,9 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
     __half *q16_s = reinterpret_cast<__half *>(red + 3 * G1_NW + 2);   // [ld16] (16-byte aligned: see g1_smem_bytes)
     q16_s = reinterpret_cast<__half *>((reinterpret_cast<uintptr_t>(q16_s) + 15) & ~(uintptr_t)15);
     short *qmap_s = reinterpret_cast<short *>(q16_s + p.ld16 + 8);  // [ld16]; q16_s[ld16 .. ld16 + 8) stays zero
+    float *speed = reinterpret_cast<float *>(qmap_s + p.ld16);      // [grid] tiles per nanosecond of every CTA's scan, smoothed
+    int *bounds = reinterpret_cast<int *>(speed + grid);            // [grid + 1] first tile of every CTA's slice
+    __shared__ unsigned s_dur;
     __shared__ int64_t s_ix;
     __shared__ float s_qn, s_qerr;
     __shared__ double s_best;
@@ -240,17 +246,23 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
     }
     finish_query();
 
-    const int64_t grp_lo = (int64_t)cta * p.groups_per_cta, grp_hi = min(p.ngroups, grp_lo + p.groups_per_cta);
+    // row slices: equal at first; with p.balance they follow the scan rates measured in the previous steps (below)
+    for (int c = tid; c <= grid; c += G1_THREADS) bounds[c] = (int)(p.ngroups * c / grid);
+    for (int c = tid; c < grid; c += G1_THREADS) speed[c] = 0.f;
+    if (tid == 0) s_dur = 0u;
+    __syncthreads();
     const int64_t last = p.Np - 1, glast = p.Np + M - 2;      // last searchable row, last frame row
-    // the warp's run of tiles: the CTA's slice in NW nearly equal parts
-    const int64_t cta_groups = max((int64_t)0, grp_hi - grp_lo), w_base = cta_groups / G1_NW, w_rem = cta_groups % G1_NW;
-    const int64_t w_lo = grp_lo + warp * w_base + min((int64_t)warp, w_rem), w_hi = w_lo + w_base + (warp < w_rem ? 1 : 0);
     const uint4 *S4 = reinterpret_cast<const uint4 *>(p.S16) + t4, *G4 = reinterpret_cast<const uint4 *>(p.G16) + t4;
 
     for (int64_t step = 0; step < nsteps; ++step) {
         const int par = (int)(step & 1);
         const double *q_cur = q_s + par * rs.D;
         double *q_nxt = q_s + (par ^ 1) * rs.D;
+        const int64_t grp_lo = bounds[cta], grp_hi = bounds[cta + 1];
+        // the warp's run of tiles: the CTA's slice in NW nearly equal parts
+        const int64_t cta_groups = max((int64_t)0, grp_hi - grp_lo), w_base = cta_groups / G1_NW, w_rem = cta_groups % G1_NW;
+        const int64_t w_lo = grp_lo + warp * w_base + min((int64_t)warp, w_rem), w_hi = w_lo + w_base + (warp < w_rem ? 1 : 0);
+        const unsigned long long t_scan = p.balance ? global_ns() : 0ull;
         // ---- scan.  A warp walks a contiguous run of 16-row tiles.  Per tile k:
         //   J(k)   = join part, NCS chunks: every N column of the mma carries the same query, column 0 is read back;
         //   C(k+1) = frame products of the NEXT tile, NCG chunks: N column j carries frame j of the query window, so ONE pass
@@ -357,8 +369,10 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
             }
         }
 
+        if (p.balance && lane == 0) atomicMax(&s_dur, (unsigned)(global_ns() - t_scan));
         const bool timing = p.dbg_times && cta == 0 && tid == 0 && step < 4096;
         if (timing) p.dbg_times[step * 16 + 0] = global_ns();
+        if (p.dbg_cta && tid == 0 && step < 256) p.dbg_cta[step * grid + cta] = global_ns();
         const bool has_next = step + 1 < nsteps;
         // ---- CTA merge: the LC smallest of the thread lists; tau = no row dropped so far has a smaller key
         {
@@ -403,6 +417,7 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
                 unpack_key(clist[G1_LC - 1], v, id);     // entries beyond the LC kept are >= the last kept (pad: +inf)
                 tau = fminf(tau, v);
                 __stcg(p.taus + (size_t)par * grid + cta, tau);
+                if (p.balance) { __stcg(p.durs + (size_t)par * grid + cta, s_dur); s_dur = 0u; }
             }
             __syncthreads();
             if (tid == 0) {
@@ -442,6 +457,17 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
                 mkey[i] = (unsigned)(e >> 32) == 0xFFFFFFFFu ? pad_key(i) : e;     // pads made distinct across CTAs
             }
             if (tid < G1_KP) { sval[tid] = INFINITY; ids[tid] = INT_MAX; s_sel[tid] = -1; }
+            // row-slice balancing: every CTA's scan rate of this step (tiles per nanosecond), smoothed over the steps
+            if (p.balance) {
+                for (int c = tid; c < grid; c += G1_THREADS) {
+                    const unsigned d = __ldcg(p.durs + (size_t)par * grid + c);
+                    const int gc = bounds[c + 1] - bounds[c];
+                    if (d > 0u && gc > 0) {
+                        const float r = (float)gc / (float)d;
+                        speed[c] = speed[c] > 0.f ? 0.5f * speed[c] + 0.5f * r : r;
+                    }
+                }
+            }
             __syncthreads();
             if (timing) p.dbg_times[step * 16 + 6] = global_ns();
             // A CTA's list is ascending, so a list whose head is not among the KP smallest heads holds none of the KP smallest
@@ -598,6 +624,40 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
                 }
             }
         }
+        // One warp re-cuts the slices in proportion to the rates (the same arithmetic on the same numbers in every CTA,
+        // so all CTAs agree); the HBM rate an SM sees is tied to the SM (measured: the same few CTAs finish 3 us late
+        // in every step), and the grid barrier waits for the slowest.  This warp is idle here (others assemble the next query /
+        // judge the certificate); nobody reads `bounds` before the next scan starts.
+        if (p.balance && has_next && warp == G1_NW - 2) {
+            const int per = (grid + 31) / 32, c0 = lane * per, c1 = min(grid, c0 + per);
+            float mine = 0.f, known = 0.f;
+            int nknown = 0;
+            for (int c = c0; c < c1; ++c)
+                if (speed[c] > 0.f) { known += speed[c]; ++nknown; }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                known += __shfl_xor_sync(0xffffffffu, known, off);
+                nknown += __shfl_xor_sync(0xffffffffu, nknown, off);
+            }
+            if (nknown > 0) {
+                const float fill_in = __fdividef(known, (float)nknown);   // CTAs without a measurement yet: the mean rate
+                for (int c = c0; c < c1; ++c) mine += speed[c] > 0.f ? speed[c] : fill_in;
+                float incl = mine;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const float o = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += o;
+                }
+                const float total = __shfl_sync(0xffffffffu, incl, 31);
+                const float scale = (float)p.ngroups / total;          // one division; the products below are monotone in cum
+                float cum = incl - mine;
+                for (int c = c0; c < c1; ++c) {
+                    bounds[c] = min((int)p.ngroups, (int)(cum * scale));
+                    cum += speed[c] > 0.f ? speed[c] : fill_in;
+                }
+                if (lane == 0) { bounds[0] = 0; bounds[grid] = (int)p.ngroups; }
+            }
+        }
         if (has_next) {
             fill(q_nxt, (s_ix >= 0 ? s_ix : p.Np) + gl.cur_row_off, gl.cur_col, 0, gl.Djq);
             finish_query();
@@ -610,7 +670,7 @@ __global__ void __launch_bounds__(G1_THREADS, 1) greedy_one_kernel(const g1_para
 
 size_t g1_smem_bytes(const rr_space &rs, int grid, int ld16) {
     return (size_t)(2 * rs.D + rs.dA + rs.dB + G1_KP) * 8 + (size_t)(grid * G1_LC + G1_NW * G1_KP + G1_ENT + G1_LC) * 8 +
-           (size_t)G1_KP * 8 + (size_t)(3 * G1_NW + 2) * 4 + 16 + (size_t)ld16 * 4 + 16 + 16;
+           (size_t)G1_KP * 8 + (size_t)(3 * G1_NW + 2) * 4 + 16 + (size_t)ld16 * 4 + 16 + 16 + (size_t)(2 * grid + 1) * 4 + 8;
 }
 
 typedef void (*g1_fn)(const g1_params);
@@ -634,7 +694,20 @@ bool snk_greedy_one_supported(const snk_db *db) {
     if (db->ldS16 != 192 || db->Djq + 3 > 160 || db->Djq + 3 <= 128) return false;
     if (db->ldG16 != 64 || db->Dt + 3 > 64 || db->Dt + 3 <= 32) return false;
     if (db->Np < 1 || db->Np >= (int64_t)INT_MAX - 64) return false;
-    return g1_pick(db->m) != nullptr;
+    g1_fn fn = g1_pick(db->m);
+    if (!fn) return false;
+    if (db->g1_resident == 0) {
+        // once per handle: one CTA per SM must be resident at the same time (cooperative launch), and the device must allow it
+        const snk_space sp = snk_make_space(db, SNK_SPACE_JOINT);
+        const size_t smem = g1_smem_bytes(make_rr(db, sp), db->sm_count, db->ldS16 + db->m * db->ldG16);
+        int coop = 0, nb = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, db->device);
+        const bool ok = coop && cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, G1_THREADS, smem) == cudaSuccess && nb >= 1;
+        cudaGetLastError();
+        const_cast<snk_db *>(db)->g1_resident = ok ? 1 : -1;
+    }
+    return db->g1_resident == 1;
 }
 
 // d_keys (optional, [Np] floats): the kernel also stores the keys of step 0 (certificate tests)
@@ -659,20 +732,23 @@ int snk_greedy_one_launch(snk_db *db, const void *meta_, const double *d_targets
     p.ngroups = snk_cdiv(db->Np, 16);
     p.groups_per_cta = snk_cdiv(p.ngroups, grid);
     // exchange area: lists [2][grid][LC] | taus [2][grid] | arrive counter
-    const size_t lists_bytes = (size_t)2 * grid * G1_LC * 8, taus_bytes = snk_round_up((size_t)2 * grid * 4, 16);
+    const size_t lists_bytes = (size_t)2 * grid * G1_LC * 8, taus_bytes = snk_round_up((size_t)4 * grid * 4, 16);   // taus + durs
     const bool timing = getenv("SNK_G1_TIMING") != nullptr;
-    SNK_TRY(snk_buf_reserve(&db->ws_g1, lists_bytes + taus_bytes + 16 + (timing ? 4096 * 128 : 0)));
+    SNK_TRY(snk_buf_reserve(&db->ws_g1, lists_bytes + taus_bytes + 16 + (timing ? 4096 * 128 + (size_t)256 * grid * 8 : 0)));
     p.lists = (unsigned long long *)db->ws_g1.p;
     p.taus = (float *)((char *)db->ws_g1.p + lists_bytes);
+    p.durs = (unsigned *)(p.taus + 2 * grid);
     p.bar = (unsigned *)((char *)db->ws_g1.p + lists_bytes + taus_bytes);
     SNK_CUDA(cudaMemsetAsync(p.bar, 0, 4, st));
     p.dbg_times = timing ? (unsigned long long *)((char *)db->ws_g1.p + lists_bytes + taus_bytes + 16) : nullptr;
+    p.dbg_cta = timing ? p.dbg_times + 4096 * 16 : nullptr;
     p.dberr = db->err_j16; p.maxn = db->maxn_j16;
     p.eps_rel = snk_tc_eps_rel(db, SNK_SPACE_JOINT);
     p.debug_fail_mod = db->debug_fail_mod;
     p.flags = d_flags; p.count = d_count;
     p.dbg_keys = d_keys;
     p.id_offset = id_offset;
+    p.balance = getenv("SNK_G1_NO_BALANCE") ? 0 : 1;
     if (d_Jc_full) {       // database-sharded: the exchange regions of the communicator; this launch owns the next nsteps epochs
         SNK_TRY(snk_comm_p2p_claim(db, (int)meta.nsteps, &p.peers, &p.rank, &p.R, &p.epoch0, &p.xflags_bytes, &p.xslot_bytes));
         SNK_CHECK(p.peers && p.R >= 2 && p.R <= 32, "internal: single-utterance sharded search needs the peer-memory exchange");
@@ -734,12 +810,24 @@ extern "C" int snk_debug_greedy_one_keys(snk_db *db, const double *targets, int6
 
 // Diagnostic (SNK_G1_TIMING=1): CTA 0's timestamps of the last single-utterance launch, [steps][16] nanoseconds (slots 0-5 used):
 // own scan finished, all warps' scans finished, list published, barrier passed, nearest row known, next query ready.
+extern "C" int snk_debug_greedy_one_cta_times(snk_db *db, unsigned long long *out, int steps) {
+    SNK_CHECK(db && out && steps >= 1 && steps <= 256, "bad argument");
+    SNK_LOCK(db);
+    SNK_CUDA(cudaSetDevice(db->device));
+    const int grid = db->sm_count;
+    const size_t off = (size_t)2 * grid * G1_LC * 8 + snk_round_up((size_t)4 * grid * 4, 16) + 16 + (size_t)4096 * 128;
+    SNK_CHECK(db->ws_g1.p && db->ws_g1.cap >= off + (size_t)256 * grid * 8, "no timed launch yet (SNK_G1_TIMING=1)");
+    SNK_CUDA(cudaDeviceSynchronize());
+    SNK_CUDA(cudaMemcpy(out, (char *)db->ws_g1.p + off, (size_t)steps * grid * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" int snk_debug_greedy_one_times(snk_db *db, unsigned long long *out, int steps) {
     SNK_CHECK(db && out && steps >= 1 && steps <= 4096, "bad argument");
     SNK_LOCK(db);
     SNK_CUDA(cudaSetDevice(db->device));
     const int grid = db->sm_count;
-    const size_t off = (size_t)2 * grid * G1_LC * 8 + snk_round_up((size_t)2 * grid * 4, 16) + 16;
+    const size_t off = (size_t)2 * grid * G1_LC * 8 + snk_round_up((size_t)4 * grid * 4, 16) + 16;
     SNK_CHECK(db->ws_g1.p && db->ws_g1.cap >= off + (size_t)steps * 128, "no timed launch yet (SNK_G1_TIMING=1)");
     SNK_CUDA(cudaDeviceSynchronize());
     SNK_CUDA(cudaMemcpy(out, (char *)db->ws_g1.p + off, (size_t)steps * 128, cudaMemcpyDeviceToHost));

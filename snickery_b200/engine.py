@@ -64,6 +64,7 @@ def load_library(path=None):
         "snk_debug_tc_keys": [vp, i32, P(dbl), i64, i64, i64, P(flt), P(flt), P(flt), P(flt)],
         "snk_debug_greedy_one_keys": [vp, P(dbl), i64, P(flt), P(flt), P(flt), P(flt)],
         "snk_debug_greedy_one_times": [vp, vp, i32],
+        "snk_debug_greedy_one_cta_times": [vp, vp, i32],
         "snk_greedy_batch_finish": [vp],
         "snk_comm_unique_id": [vp, i32],
         "snk_comm_init": [vp, vp, i32, i32],
@@ -106,7 +107,7 @@ STD_FLOAT32 = 1
 EXPORTED_SYMBOLS = ["snk_last_error", "snk_version", "snk_device_count", "snk_db_create", "snk_db_destroy",
                     "snk_db_info", "snk_db_set_weights", "snk_db_set_engine", "snk_db_counters", "snk_db_profile_enable",
                     "snk_db_profile_read", "snk_knn",
-                    "snk_knn_dev", "snk_knn_finish", "snk_debug_tc_keys", "snk_debug_greedy_one_keys", "snk_debug_greedy_one_times", "snk_topk_merge_dev", "snk_comm_unique_id", "snk_comm_init",
+                    "snk_knn_dev", "snk_knn_finish", "snk_debug_tc_keys", "snk_debug_greedy_one_keys", "snk_debug_greedy_one_times", "snk_debug_greedy_one_cta_times", "snk_topk_merge_dev", "snk_comm_unique_id", "snk_comm_init",
                     "snk_comm_info", "snk_comm_peer_exchange", "snk_knn_sharded_dev", "snk_knn_sharded_finish", "snk_greedy_batch",
                     "snk_greedy_batch_dev", "snk_greedy_batch_finish", "snk_greedy_sharded_batch_dev",
                     "snk_db_set_standardisation", "snk_prepare_targets", "snk_halfphone_targets",

@@ -77,6 +77,17 @@ for mb in [0.0]:
               mb, np.median(tt[1:, 0] - tt[:-1, 5]) / 1e3, med(1, 0), med(9, 1), med(10, 9), med(2, 10), med(3, 2), med(6, 3),
               med(7, 6), med(8, 7), med(4, 8), med(5, 4), np.median(tt[1:, 5] - tt[:-1, 5]) / 1e3), flush=True)
     assert np.array_equal(d_p.cpu().numpy(), res[(seed, "one")][1])
+# per-CTA scan end times: is the skew the barrier waits for tied to the SM (systematic) or random?
+ct = np.zeros((steps, 148), dtype=np.uint64)
+if lib.snk_debug_greedy_one_cta_times(syn.db._h, ct.ctypes.data, steps) == 0:
+    ct = ct.astype(np.int64)[2:]
+    rel = (ct - np.median(ct, axis=1, keepdims=True)) / 1e3            # us after the median CTA, per step
+    per_cta = rel.mean(axis=0)
+    print("scan-end skew: last CTA %.1f us after the median (mean over steps); per-CTA mean offset std %.2f us, "
+          "per-step residual std %.2f us; slowest CTAs %s" % (
+              (rel.max(axis=1)).mean(), per_cta.std(), (rel - per_cta[None, :]).std(),
+              np.argsort(per_cta)[-6:].tolist()), flush=True)
+    print("per-CTA mean offsets (us):", np.round(per_cta, 1).tolist(), flush=True)
 del os.environ["SNK_G1_TIMING"]
 t0 = time.perf_counter()
 syn.greedy_joint_search(uf)
