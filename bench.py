@@ -709,6 +709,22 @@ def block_halfphone(D, args, headline):
     for _ in range(e2e_reps):
         host_paths, _, _, _ = g.db.acoustic_viterbi_batch_cat(pinned.numpy(), lens, K)
     wall = D.max(time.perf_counter() - t0) / e2e_reps
+    # (b') the reference's own call pattern: one utterance at a time (synth_halfphone.py synth_utt)
+    lens1 = lens[:1].copy()
+
+    def pipeline1():
+        rc = lib.snk_acoustic_viterbi_batch_dev(g.db.handle, C.c_void_p(d_q.data_ptr()), lens1.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                1, K, 0, C.c_void_p(d_paths.data_ptr()), C.c_void_p(d_plen.data_ptr()),
+                                                C.c_void_p(d_cost[0].data_ptr()), C.c_void_p(d_cost[1].data_ptr()),
+                                                C.c_void_p(d_cost[2].data_ptr()), C.c_void_p(stream.cuda_stream))
+        rc = rc or lib.snk_acoustic_viterbi_finish(g.db.handle)
+        if rc:
+            raise RuntimeError(lib.snk_last_error().decode())
+
+    g.db.counters(reset=True)
+    ms_one = D.timed_median(pipeline1, 7, warm=2)
+    launches_one = g.db.counters()["launches"] // 9
+    pipeline()                                   # leave the full batch's paths / costs in place for the parity sample
     frames_all = world * B * T
     knn_flops = 2.0 * B * T * args.hp_units * 184
     knn_tf = knn_flops / (ms_knn / 1e3) / 1e12
@@ -729,6 +745,9 @@ def block_halfphone(D, args, headline):
                          "rerank_launch_ms": pr["ms"] / nlaunch,       # float64 re-rank + certificate of the shortlists
                          "selection_and_conversion_ms": ms_knn - (pk["ms"] + pr["ms"]) / nlaunch,   # bound, shortlist selection, query conversion, gaps
                          "peak_kind": kind},
+        "single_utterance": {"ms": ms_one, "targets": T, "launches": launches_one,
+                             "what": "the same call for ONE utterance of 80 targets (the reference synthesises one at a time), "
+                                     "device-resident, including the host-side finish"},
         "join_viterbi": {"ms": ms_jv, "frames_per_s": world * B * T / (ms_jv / 1e3),
                          "what": "join costs + Viterbi on given candidate lattices (snk_join_viterbi_batch_dev)"},
     }

@@ -674,14 +674,60 @@ __device__ __forceinline__ uint32_t warp_kth(const uint32_t *keys, int n, int K,
     }
     return lo;
 }
+// the same with the keys in registers (n <= 32 PER).  Returns t such that the entries below t, then those equal to t in
+// order, make up the K smallest: the exact order statistic, or mid + 1 of a round that counted exactly K at or below mid.
+template <int PER>
+__device__ __forceinline__ uint32_t warp_kth_exact_regs(const uint32_t *keys, int n, int K, int lane) {
+    uint32_t key[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) key[j] = lane + 32 * j < n ? keys[lane + 32 * j] : 0xffffffffu;
+    uint32_t lo = 0u, hi = 0xffffffffu;
+#pragma unroll 1
+    for (int it = 0; it < 32 && lo < hi; ++it) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) cnt += key[j] <= mid ? 1 : 0;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt == K && mid != 0xffffffffu) return mid + 1u;
+        if (cnt >= K) hi = mid; else lo = mid + 1u;
+    }
+    return lo;
+}
 constexpr int SEL_WARPS = 4;
 constexpr int SEL_CAP = 1024;      // keys staged in shared memory per query; longer rows bisect over global memory
 
-// thr[q] = tau[q] = k-th smallest of row q of vals [nq, ld] (n <= ld values; +inf if fewer than k are finite)
+// An upper bound on the k-th smallest of row q of vals [nq, ld] (n <= ld values; +inf if fewer than k are finite):
+// thr[q] = tau[q] = a value with at least k and at most k + slack of the row's values at or below it.  The bound only has to
+// be the key of SOME count >= k of actual rows (knn search: every order statistic of actual keys bounds the k-th key from
+// above), so the bisection on the key bits stops as soon as the count lands in [k, k + slack] instead of running all 32
+// rounds down to the exact order statistic; the keys sit in registers (PER per lane), one warp per query.
+template <int PER>
+__device__ __forceinline__ uint32_t warp_kth_regs(const float *__restrict__ row, int n, int K, int slack, int lane) {
+    uint32_t key[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) key[j] = lane + 32 * j < n ? key_bits(__ldg(row + lane + 32 * j)) : 0xffffffffu;
+    uint32_t lo = 0u, hi = 0xffffffffu;
+#pragma unroll 1
+    for (int it = 0; it < 32 && lo < hi; ++it) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) cnt += key[j] <= mid ? 1 : 0;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt >= K) {
+            hi = mid;
+            if (cnt <= K + slack) break;
+        } else {
+            lo = mid + 1u;
+        }
+    }
+    return hi;        // count(keys <= hi) >= K always holds for hi
+}
+
 __global__ void __launch_bounds__(SEL_WARPS * 32) kth_of_rows_kernel(const float *__restrict__ vals, int64_t nq, int n,
-                                                                     int64_t ld, int k, float *__restrict__ thr,
+                                                                     int64_t ld, int k, int slack, float *__restrict__ thr,
                                                                      float *__restrict__ tau) {
-    __shared__ uint32_t sk[SEL_WARPS][SEL_CAP];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t q = (int64_t)blockIdx.x * SEL_WARPS + w;
     if (q >= nq) return;
@@ -689,11 +735,11 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) kth_of_rows_kernel(const float
     float out = INFINITY;
     if (n >= k) {
         uint32_t t;
-        if (n <= SEL_CAP) {
-            for (int i = lane; i < n; i += 32) sk[w][i] = key_bits(__ldg(row + i));
-            __syncwarp();
-            t = warp_kth(sk[w], n, k, lane);
-        } else {
+        if (n <= 256) t = warp_kth_regs<8>(row, n, k, slack, lane);
+        else if (n <= 512) t = warp_kth_regs<16>(row, n, k, slack, lane);
+        else if (n <= 768) t = warp_kth_regs<24>(row, n, k, slack, lane);
+        else if (n <= 1024) t = warp_kth_regs<32>(row, n, k, slack, lane);
+        else {
             uint32_t lo = 0u, hi = 0xffffffffu;
 #pragma unroll 1
             for (int it = 0; it < 32; ++it) {
@@ -743,7 +789,13 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_segments_kernel(const f
             for (int i = lane; i < tot; i += 32) { ov[i] = key_value(sk[w][i]); oi[i] = si[w][i]; }
             nout = tot;
         } else {
-            const uint32_t t = warp_kth(sk[w], tot, KP, lane);
+            // the keys go to registers for the bisection (no shared-memory read per round); a round whose count is exactly
+            // KP ends it: everything at or below that value IS the answer
+            uint32_t t;
+            if (tot <= 256) t = warp_kth_exact_regs<8>(sk[w], tot, KP, lane);
+            else if (tot <= 512) t = warp_kth_exact_regs<16>(sk[w], tot, KP, lane);
+            else if (tot <= 768) t = warp_kth_exact_regs<24>(sk[w], tot, KP, lane);
+            else t = warp_kth_exact_regs<32>(sk[w], tot, KP, lane);
             // everything below t, then keys equal to t until KP entries are out
             for (int pass = 0; pass < 2; ++pass) {
                 for (int i0 = 0; i0 < tot && nout < KP; i0 += 32) {
@@ -1242,7 +1294,9 @@ int snk_shortlist_tc(snk_db *db, int space, const __half *dQ16, int ldq16, int64
             // queries in 10^5 (measured; each failure costs a re-search).  SNK_TC_KMARGIN overrides the factor.
             const int margin = getenv("SNK_TC_KMARGIN") ? std::max(1, atoi(getenv("SNK_TC_KMARGIN"))) : 2;
             const int kth = (int)std::min<int64_t>(nmin, (int64_t)k * margin);
-            kth_of_rows_kernel<<<(unsigned)snk_cdiv(nq, SEL_WARPS), SEL_WARPS * 32, 0, st>>>(p.odist, nq, (int)nmin, nmin, kth,
+            // a bound a few ranks above the (2k)-th minimum emits a few rows more and saves a third of the bisection rounds
+            const int slack = getenv("SNK_TC_KSLACK") ? std::max(0, atoi(getenv("SNK_TC_KSLACK"))) : std::max(1, kth / 8);
+            kth_of_rows_kernel<<<(unsigned)snk_cdiv(nq, SEL_WARPS), SEL_WARPS * 32, 0, st>>>(p.odist, nq, (int)nmin, nmin, kth, slack,
                                                                                           (float *)db->ws_misc.p, d_tau);
             SNK_CUDA(cudaGetLastError());
             db->counters[2] += 1;
