@@ -618,7 +618,9 @@ def block_sharded_greedy(D, db, wt, wj, cfg):
             case["paths_hash"] = int(paths[0].sum().item() % 1000003)
         else:               # one utterance: the persistent kernel with the exchange inside it (greedy_one.cu) when peers are mapped
             case["path"] = "one persistent kernel per utterance, exchange through peer memory inside it" \
-                if (world > 1 and sg.knn.db.comm_info()["peer_exchange"]) else "batched path (three launches + exchange per step)"
+                if (world > 1 and sg.knn.db.comm_info()["peer_exchange"]) else \
+                ("one persistent kernel per utterance (one rank: nothing to exchange)" if world == 1 else
+                 "batched path (three launches + exchange per step)")
             keep1 = paths[0][0].cpu().numpy()
         res["cases"].append(case)
         keep = paths[0][:4].cpu().numpy() if B == 1024 else None

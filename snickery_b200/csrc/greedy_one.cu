@@ -749,7 +749,7 @@ int snk_greedy_one_launch(snk_db *db, const void *meta_, const double *d_targets
     p.dbg_keys = d_keys;
     p.id_offset = id_offset;
     p.balance = getenv("SNK_G1_NO_BALANCE") ? 0 : 1;
-    if (d_Jc_full) {       // database-sharded: the exchange regions of the communicator; this launch owns the next nsteps epochs
+    if (d_Jc_full && snk_comm_nranks(db) > 1) {   // database-sharded: the exchange regions of the communicator; this launch owns the next nsteps epochs
         SNK_TRY(snk_comm_p2p_claim(db, (int)meta.nsteps, &p.peers, &p.rank, &p.R, &p.epoch0, &p.xflags_bytes, &p.xslot_bytes));
         SNK_CHECK(p.peers && p.R >= 2 && p.R <= 32, "internal: single-utterance sharded search needs the peer-memory exchange");
     }

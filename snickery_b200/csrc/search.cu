@@ -361,7 +361,7 @@ int greedy_run(snk_db *db, const std::vector<greedy_meta> &meta, const double *d
                int64_t *d_paths, double *d_step_dist, int *d_flags, int *d_count, cudaStream_t st,
                const greedy_shard *sh = nullptr) {
     const int B = (int)meta.size();
-    if (B == 1 && snk_greedy_one_supported(db) && (!sh || snk_comm_has_p2p(db))) {
+    if (B == 1 && snk_greedy_one_supported(db) && (!sh || snk_comm_has_p2p(db) || snk_comm_nranks(db) == 1)) {
         // one utterance: the whole chain is one persistent kernel (greedy_one.cu), over a sharded database with the per-step
         // exchange through peer memory inside it; all its frames must have landed
         for (auto &w : db->step_waits) SNK_CUDA(cudaStreamWaitEvent(st, w.second, 0));
