@@ -118,7 +118,7 @@ int snk_db_create(snk_db **out, int device_id, int64_t N, int Dt, int Dj, int mu
         SNK_CHECK(Dj % 2 == 0, "halfphone-epoch layout needs an even join dimension");
         db->Djq = Dj / 2; db->prev_row_off = 0; db->prev_col = 0; db->cur_row_off = multiepoch - 1; db->cur_col = Dj / 2;
     }
-    db->ldJ32 = (int)snk_round_up(Dj, 4);
+    db->ldJ32 = (int)snk_round_up(Dj, 32);   // rows start on 128-byte lines: a 32-dim group of four rows is four lines, not seven (join_tc.cu)
     db->ldG16 = (int)snk_round_up(Dt, 64);
     db->ldS16 = (int)snk_round_up(db->Djq, 64);
 #define ALLOC(ptr, bytes)                                                                      \

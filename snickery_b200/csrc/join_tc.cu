@@ -171,9 +171,12 @@ __global__ void __launch_bounds__(JT_THREADS, JT_CTAS_PER_SM) join_tile_tc_kerne
     const int c = 16 * warp + (lane & 15), h = lane >> 4;
     const int a_lo = h ? min(HA, K) : 0, a_hi = h ? K : min(HA, K);
     // conversion role: float4 j of a 32-dim group, rows rq + 16 i of the A (i < 4) and the B operand.  A warp's four rows
-    // are {0, 1, 4, 5} + 2 (w & 1) + 8 (w >> 1): their swizzled chunks cover all 32 banks between them.
+    // are {0, 1, 4, 5} + 2 (w & 1) + 8 (w >> 1), and each HALF warp holds two rows that differ in bit 2 ({0, 4} and {1, 5}):
+    // an 8-byte store is served per half warp, and under the 128-byte swizzle rows r and r ^ 4 put their hi (and their lo)
+    // halves into different halves of the banks -- two wavefronts per store instead of four (ncu: the stores were at twice
+    // their ideal wavefront count, and the kernel at 74 % of the L1 wavefront peak).
     const int j = lane & 7;
-    const int rq = ((lane >> 3) & 1) + 4 * (lane >> 4) + 2 * (warp & 1) + 8 * (warp >> 1);
+    const int rq = 4 * ((lane >> 3) & 1) + (lane >> 4) + 2 * (warp & 1) + 8 * (warp >> 1);
     // 16-byte chunk ch of operand row r sits at chunk ch ^ (r & 7) (SWIZZLE_128B); r & 7 = rq & 7 for all four rows
     uint32_t st_base = sbase + rq * 128 + ((((uint32_t)(j >> 1)) ^ (uint32_t)(rq & 7)) << 4) + ((j & 1) << 3);
     st_base = __shfl_sync(0xffffffffu, st_base, lane);   // identity; ptxas otherwise recomputes the address from the thread id at all eight stores of a group
