@@ -152,6 +152,12 @@ def test_config2_full_size_vs_ckdtree():
             mism += assert_greedy_path_ok(o, u, p, d)
     assert mism <= 2
     assert g.db.counters()["recertified"] == 0
+    # the reference's literal call, one utterance: the persistent single-utterance kernel (greedy_one.cu) at full size --
+    # the same path and bit-identical distances as the batched tensor-core path just checked against cKDTree
+    g.db.counters(reset=True)
+    p1, d1 = g.greedy_joint_search_batch(utts[:1], return_dists=True)
+    assert g.db.counters()["launches"] <= 3 and g.db.counters()["recertified"] == 0
+    assert p1[0] == paths[0] and np.array_equal(np.asarray(d1[0]), np.asarray(dists[0]))
 
 
 def test_config3_full_size_vs_reference_engines():
