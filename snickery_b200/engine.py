@@ -329,9 +329,11 @@ class UnitDatabase:
                                                     _ptr(dur, C.c_double), _ptr(out, C.c_double)))
         return out
 
-    def greedy_batch_cat(self, cat, lens, start_states=None, return_dists=False, unnorm=False):
+    def greedy_batch_cat(self, cat, lens, start_states=None, return_dists=False, unnorm=False, as_arrays=False):
         """Batch given as one concatenated array [sum T_b, Dt] (may be pinned) + lengths: weighted float64
-        unit features, or (unnorm=True) un-normalised float32 speech that the device standardises and weights."""
+        unit features, or (unnorm=True) un-normalised float32 speech that the device standardises and weights.
+        Returns one list of unit ids per utterance, as the reference does -- or, with as_arrays, one int64 array per
+        utterance (views of one buffer): boxing 10^5 ids into Python ints costs several milliseconds per batch."""
         m = self.multiepoch
         lens = np.ascontiguousarray(lens, dtype=np.int64)
         B = lens.size
@@ -353,7 +355,7 @@ class UnitDatabase:
         _check(fn(self._h, _ptr(cat, ct), _ptr(lens, C.c_int64), B, _ptr(ss, C.c_int64), _ptr(paths, C.c_int64),
                   _ptr(dists, C.c_double)))
         cuts = np.cumsum(steps)[:-1]
-        p = [x.tolist() for x in np.split(paths, cuts)]
+        p = np.split(paths, cuts) if as_arrays else [x.tolist() for x in np.split(paths, cuts)]
         if return_dists:
             return p, np.split(dists, cuts)
         return p
