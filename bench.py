@@ -706,12 +706,12 @@ def block_halfphone(D, args, headline):
     pv = g.db.profile_read(engine.PROF_VITERBI)
     g.db.profile_enable(False)
     # (b) host buffers
-    g.db.acoustic_viterbi_batch_cat(pinned.numpy(), lens, K)
+    g.db.acoustic_viterbi_batch_cat(pinned.numpy(), lens, K, as_arrays=True)
     D.barrier()
     t0 = time.perf_counter()
     e2e_reps = 2
     for _ in range(e2e_reps):
-        host_paths, _, _, _ = g.db.acoustic_viterbi_batch_cat(pinned.numpy(), lens, K)
+        host_paths, _, _, _ = g.db.acoustic_viterbi_batch_cat(pinned.numpy(), lens, K, as_arrays=True)
     wall = D.max(time.perf_counter() - t0) / e2e_reps
     # (b') the reference's own call pattern: one utterance at a time (synth_halfphone.py synth_utt)
     lens1 = lens[:1].copy()
@@ -773,9 +773,9 @@ def block_halfphone(D, args, headline):
             ufb = uf[b * T:(b + 1) * T]
             rc, rd = o.preselect_units_acoustic(ufb)
             ref_path, ref_cost = O.viterbi_search_numpy(o, rc, rd, return_cost=True)
-            if host_paths[b] != ref_path:
+            if host_paths[b].tolist() != ref_path:
                 mism += 1
-                _, _, tot = o.path_costs(rc, rd, host_paths[b])
+                _, _, tot = o.path_costs(rc, rd, host_paths[b].tolist())
                 outside += int(abs(tot - ref_cost) > 1e-6 * ref_cost)
             max_rel = max(max_rel, abs(costs[b] - ref_cost) / ref_cost)
         halfphone["parity"] = {"what": "2 utterances x 80 targets: CUDA pipeline vs oracle (cKDTree k=50 + numpy join + DP)",

@@ -416,13 +416,15 @@ class UnitDatabase:
                                                      _ptr(tcost, C.c_double), _ptr(jcost, C.c_double)))
         out, off = [], 0
         for b in range(B):
-            out.append(paths[off:off + plen[b]].tolist() if plen[b] > 0 else [])
+            seg = paths[off:off + max(int(plen[b]), 0)]
+            out.append(seg if as_arrays else seg.tolist())
             off += lens[b]
         return out, pcost, tcost, jcost
 
-    def acoustic_viterbi_batch_cat(self, cat, lens, K, flags=0):
+    def acoustic_viterbi_batch_cat(self, cat, lens, K, flags=0, as_arrays=False):
         """preselect_units_acoustic + viterbi_search for a batch given as one concatenated float64 array [sum T_b, Dt]
-        (may be pinned) + lengths; the candidate lists stay on the device."""
+        (may be pinned) + lengths; the candidate lists stay on the device.  Paths come back as lists of unit ids (the
+        reference's form) or, with as_arrays, as int64 array views (no per-id boxing)."""
         lens = np.ascontiguousarray(lens, dtype=np.int64)
         B = lens.size
         cat = np.ascontiguousarray(cat, dtype=np.float64)
@@ -437,7 +439,8 @@ class UnitDatabase:
                                                          _ptr(jcost, C.c_double)))
         out, off = [], 0
         for b in range(B):
-            out.append(paths[off:off + plen[b]].tolist() if plen[b] > 0 else [])
+            seg = paths[off:off + max(int(plen[b]), 0)]
+            out.append(seg if as_arrays else seg.tolist())
             off += lens[b]
         return out, pcost, tcost, jcost
 
