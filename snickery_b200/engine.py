@@ -397,7 +397,7 @@ class UnitDatabase:
         _check(load_library().snk_join_stats(self._h, _ptr(out, C.c_int64)))
         return int(out[0]), int(out[1])
 
-    def join_viterbi_batch(self, cand_list, dist_list, flags=0):
+    def join_viterbi_batch(self, cand_list, dist_list, flags=0, as_arrays=False):
         B = len(cand_list)
         if B == 0:
             return [], np.zeros(0), np.zeros(0), np.zeros(0)
