@@ -241,6 +241,34 @@ class Hdf5File:
             return np.dtype("%sf%d" % (order, size))
         if cls == 3:
             return np.dtype("S%d" % size)
+        if cls == 6:
+            n = buf[p + 1] | (buf[p + 2] << 8)
+            q = p + 8
+            names, formats, offsets = [], [], []
+            for _ in range(n):
+                end = q
+                while buf[end] != 0:
+                    end += 1
+                names.append(bytes(buf[q:end]).decode("ascii"))
+                if ver < 3:
+                    q += (end - q + 8) // 8 * 8            # name + NUL padded to a multiple of eight
+                    offsets.append(self._u(q, 4))
+                    q += 4
+                    if ver == 1:
+                        if buf[q] != 0:
+                            raise Hdf5FormatError("array members of a compound are not supported")
+                        q += 28                            # dimensionality, reserved, permutation, reserved, 4 sizes
+                else:
+                    q = end + 1
+                    w = 1 if size < (1 << 8) else 2 if size < (1 << 16) else 4 if size < (1 << 32) else 8
+                    offsets.append(self._u(q, w))
+                    q += w
+                sub = self._parse_dtype(q)
+                if sub.names:
+                    raise Hdf5FormatError("nested compounds are not supported")
+                formats.append(sub)
+                q += 8 + {"i": 4, "u": 4, "f": 12, "S": 0}[sub.kind]
+            return np.dtype({"names": names, "formats": formats, "offsets": offsets, "itemsize": size})
         raise Hdf5FormatError("datatype class %d (version %d) is not supported" % (cls, ver))
 
     # ---- data
@@ -359,7 +387,8 @@ _UNDEF = (1 << 64) - 1
 _LEAF_K, _INTERNAL_K, _CHUNK_K = 16, 16, 32
 
 
-def _dtype_message(dt):
+def _atomic_dtype_message(dt):
+    """Datatype message of an atomic type: 8-byte header + properties, nothing after them (what a compound member embeds)."""
     dt = np.dtype(dt)
     if dt.kind == "f" and dt.itemsize in (4, 8):
         exp_bits, mant_bits, bias = (8, 23, 127) if dt.itemsize == 4 else (11, 52, 1023)
@@ -367,10 +396,28 @@ def _dtype_message(dt):
         return head + struct.pack("<HHBBBBI", 0, 8 * dt.itemsize, mant_bits, exp_bits, 0, mant_bits, bias)
     if dt.kind in "iu":
         head = struct.pack("<BBBBI", 0x10, 0x08 if dt.kind == "i" else 0, 0, 0, dt.itemsize)
-        return head + struct.pack("<HH", 0, 8 * dt.itemsize) + b"\0" * 4
+        return head + struct.pack("<HH", 0, 8 * dt.itemsize)
     if dt.kind == "S":
         return struct.pack("<BBBBI", 0x13, 0x01, 0, 0, dt.itemsize)
     raise Hdf5FormatError("cannot write dtype %s" % dt)
+
+
+def _dtype_message(dt):
+    """Datatype message (type 0x03).  Structured dtypes become a version-1 compound (the form libhdf5 writes by default,
+    e.g. for sklearn's KDTree node array in a StashableKDTree stash): per member the name padded to 8 bytes, byte offset,
+    a scalar dimensionality block and the member's own atomic datatype message."""
+    dt = np.dtype(dt)
+    if dt.names:
+        body = struct.pack("<BBBBI", 0x16, len(dt.names) & 0xff, len(dt.names) >> 8, 0, dt.itemsize)
+        for name in dt.names:
+            sub, off = dt.fields[name][0], dt.fields[name][1]
+            if sub.names or sub.shape:
+                raise Hdf5FormatError("nested / array members are not supported (%s)" % name)
+            nm = name.encode("ascii") + b"\0"
+            nm += b"\0" * (-len(nm) % 8)
+            body += nm + struct.pack("<IB3xI4x4I", off, 0, 0, 0, 0, 0, 0) + _atomic_dtype_message(sub)
+        return body
+    return _atomic_dtype_message(dt)
 
 
 def _message(mtype, body):

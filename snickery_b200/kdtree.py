@@ -102,6 +102,7 @@ class GpuStashableKDTree(GpuKDTree):
     def __init__(self, data, leaf_size=40, metric="euclidean", device=0, **kwargs):
         if metric not in ("euclidean", "minkowski", "l2"):
             raise NotImplementedError("StashableKDTree is Euclidean only (StashableKDTree.py:86)")
+        self.leaf_size = int(leaf_size)
         super().__init__(data, device=device)
 
     def query(self, X, k=1, return_distance=True, dualtree=False, breadth_first=False, sort_results=True):
@@ -112,17 +113,15 @@ class GpuStashableKDTree(GpuKDTree):
         return (d, i) if return_distance else i
 
     # ---- persistence (StashableKDTree.py:43-83)
-    def save_hdf(self, fname):
-        """Stash the tree in the reference's HDF5 layout: ``state_0`` holds the data matrix, ``int_values`` the
-        seven integers of sklearn's state.  There is no tree to store, so ``state_1..3`` (sklearn's index /
-        node arrays) are written empty: the file round-trips through this class, not through sklearn."""
-        from .hdf5_voice import save_voice
+    def save_hdf(self, fname, interoperable=None):
+        """Stash the tree in the reference's HDF5 layout (StashableKDTree.py:43-54): ``state_0..3`` = the arrays of
+        sklearn's ``KDTree.__getstate__()`` (data, index array, node array, node bounds), ``int_values`` = its seven
+        integers.  This engine has no tree, so for a stash the reference's own ``resurrect_tree`` can load the node arrays
+        are built with scikit-learn on the host (``interoperable=True``; the default when scikit-learn is importable);
+        without it ``state_1..3`` are written empty and the file round-trips through this class only."""
         if self.data is None:
             raise ValueError("this tree is a view over a resident database and holds no data matrix of its own")
-        data = np.ascontiguousarray(self.data, dtype=np.float64)
-        ints = np.array([40, 0, 0, 0, 0, 0, 0], dtype=np.int64)       # leaf_size, n_levels, n_nodes, n_trims, ...
-        save_voice(fname, {"state_0": data, "state_1": np.zeros((0,), np.int64), "state_2": np.zeros((0,), np.float64),
-                           "state_3": np.zeros((0,), np.float64), "int_values": ints}, chunked=())
+        write_stash(fname, np.ascontiguousarray(self.data, dtype=np.float64), self.leaf_size, interoperable)
 
     @classmethod
     def load_hdf(cls, fname, device=0):
@@ -133,6 +132,29 @@ class GpuStashableKDTree(GpuKDTree):
         if "state_0" not in f:
             raise ValueError("%s is not a StashableKDTree stash (no state_0)" % fname)
         return cls(f["state_0"], device=device)
+
+
+def write_stash(fname, data, leaf_size=40, interoperable=None):
+    """The HDF5 stash of StashableKDTree.save_hdf (StashableKDTree.py:43-54) for a data matrix.  interoperable: build
+    sklearn's tree arrays so that the reference's sklearn-backed class can ``load_hdf`` the file (None: if scikit-learn is
+    importable)."""
+    from .hdf5_voice import save_voice
+    state = None
+    if interoperable is None or interoperable:
+        try:
+            from sklearn.neighbors import KDTree
+            state = KDTree(data, leaf_size=int(leaf_size), metric="euclidean").__getstate__()
+        except ImportError:
+            if interoperable:
+                raise
+    if state is not None:
+        arrays = {"state_%d" % i: np.ascontiguousarray(state[i]) for i in range(4)}
+        arrays["int_values"] = np.asarray(state[4:11], dtype=np.int64)     # leaf_size, n_levels, n_nodes, n_trims, n_leaves, n_splits, n_calls
+    else:
+        arrays = {"state_0": data, "state_1": np.zeros((0,), np.int64), "state_2": np.zeros((0,), np.float64),
+                  "state_3": np.zeros((0,), np.float64),
+                  "int_values": np.array([int(leaf_size), 0, 0, 0, 0, 0, 0], dtype=np.int64)}
+    save_voice(fname, arrays, chunked=())
 
 
 def resurrect_tree(fname, device=0):

@@ -91,15 +91,16 @@ def test_errors(tmp_path):
 
 
 def test_stash_with_unsupported_member(tmp_path, monkeypatch):
-    """A StashableKDTree stash written by the reference holds sklearn's node array as a compound dataset; the
-    reader must still open the file and serve state_0 (all the GPU tree needs), failing only on access."""
+    """A file may hold datasets of a type this reader does not know (here: a variable-length type); it must still open
+    and serve the others, failing only on access.  (Compound types -- sklearn's node array in a StashableKDTree stash --
+    are read: test_stash_written_for_the_reference_is_a_valid_sklearn_state.)"""
     import struct
     from snickery_b200 import hdf5_voice
     real = hdf5_voice._dtype_message
 
-    def fake(dt):   # float32 members get a compound (class 6) datatype message
+    def fake(dt):   # float32 members get a variable-length (class 9) datatype message
         if np.dtype(dt) == np.float32:
-            return struct.pack("<BBBBI", 0x16, 1, 0, 0, 4)
+            return struct.pack("<BBBBI", 0x19, 0, 0, 0, 4)
         return real(dt)
     monkeypatch.setattr(hdf5_voice, "_dtype_message", fake)
     data = np.random.default_rng(3).normal(size=(40, 7))
@@ -107,7 +108,7 @@ def test_stash_with_unsupported_member(tmp_path, monkeypatch):
     save_voice(path, {"state_0": data, "state_2": np.zeros(9, np.float32), "int_values": np.arange(7)}, chunked=())
     f = Hdf5File(path)
     assert np.array_equal(f["state_0"], data) and np.array_equal(f["int_values"], np.arange(7))
-    with pytest.raises(Hdf5FormatError, match="datatype class 6"):
+    with pytest.raises(Hdf5FormatError, match="datatype class 9"):
         f["state_2"]
 
 
@@ -147,3 +148,37 @@ def test_round_trip_fuzz(tmp_path):
         for k, a in arrays.items():
             b = f[k]
             assert b.shape == a.shape and b.dtype == a.dtype and np.array_equal(b, a), (trial, k, a.shape, a.dtype, kw)
+
+
+def test_stash_written_for_the_reference_is_a_valid_sklearn_state(tmp_path):
+    """StashableKDTree.save_hdf / load_hdf (reference script/StashableKDTree.py:43-83): state_0..3 are the arrays of sklearn's
+    KDTree.__getstate__(), int_values its seven integers.  The stash this package writes must carry exactly those (the node
+    array is a compound HDF5 type), so that the reference's sklearn-backed resurrect_tree can __setstate__ it: rebuild a
+    sklearn KDTree from the file's arrays and query it."""
+    sklearn_neighbors = pytest.importorskip("sklearn.neighbors")
+    from snickery_b200.kdtree import write_stash
+    rng = np.random.default_rng(7)
+    X = rng.standard_normal((700, 9))
+    fn = str(tmp_path / "stash.hdf5")
+    write_stash(fn, X, leaf_size=25, interoperable=True)
+    f = Hdf5File(fn)
+    ref_tree = sklearn_neighbors.KDTree(X, leaf_size=25, metric="euclidean")
+    ref = ref_tree.__getstate__()
+    loaded = [f["state_%d" % i] for i in range(4)]
+    assert loaded[2].dtype.names == ("idx_start", "idx_end", "is_leaf", "radius")
+    for i in range(4):
+        assert loaded[i].dtype == ref[i].dtype and loaded[i].shape == ref[i].shape
+        assert loaded[i].tobytes() == np.ascontiguousarray(ref[i]).tobytes()
+    ints = [int(v) for v in f["int_values"]]
+    assert ints == [int(v) for v in ref[4:11]] and ints[0] == 25
+    # what load_hdf does (StashableKDTree.py:56-80), with the metric object(s) sklearn's own state carries
+    tree = sklearn_neighbors.KDTree.__new__(sklearn_neighbors.KDTree)
+    tree.__setstate__(tuple(loaded + ints + list(ref[11:])))
+    q = rng.standard_normal((30, 9))
+    d1, i1 = tree.query(q, k=6)
+    d2, i2 = ref_tree.query(q, k=6)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    # without scikit-learn's arrays the file still round-trips through this package (state_0 is all it needs)
+    fn2 = str(tmp_path / "plain.hdf5")
+    write_stash(fn2, X, interoperable=False)
+    assert np.array_equal(Hdf5File(fn2)["state_0"], X) and Hdf5File(fn2)["state_1"].size == 0
