@@ -78,8 +78,10 @@ for mb in [0.0]:
               med(7, 6), med(8, 7), med(4, 8), med(5, 4), np.median(tt[1:, 5] - tt[:-1, 5]) / 1e3), flush=True)
     assert np.array_equal(d_p.cpu().numpy(), res[(seed, "one")][1])
 # per-CTA scan end times: is the skew the barrier waits for tied to the SM (systematic) or random?
-ct = np.zeros((steps, 148), dtype=np.uint64)
-if lib.snk_debug_greedy_one_cta_times(syn.db._h, ct.ctypes.data, steps) == 0:
+n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+ct = np.zeros((min(steps, 256), n_sm), dtype=np.uint64)
+lib.snk_debug_greedy_one_cta_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+if lib.snk_debug_greedy_one_cta_times(syn.db._h, ct.ctypes.data, min(steps, 256)) == 0:
     ct = ct.astype(np.int64)[2:]
     rel = (ct - np.median(ct, axis=1, keepdims=True)) / 1e3            # us after the median CTA, per step
     per_cta = rel.mean(axis=0)
