@@ -691,6 +691,13 @@ def block_halfphone(D, args, headline):
                                     d_cost[0].data_ptr(), d_cost[1].data_ptr(), d_cost[2].data_ptr(), stream=stream.cuda_stream)
 
     reps = max(2, min(args.steps, 5))
+    if headline:
+        # this block is the first GPU work of the process when it is the headline: a fresh process starts at idle clocks and
+        # the first tens of milliseconds run slow (measured: 7.4 ms vs 12-21 ms for the same call) -- bring the clocks up first
+        t_heat = time.perf_counter()
+        while time.perf_counter() - t_heat < 0.5:
+            knn_only()
+        torch.cuda.synchronize()
     g.db.counters(reset=True)
     # as the headline (--workload halfphone) the contract's timing: K calls between one pair of events; as a block of the
     # default run the median of five calls (each ends in a host-side wait, one slow host iteration should not be averaged in)
