@@ -677,9 +677,13 @@ typedef void (*g1_fn)(const g1_params);
 g1_fn g1_pick(int m) {
     switch (m) {
     case 1: return greedy_one_kernel<1, 5, 2>;
+    case 2: return greedy_one_kernel<2, 5, 2>;
     case 3: return greedy_one_kernel<3, 5, 2>;
     case 4: return greedy_one_kernel<4, 5, 2>;
+    case 5: return greedy_one_kernel<5, 5, 2>;
     case 6: return greedy_one_kernel<6, 5, 2>;
+    case 7: return greedy_one_kernel<7, 5, 2>;     // the window's frames ride in the eight N columns of the mma (m <= 8); the
+                                                   // query operand layout it shares with knn_tc.cu holds ten K-blocks (m <= 7)
     default: return nullptr;
     }
 }
@@ -687,7 +691,7 @@ g1_fn g1_pick(int m) {
 }  // namespace
 
 // shapes the kernel is instantiated for: the shipped epoch voices (151-dim join contexts, 61-dim frames) whose operand rows
-// carry their norms, multiepoch 1 / 3 / 4 / 6
+// carry their norms, multiepoch 1 - 7
 bool snk_greedy_one_supported(const snk_db *db) {
     if (getenv("SNK_GREEDY_NO_ONE")) return false;
     if (!db->tc_ok || !db->tc_state || db->engine == SNK_ENGINE_SIMT || db->engine == SNK_ENGINE_EXACT) return false;
@@ -696,6 +700,7 @@ bool snk_greedy_one_supported(const snk_db *db) {
     if (db->Np < 1 || db->Np >= (int64_t)INT_MAX - 64) return false;
     g1_fn fn = g1_pick(db->m);
     if (!fn) return false;
+    if (!snk_tc_supported(db, snk_make_space(db, SNK_SPACE_JOINT), G1_KP)) return false;   // the operand layout / query map it reads
     if (db->g1_resident == 0) {
         // once per handle: one CTA per SM must be resident at the same time (cooperative launch), and the device must allow it
         const snk_space sp = snk_make_space(db, SNK_SPACE_JOINT);

@@ -28,7 +28,7 @@ def _launches(g, fn):
     return out, g.db.counters()["launches"]
 
 
-@pytest.mark.parametrize("m", [1, 3, 4, 6])
+@pytest.mark.parametrize("m", [1, 2, 3, 4, 5, 6, 7])
 def test_one_kernel_equals_batched_path_and_oracle(m, monkeypatch):
     db, o, g = _pair(m)
     steps = 24
