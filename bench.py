@@ -577,6 +577,11 @@ def block_single_utterance(D, syn, db, wt):
             "steps": steps, "us_per_step": ms * 1e3 / steps, "hbm_floor_us_per_step": floor_us,
             "frac_of_hbm_floor": floor_us / (ms * 1e3 / steps), "algorithmic_bytes_per_step": nprime * row_bytes,
             "achieved_gbs": nprime * row_bytes / (ms * 1e-3 / steps) / 1e9, "peak_kind": kind,
+            "roofline": {"bound": "hbm", "kernel": "greedy_one_kernel (one launch = the whole utterance)",
+                         "achieved": nprime * row_bytes / (ms * 1e-3 / steps) / 1e9, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
+                         "frac": floor_us / (ms * 1e3 / steps), "traffic": ncu_traffic("greedy_one_kernel_bytes_per_step"),
+                         "traffic_source": "ncu --set full capture committed under profiles/ (dram bytes per step)",
+                         "algorithmic_bytes": nprime * row_bytes},
             "kernel_launches_per_utterance": launches // 7,
             "batched_path_us_per_step": ms_batched * 1e3 / steps, "same_path_as_batched": same,
             "host_call_ms": host_ms, "host_call_frames_per_s": UTT_FRAMES / (host_ms / 1e3)}
