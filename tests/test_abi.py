@@ -99,3 +99,39 @@ def test_dev_entry_points_do_not_synchronise():
         assert hit is None or name in ("snk_upload_async", "snk_buf_reserve", "take_flags"), "%s reaches %s" % (name, hit.group(0))
         todo += [c for c in set(re.findall(r"\b(\w+)\s*\(", body)) if c in bodies]
     assert len(seen) > 25
+
+
+def _build_c_host(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "c_host")
+    libdir = os.path.dirname(engine.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_host.c"), "-L", libdir, "-lsnk_b200", "-Wl,-rpath," + libdir,
+                           "-lm", "-o", exe])
+    return exe
+
+
+def test_header_is_c_and_a_c_host_links(tmp_path):
+    """The boundary is a C ABI: include/snk_b200.h must compile as C99 and a plain C program (examples/c_host.c) must link
+    against the library with nothing but -lsnk_b200.  Without a GPU it reports that and exits 2 (no compute, no fallback)."""
+    import subprocess
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                           os.path.join(ROOT, "include", "snk_b200.h")])
+    exe = _build_c_host(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode in (0, 2), (r.returncode, r.stdout, r.stderr)
+    if r.returncode == 2:
+        assert "no CUDA device" in r.stderr or "snk_db_create" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_host_recovers_the_identity_path(tmp_path):
+    """The same C program on a B200: database frames in, consecutive units out at distance 0 (the reference's own
+    assertion, synth_simple.py:909-928), through snk_db_create / snk_db_set_weights / snk_greedy_batch from C."""
+    import subprocess
+    r = subprocess.run([_build_c_host(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[-500:], r.stderr[-500:])
+    assert "identity path recovered" in r.stdout
