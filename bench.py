@@ -761,6 +761,9 @@ def block_halfphone(D, args, headline):
                          "achieved": knn_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": knn_tf / tpeak,
                          "flops": knn_flops, "ms": ms_knn, "gemm_launch_ms": pk["ms"] / nlaunch,
                          "gemm_launches_per_search": pk["launches"] / nlaunch,
+                         # the contraction alone (sampling pass over every 4th tile + emit pass over all of them), 184-dim shape
+                         "gemm_only_tflops": pk["work"] / nlaunch / (pk["ms"] / nlaunch / 1e3) / 1e12 if pk["ms"] else None,
+                         "gemm_only_frac_of_peak": (pk["work"] / nlaunch / (pk["ms"] / nlaunch / 1e3) / 1e12 / tpeak) if pk["ms"] else None,
                          "rerank_launch_ms": pr["ms"] / nlaunch,       # float64 re-rank + certificate of the shortlists
                          "selection_and_conversion_ms": ms_knn - (pk["ms"] + pr["ms"]) / nlaunch,   # bound, shortlist selection, query conversion, gaps
                          "peak_kind": kind},
