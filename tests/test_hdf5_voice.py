@@ -182,3 +182,41 @@ def test_stash_written_for_the_reference_is_a_valid_sklearn_state(tmp_path):
     fn2 = str(tmp_path / "plain.hdf5")
     write_stash(fn2, X, interoperable=False)
     assert np.array_equal(Hdf5File(fn2)["state_0"], X) and Hdf5File(fn2)["state_1"].size == 0
+
+
+@pytest.mark.parametrize("version", [1, 2, 3])
+def test_compound_datatype_versions_are_read(tmp_path, monkeypatch, version):
+    """libhdf5 writes compound datatype messages in three encodings (version 1: padded names + a dimensionality block,
+    version 2: padded names, version 3: unpadded names and an offset as wide as the element size needs).  The writer here
+    emits version 1; the reader must take all three (a stash written with libver='latest' carries version 3)."""
+    import struct
+    from snickery_b200 import hdf5_voice
+    real = hdf5_voice._dtype_message
+    dt = np.dtype([("idx_start", "<i8"), ("idx_end", "<i8"), ("is_leaf", "<i8"), ("radius", "<f8")])
+
+    def encode(d):
+        d = np.dtype(d)
+        if not d.names or version == 1:
+            return real(d)
+        body = struct.pack("<BBBBI", 0x06 | (version << 4), len(d.names), 0, 0, d.itemsize)
+        for name in d.names:
+            sub, off = d.fields[name][0], d.fields[name][1]
+            nm = name.encode("ascii") + b"\0"
+            if version == 2:
+                nm += b"\0" * (-len(nm) % 8)
+                body += nm + struct.pack("<I", off)
+            else:
+                body += nm + struct.pack("<B", off)              # element size 32 < 256: one byte
+            body += hdf5_voice._atomic_dtype_message(sub)
+        return body
+    monkeypatch.setattr(hdf5_voice, "_dtype_message", encode)
+    rng = np.random.default_rng(version)
+    a = np.zeros(37, dtype=dt)
+    a["idx_start"], a["idx_end"] = rng.integers(0, 1000, 37), rng.integers(0, 1000, 37)
+    a["is_leaf"], a["radius"] = rng.integers(0, 2, 37), rng.random(37)
+    path = str(tmp_path / "c.hdf5")
+    save_voice(path, {"state_2": a, "other": np.arange(5.0)}, chunked=())
+    f = Hdf5File(path)
+    b = f["state_2"]
+    assert b.dtype == dt and b.tobytes() == a.tobytes()
+    assert np.array_equal(f["other"], np.arange(5.0))
